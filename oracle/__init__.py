@@ -1,0 +1,347 @@
+"""CPU oracle for the weight-only matmul hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this package.  It wraps
+
+* ``oracle/liboracle.so``   -- our plain-C restatement (oracle_ggml.c, oracle_btla.c), and
+* ``oracle/_ref/*.so``      -- the reference's own sources compiled in place (ref_ggml.c, ref_btla.cpp),
+  present when built in a container that has ``/root/reference`` (the built .so travels to the GPU box).
+
+Parity status: PINNED (tests/test_oracle_vs_ref.py + tests/golden/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+Q4_0_BLOCK_BYTES = 18
+Q8_0_BLOCK_BYTES = 34
+BTLA_S4_CLIP = 4 | (1 << 8)
+BTLA_S8 = 8 | (1 << 8)
+BTLA_F32 = 32
+BTLA_BF16 = 16 | (1 << 16)
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so and (when /root/reference exists) oracle/_ref/."""
+    need = force or not os.path.exists(os.path.join(_HERE, "liboracle.so"))
+    if os.path.isdir("/root/reference/neural_speed") and not os.path.exists(os.path.join(_HERE, "_ref", "libref_btla.so")):
+        need = True
+    if need:
+        subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
+
+
+_lib = None
+_ref_ggml = None
+_ref_btla = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(os.path.join(_HERE, "liboracle.so"))
+        L.orc_fp16_to_fp32.restype = C.c_float
+        L.orc_fp16_to_fp32.argtypes = [C.c_uint16]
+        L.orc_fp32_to_fp16.restype = C.c_uint16
+        L.orc_fp32_to_fp16.argtypes = [C.c_float]
+        L.orc_f32_to_bf16.restype = C.c_uint16
+        L.orc_f32_to_bf16.argtypes = [C.c_float]
+        L.orc_bf16_to_f32.restype = C.c_float
+        L.orc_bf16_to_f32.argtypes = [C.c_uint16]
+        L.orc_nf4_unpack.restype = C.c_float
+        L.orc_nf4_unpack.argtypes = [C.c_int]
+        L.orc_nf4_quantize.restype = C.c_int
+        L.orc_nf4_quantize.argtypes = [C.c_float]
+        L.orc_silu.restype = C.c_float
+        L.orc_silu.argtypes = [C.c_float]
+        for n, r in (("orc_cast_f32_s8", C.c_int8), ("orc_cast_f32_u8", C.c_uint8), ("orc_cast_f32_s32", C.c_int)):
+            getattr(L, n).restype = r
+            getattr(L, n).argtypes = [C.c_float]
+        _lib = L
+    return _lib
+
+
+def ref_ggml():
+    """The reference's own ggml Q4_0/Q8_0 code (oracle/_ref/libref_ggml.so) or None."""
+    global _ref_ggml
+    if _ref_ggml is None:
+        p = os.path.join(_HERE, "_ref", "libref_ggml.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if not os.path.exists(p):
+            return None
+        L = C.CDLL(p)
+        L.ref_ggml_init()
+        L.ref_fp16_to_fp32.restype = C.c_float
+        L.ref_fp16_to_fp32.argtypes = [C.c_uint16]
+        L.ref_fp32_to_fp16.restype = C.c_uint16
+        L.ref_fp32_to_fp16.argtypes = [C.c_float]
+        _ref_ggml = L
+    return _ref_ggml
+
+
+def ref_btla():
+    """The reference's kernel_ref.h (oracle/_ref/libref_btla.so) or None."""
+    global _ref_btla
+    if _ref_btla is None:
+        p = os.path.join(_HERE, "_ref", "libref_btla.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if not os.path.exists(p):
+            return None
+        L = C.CDLL(p)
+        L.ref_btla_nf4_unpack.restype = C.c_float
+        L.ref_btla_nf4_unpack.argtypes = [C.c_int8]
+        L.ref_btla_nf4_quantize.restype = C.c_int8
+        L.ref_btla_nf4_quantize.argtypes = [C.c_float]
+        L.ref_btla_f32_to_bf16.restype = C.c_uint16
+        L.ref_btla_f32_to_bf16.argtypes = [C.c_float]
+        L.ref_btla_bf16_to_f32.restype = C.c_float
+        L.ref_btla_bf16_to_f32.argtypes = [C.c_uint16]
+        L.ref_btla_cast_f32_s8.restype = C.c_int8
+        L.ref_btla_cast_f32_s8.argtypes = [C.c_float]
+        L.ref_btla_cast_f32_u8.restype = C.c_uint8
+        L.ref_btla_cast_f32_u8.argtypes = [C.c_float]
+        L.ref_btla_cast_f32_s32.restype = C.c_int
+        L.ref_btla_cast_f32_s32.argtypes = [C.c_float]
+        _ref_btla = L
+    return _ref_btla
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+# ----------------------------------------------------------------------------- ggml Q4_0 / Q8_0
+def _rowwise(fn, x, out_bytes_per_block):
+    x = _c(x, np.float32)
+    rows, k = x.reshape(-1, x.shape[-1]).shape
+    assert k % 32 == 0
+    out = np.empty((rows, k // 32 * out_bytes_per_block), np.uint8)
+    x2 = x.reshape(rows, k)
+    for r in range(rows):
+        fn(_p(x2[r]), _p(out[r]), C.c_int(k))
+    return out
+
+
+def quantize_q4_0(w, impl="oracle"):
+    """w [N,K] f32 -> uint8 [N, K/32*18] (block_q4_0 rows)."""
+    L = lib() if impl == "oracle" else ref_ggml()
+    fn = L.orc_quantize_row_q4_0 if impl == "oracle" else L.ref_quantize_row_q4_0
+    return _rowwise(fn, w, Q4_0_BLOCK_BYTES)
+
+
+def quantize_q8_0(x, impl="oracle", variant="runtime"):
+    """x [M,K] f32 -> uint8 [M, K/32*34] (block_q8_0 rows). variant: 'runtime' (x86 body) | 'reference'."""
+    if impl == "oracle":
+        fn = lib().orc_quantize_row_q8_0 if variant == "runtime" else lib().orc_quantize_row_q8_0_reference
+    else:
+        fn = ref_ggml().ref_quantize_row_q8_0 if variant == "runtime" else ref_ggml().ref_quantize_row_q8_0_reference
+    return _rowwise(fn, x, Q8_0_BLOCK_BYTES)
+
+
+def dequantize_q4_0(wq, k, impl="oracle"):
+    wq = _c(wq, np.uint8)
+    out = np.empty((wq.shape[0], k), np.float32)
+    fn = lib().orc_dequantize_row_q4_0 if impl == "oracle" else ref_ggml().ref_dequantize_row_q4_0
+    for r in range(wq.shape[0]):
+        fn(_p(wq[r]), _p(out[r]), C.c_int(k))
+    return out
+
+
+def dequantize_q8_0(xq, k, impl="oracle"):
+    xq = _c(xq, np.uint8)
+    out = np.empty((xq.shape[0], k), np.float32)
+    fn = lib().orc_dequantize_row_q8_0 if impl == "oracle" else ref_ggml().ref_dequantize_row_q8_0
+    for r in range(xq.shape[0]):
+        fn(_p(xq[r]), _p(out[r]), C.c_int(k))
+    return out
+
+
+def vec_dot_q4_0_q8_0(wrow, arow, k, impl="oracle", scalar=False):
+    s = C.c_float()
+    if impl == "oracle":
+        fn = lib().orc_vec_dot_q4_0_q8_0_scalar if scalar else lib().orc_vec_dot_q4_0_q8_0
+    else:
+        fn = ref_ggml().ref_vec_dot_q4_0_q8_0
+    fn(C.c_int(k), C.byref(s), _p(_c(wrow, np.uint8)), _p(_c(arow, np.uint8)))
+    return np.float32(s.value)
+
+
+def block_isum_q4_0_q8_0(wrow, arow, k):
+    out = np.empty(k // 32, np.int32)
+    lib().orc_block_isum_q4_0_q8_0(C.c_int(k), _p(out), _p(_c(wrow, np.uint8)), _p(_c(arow, np.uint8)))
+    return out
+
+
+def mul_mat_q4_0_f32(wq, a, impl="oracle", nth=0):
+    """wq uint8 [N, K/32*18], a f32 [M,K] -> f32 [M,N] (ne_compute_forward_mul_mat_q_f32 semantics)."""
+    wq = _c(wq, np.uint8)
+    a = _c(a, np.float32)
+    m, k = a.shape
+    n = wq.shape[0]
+    assert wq.shape[1] == k // 32 * Q4_0_BLOCK_BYTES
+    dst = np.empty((m, n), np.float32)
+    wdata = np.empty(m * (k // 32) * Q8_0_BLOCK_BYTES + 64, np.uint8)
+    fn = lib().orc_mul_mat_q4_0_f32 if impl == "oracle" else ref_ggml().ref_mul_mat_q4_0_f32
+    fn.restype = C.c_int
+    used = fn(_p(wq), _p(a), _p(dst), C.c_int(n), C.c_int(k), C.c_int(m), _p(wdata), C.c_int(nth))
+    mul_mat_q4_0_f32.threads_used = used
+    return dst
+
+
+def argmax(x):
+    x = _c(x, np.float32).ravel()
+    lib().orc_argmax_f32.restype = C.c_int
+    return int(lib().orc_argmax_f32(_p(x), C.c_int(x.size)))
+
+
+# ----------------------------------------------------------------------------- BesTLA
+def btla_quantize(w_kn, g, nbits=4, asym=False, impl="oracle"):
+    """RTN quantise W [K,N] f32 -> (q int8 [K,N], scales f32 [ceil(K/g),N], zps int8 [..] | None)."""
+    w = _c(w_kn, np.float32)
+    k, n = w.shape
+    nb = (k + g - 1) // g
+    q = np.zeros((k, n), np.int8)
+    sc = np.zeros((nb, n), np.float32)
+    zp = np.zeros((nb, n), np.int8) if asym else None
+    if impl == "oracle":
+        lib().orc_btla_quantize_rowblock(_p(w), _p(q), C.c_int(k), C.c_int(n), C.c_int(n), C.c_int(n), _p(sc),
+                                         _p(zp) if asym else None, C.c_int(g), C.c_int(nbits))
+    else:
+        qt = {4: BTLA_S4_CLIP, 8: BTLA_S8}[nbits]
+        ref_btla().ref_btla_quantize_f32_sign_int_rowblock(_p(w), _p(q), C.c_int(k), C.c_int(n), C.c_int(n), C.c_int(n),
+                                                           _p(sc), _p(zp) if asym else None, C.c_int(g), C.c_uint32(qt))
+    return q, sc, zp
+
+
+def btla_quantize_nf4(w_kn, g, impl="oracle"):
+    w = _c(w_kn, np.float32)
+    k, n = w.shape
+    nb = (k + g - 1) // g
+    q = np.zeros((k, n), np.int8)
+    sc = np.zeros((nb, n), np.float32)
+    if impl == "oracle":
+        lib().orc_btla_quantize_nf4_rowblock(_p(w), _p(q), C.c_int(k), C.c_int(n), C.c_int(n), C.c_int(n), _p(sc), C.c_int(g))
+    else:
+        ref_btla().ref_btla_quantize_f32_nf4_rowblock(_p(w), _p(q), C.c_int(k), C.c_int(n), C.c_int(n), C.c_int(n), _p(sc),
+                                                      C.c_int(g))
+    return q, sc
+
+
+def btla_dequant(q, sc, zp, g, nf4=False):
+    q = _c(q, np.int8)
+    k, n = q.shape
+    w = np.empty((k, n), np.float32)
+    lib().orc_btla_dequant(_p(q), _p(_c(sc, np.float32)), _p(_c(zp, np.int8)) if zp is not None else None, _p(w),
+                           C.c_int(k), C.c_int(n), C.c_int(g), C.c_int(1 if nf4 else 0))
+    return w
+
+
+def btla_quantize_act_u8(a, g, impl="oracle", want_reduce=False):
+    a = _c(a, np.float32)
+    m, k = a.shape
+    nb = (k + g - 1) // g
+    q = np.zeros((m, k), np.uint8)
+    sc = np.zeros((m, nb), np.float32)
+    zp = np.zeros((m, nb), np.uint8)
+    red = np.zeros((m, nb), np.float32) if want_reduce else None
+    if impl == "oracle":
+        lib().orc_btla_quantize_act_u8(C.c_int(m), C.c_int(k), _p(a), C.c_int(k), _p(q), C.c_int(k), _p(sc), C.c_int(nb),
+                                       _p(zp), C.c_int(g), _p(red) if want_reduce else None)
+    else:
+        ref_btla().ref_btla_quantize_fp_u8_colblock(C.c_int(m), C.c_int(k), _p(a), C.c_int(k), _p(q), C.c_int(k), _p(sc),
+                                                    C.c_int(nb), _p(zp), C.c_int(g), _p(red) if want_reduce else None)
+    return (q, sc, zp, red) if want_reduce else (q, sc, zp)
+
+
+def btla_quantize_act_s8(a, g, impl="oracle"):
+    a = _c(a, np.float32)
+    m, k = a.shape
+    nb = (k + g - 1) // g
+    q = np.zeros((m, k), np.int8)
+    sc = np.zeros((m, nb), np.float32)
+    if impl == "oracle":
+        lib().orc_btla_quantize_act_s8(C.c_int(m), C.c_int(k), _p(a), C.c_int(k), _p(q), C.c_int(k), _p(sc), C.c_int(nb),
+                                       C.c_int(g), None)
+    else:
+        ref_btla().ref_btla_quantize_fp_s8_colblock(C.c_int(m), C.c_int(k), _p(a), C.c_int(k), _p(q), C.c_int(k), _p(sc),
+                                                    C.c_int(nb), C.c_int(g), None)
+    return q, sc
+
+
+def btla_gemv_fp32(a, q, sc, zp, g):
+    a = _c(a, np.float32)
+    m, k = a.shape
+    n = q.shape[1]
+    c = np.empty((m, n), np.float32)
+    lib().orc_btla_gemv_fp32(_p(a), C.c_int(k), _p(_c(q, np.int8)), _p(_c(sc, np.float32)),
+                             _p(_c(zp, np.int8)) if zp is not None else None, _p(c), C.c_int(n), C.c_int(m), C.c_int(n),
+                             C.c_int(k), C.c_int(g))
+    return c
+
+
+def btla_gemv_u8s8(a8, asc, azp, q, sc, zp, g, blocksum=False):
+    a8 = _c(a8, np.uint8)
+    m, k = a8.shape
+    n = q.shape[1]
+    nb = asc.shape[1]
+    c = np.empty((m, n), np.float32)
+    fn = lib().orc_btla_gemv_u8s8_blocksum if blocksum else lib().orc_btla_gemv_u8s8
+    fn(_p(a8), _p(_c(asc, np.float32)), _p(_c(azp, np.uint8)), C.c_int(k), C.c_int(nb), _p(_c(q, np.int8)),
+       _p(_c(sc, np.float32)), _p(_c(zp, np.int8)) if zp is not None else None, _p(c), C.c_int(n), C.c_int(m), C.c_int(n),
+       C.c_int(k), C.c_int(g))
+    return c
+
+
+def btla_gemv_s8s8(a8, asc, q, sc, zp, g):
+    a8 = _c(a8, np.int8)
+    m, k = a8.shape
+    n = q.shape[1]
+    nb = asc.shape[1]
+    c = np.empty((m, n), np.float32)
+    lib().orc_btla_gemv_s8s8(_p(a8), _p(_c(asc, np.float32)), C.c_int(k), C.c_int(nb), _p(_c(q, np.int8)),
+                             _p(_c(sc, np.float32)), _p(_c(zp, np.int8)) if zp is not None else None, _p(c), C.c_int(n),
+                             C.c_int(m), C.c_int(n), C.c_int(k), C.c_int(g))
+    return c
+
+
+def gemm_f64acc(a, w_kn):
+    a = _c(a, np.float32)
+    w = _c(w_kn, np.float32)
+    m, k = a.shape
+    n = w.shape[1]
+    c = np.empty((m, n), np.float32)
+    lib().orc_gemm_f64acc(_p(a), C.c_int(k), _p(w), _p(c), C.c_int(n), C.c_int(m), C.c_int(n), C.c_int(k))
+    return c
+
+
+def f32_to_bf16_bits(x):
+    """RNE fp32 -> bf16 bit pattern (bestla_utils.h:146-153), vectorised."""
+    u = _c(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = u + 0x7FFF + ((u >> 16) & 1)
+    return ((u >> 16) & 0xFFFF).astype(np.uint16)
+
+
+def bf16_bits_to_f32(b):
+    return (np.asarray(b, np.uint16).astype(np.uint32) << 16).view(np.float32)

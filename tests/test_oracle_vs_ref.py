@@ -1,0 +1,132 @@
+"""Pin the CPU oracle (oracle/oracle_*.c) against the reference's own code compiled in place
+(oracle/_ref/*.so built from /root/reference by oracle/Makefile).  Everything here must be BIT-exact."""
+import numpy as np
+import pytest
+
+import oracle
+
+ref_g = oracle.ref_ggml()
+ref_b = oracle.ref_btla()
+need_ref_g = pytest.mark.skipif(ref_g is None, reason="oracle/_ref/libref_ggml.so not built (no /root/reference)")
+need_ref_b = pytest.mark.skipif(ref_b is None, reason="oracle/_ref/libref_btla.so not built (no /root/reference)")
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+@need_ref_g
+def test_fp16_roundtrip_all_bit_patterns():
+    L = oracle.lib()
+    for h in range(0, 1 << 16, 1):
+        a = L.orc_fp16_to_fp32(h)
+        b = ref_g.ref_fp16_to_fp32(h)
+        assert (a == b) or (a != a and b != b), h
+    r = _rng(0)
+    xs = np.concatenate([r.normal(0, 1, 20000), r.normal(0, 1e-6, 5000), r.normal(0, 3e4, 5000),
+                         np.array([0.0, -0.0, 65504.0, 65519.9, 65520.0, 1e-8, 5.96e-8, 2.98e-8, 6.1e-5])]).astype(np.float32)
+    for x in xs:
+        assert L.orc_fp32_to_fp16(float(x)) == ref_g.ref_fp32_to_fp16(float(x)), x
+
+
+@need_ref_g
+@pytest.mark.parametrize("seed,scale", [(1, 0.02), (2, 1.0), (3, 50.0)])
+def test_q4_0_quantize_dequantize(seed, scale):
+    w = (_rng(seed).normal(0, scale, (64, 256))).astype(np.float32)
+    w[3, :32] = 0.0  # all-zero block: d == 0 branch
+    a = oracle.quantize_q4_0(w, "oracle")
+    b = oracle.quantize_q4_0(w, "ref")
+    assert np.array_equal(a, b)
+    assert np.array_equal(oracle.dequantize_q4_0(a, 256, "oracle"), oracle.dequantize_q4_0(a, 256, "ref"))
+
+
+@need_ref_g
+@pytest.mark.parametrize("variant", ["runtime", "reference"])
+def test_q8_0_quantize(variant):
+    r = _rng(7)
+    x = r.normal(0, 1.0, (32, 512)).astype(np.float32)
+    x[0, :32] = 0.0
+    x[1, :64] = np.round(x[1, :64] * 4) / 4  # plenty of exact .5 ties after scaling
+    x[2, :32] = np.arange(32) - 15.5
+    a = oracle.quantize_q8_0(x, "oracle", variant)
+    b = oracle.quantize_q8_0(x, "ref", variant)
+    assert np.array_equal(a, b)
+    assert np.array_equal(oracle.dequantize_q8_0(a, 512, "oracle"), oracle.dequantize_q8_0(a, 512, "ref"))
+
+
+@need_ref_g
+def test_vec_dot_and_mul_mat_bit_exact():
+    r = _rng(11)
+    N, K, M = 96, 1024, 5
+    w = r.normal(0, 0.02, (N, K)).astype(np.float32)
+    a = r.uniform(-0.5, 0.5, (M, K)).astype(np.float32)
+    wq = oracle.quantize_q4_0(w)
+    aq = oracle.quantize_q8_0(a)
+    for n in range(0, N, 7):
+        assert oracle.vec_dot_q4_0_q8_0(wq[n], aq[0], K, "oracle") == oracle.vec_dot_q4_0_q8_0(wq[n], aq[0], K, "ref")
+    c0 = oracle.mul_mat_q4_0_f32(wq, a, "oracle")
+    c1 = oracle.mul_mat_q4_0_f32(wq, a, "ref")
+    assert np.array_equal(c0, c1)
+    # the scalar body only differs in fp32 summation order
+    s = np.array([oracle.vec_dot_q4_0_q8_0(wq[n], aq[0], K, "oracle", scalar=True) for n in range(N)])
+    np.testing.assert_allclose(s, c0[0], rtol=2e-4, atol=1e-5)
+
+
+@need_ref_b
+def test_btla_scalar_casts_and_bf16():
+    L = oracle.lib()
+    r = _rng(5)
+    xs = np.concatenate([r.normal(0, 60, 4000), np.arange(-130, 131) + 0.5, np.arange(-130, 131) - 0.5,
+                         [0.0, 254.5, 255.49, 300.0, -0.4]]).astype(np.float32)
+    for x in xs:
+        x = float(x)
+        assert L.orc_cast_f32_s8(x) == ref_b.ref_btla_cast_f32_s8(x)
+        assert L.orc_cast_f32_u8(x) == ref_b.ref_btla_cast_f32_u8(x)
+        assert L.orc_cast_f32_s32(x) == ref_b.ref_btla_cast_f32_s32(x)
+        assert L.orc_f32_to_bf16(x * 1e-3) == ref_b.ref_btla_f32_to_bf16(x * 1e-3)
+    for c in range(16):
+        assert L.orc_nf4_unpack(c) == ref_b.ref_btla_nf4_unpack(c)
+    for x in np.linspace(-1.1, 1.1, 4001).astype(np.float32):
+        assert L.orc_nf4_quantize(float(x)) == ref_b.ref_btla_nf4_quantize(float(x))
+    v = r.normal(0, 1, 1000).astype(np.float32)
+    assert np.array_equal(oracle.f32_to_bf16_bits(v), np.array([L.orc_f32_to_bf16(float(t)) for t in v], np.uint16))
+
+
+@need_ref_b
+@pytest.mark.parametrize("nbits", [4, 8])
+@pytest.mark.parametrize("asym", [False, True])
+@pytest.mark.parametrize("g,K", [(32, 256), (128, 256), (128, 320), (256, 256)])
+def test_btla_rtn_quantize(nbits, asym, g, K):
+    r = _rng(100 + nbits + g + K)
+    w = r.uniform(-0.5, 0.5, (K, 48)).astype(np.float32)  # bestla_ut.h fill convention
+    w[:, 1] = np.abs(w[:, 1])          # one-sided column: exercises the NVal = -FullValue branch
+    w[:, 2] = -np.abs(w[:, 2])
+    q0, s0, z0 = oracle.btla_quantize(w, g, nbits, asym, "oracle")
+    q1, s1, z1 = oracle.btla_quantize(w, g, nbits, asym, "ref")
+    assert np.array_equal(q0, q1) and np.array_equal(s0, s1)
+    if asym:
+        assert np.array_equal(z0, z1)
+
+
+@need_ref_b
+@pytest.mark.parametrize("g", [32, 128])
+def test_btla_nf4_quantize(g):
+    w = _rng(9).normal(0, 0.05, (256, 48)).astype(np.float32)
+    q0, s0 = oracle.btla_quantize_nf4(w, g, "oracle")
+    q1, s1 = oracle.btla_quantize_nf4(w, g, "ref")
+    assert np.array_equal(q0, q1) and np.array_equal(s0, s1)
+
+
+@need_ref_b
+@pytest.mark.parametrize("g,K", [(32, 256), (128, 384), (128, 300)])
+def test_btla_activation_quant(g, K):
+    a = _rng(21).normal(0, 1, (4, K)).astype(np.float32)
+    a[1] = np.abs(a[1])
+    o = oracle.btla_quantize_act_u8(a, g, "oracle", want_reduce=True)
+    f = oracle.btla_quantize_act_u8(a, g, "ref", want_reduce=True)
+    for x, y in zip(o, f):
+        assert np.array_equal(x, y)
+    o = oracle.btla_quantize_act_s8(a, g, "oracle")
+    f = oracle.btla_quantize_act_s8(a, g, "ref")
+    for x, y in zip(o, f):
+        assert np.array_equal(x, y)
