@@ -1,0 +1,189 @@
+/*
+ * ns_b200.h -- C ABI of libns_b200.so: the B200-native (sm_100a) replacement for neural-speed's low-bit
+ * weight-only matmul path.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to /root/reference).
+ * Three groups:
+ *   1. bestla_*          host-buffer drop-ins with the exact signatures of neural_speed/core/ne_bestla.h:21-83.
+ *                        `weiptr` is a serialized BesTLA blob in HOST memory (bestla/bestla/bestla_storage.h:697-834);
+ *                        activations / outputs are HOST fp32.  The library uploads + repacks each blob once
+ *                        (cached by address), runs the CUDA kernels, copies the result back.
+ *   2. bestla_device_*   device-resident set modelled on the reference's NS_SYCL block, ne_bestla.h:85-112
+ *                        (void* queue == cudaStream_t).  Activations / outputs are DEVICE fp32.
+ *   3. ns_* / BTLAGemm*  ggml Q4_0 path (ne_compute_forward_mul_mat_q_f32, core/ne_layers.c:7085), the weight
+ *                        packing API (core/layers/bestla_gemm.h:30-58, models/model_utils/quant_utils.cpp:226-400)
+ *                        and handles for fused / graph-captured decode.
+ *
+ * Error convention (mirrors the reference): *_support() are pure probes returning bool;
+ * *_forward() print "Err: ..." and abort() on invalid input or when no CUDA device / kernel image is usable
+ * (there is NO CPU fallback in this library); pack functions return false / 0 on failure;
+ * ns_* functions return 0 on success and a negative NS_E_* code otherwise (message via ns_last_error()).
+ */
+#ifndef NS_B200_H
+#define NS_B200_H
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NS_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------------ enums */
+/* weight element formats in the device ("NSB") layout */
+enum ns_wfmt { NS_W_S4 = 0, NS_W_S8 = 1, NS_W_NF4 = 2 };
+/* scale storage */
+enum ns_stype { NS_S_F32 = 0, NS_S_BF16 = 1, NS_S_F16 = 2 };
+/* activation numerics ("compute type"): which reference arithmetic the kernel reproduces
+ *   NS_COMP_F32     fp32 activations, w = (q-zp)*scale in fp32, fp32 FMA      (BesTLA CompFp32, kernel_ref.h:2490)
+ *   NS_COMP_BF16    activations and dequantised weights rounded to bf16, fp32 accumulate (BesTLA CompBf16)
+ *   NS_COMP_INT8    u8-asym per-K-block activations x int weights, exact integer block dots
+ *                   (BesTLA CompInt8, kernel_ref.h:1825 + :2372)
+ *   NS_COMP_Q8_0    ggml: s8 activations per 32, fp16 scales, round-half-even (quantize.h:447, vec_dot.h:131)
+ *   NS_COMP_INT8_S8 s8-sym per-K-block activations (kernel_ref.h:1886 + :2432)
+ */
+enum ns_comp { NS_COMP_F32 = 0, NS_COMP_BF16 = 1, NS_COMP_INT8 = 2, NS_COMP_Q8_0 = 3, NS_COMP_INT8_S8 = 4 };
+/* ne_comp_type, neural_speed/core/data_types.h:55-62 */
+enum ns_ne_comp_type { NS_NE_COMP_UNDEF = 0, NS_NE_COMP_F32 = 1, NS_NE_COMP_BF16 = 2, NS_NE_COMP_F16 = 3, NS_NE_COMP_INT8 = 4 };
+/* BTLA_DTYPE raw values, bestla/bestla/bestla.h:38-87 */
+#define NS_BTLA_F32 32u
+#define NS_BTLA_BF16 (16u | (1u << 16))
+#define NS_BTLA_F16 16u
+#define NS_BTLA_S8 (8u | (1u << 8))
+#define NS_BTLA_S4_CLIP (4u | (1u << 8))
+#define NS_BTLA_F4_NF4 (4u | (2u << 16))
+
+#define NS_OK 0
+#define NS_E_INVALID (-1)
+#define NS_E_NODEVICE (-2)
+#define NS_E_CUDA (-3)
+#define NS_E_UNSUPPORTED (-4)
+
+NS_API const char* ns_last_error(void);
+NS_API const char* ns_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+NS_API unsigned long long ns_launch_count(void);
+
+/* ------------------------------------------------------------------ 1. ne_bestla.h host-buffer drop-ins */
+/* ne_bestla.h:33 / core/layers/ne_bestla.cpp:19.  Selects cuda:0 lazily; aborts later if none. */
+NS_API void bestla_init(void);
+/* ne_bestla.h:25-27.  Host threads are irrelevant on the GPU path; kept for ABI compatibility. */
+NS_API int bestla_set_threads(int nth);
+NS_API void* bestla_get_thread_handle(void);
+NS_API void bestla_timer(bool init);
+
+/* ne_bestla.h:35 / core/layers/inner_product.cpp:20 -- M * pad128(K) * 4 bytes, as the reference */
+NS_API unsigned long long bestla_f32f32_get_workspace_size(int m, int n, int k, void* wptr);
+/* ne_bestla.h:37 / inner_product.cpp:28 -- C[m][n] = A[m][k] . dequant(W)  (lda is ignored, K is used: bestla_gemm.cpp:44) */
+NS_API void bestla_f32f32_forward(float* activation, void* weiptr, float* output, int m, int n, int k, int lda, int ldo,
+                                  void* workspace);
+/* ne_bestla.h:40-42 / inner_product.cpp:113,132 -- bias epilogue */
+NS_API bool bestla_fusion_add_f32f32_support(void* weiptr, int m, int n, int k);
+NS_API void bestla_fusion_add_f32f32_forward(float* activation, void* weiptr, float* bias, float* output, int m, int n,
+                                             int k, int lda, int ldo, bool boardcast_bias, void* workspace);
+/* ne_bestla.h:44-51 / core/layers/ip_fusion_qkv.cpp:155,163,194 -- out = [3][M][N] */
+NS_API unsigned long long bestla_fusion_QKV_f32f32_get_workspace_size(int m, int n, int k, void* w1ptr);
+NS_API bool bestla_fusion_QKV_f32f32_support(void* wqptr, void* wkptr, void* wvptr, int m, int n, int k);
+NS_API void bestla_fusion_QKV_f32f32_forward(float* activation, void* wqptr, void* wkptr, void* wvptr, float* output,
+                                             int m, int n, int k, int lda, int ldo, void* workspace);
+/* ne_bestla.h:53-66 / core/layers/ip_fusion_ffn.cpp:20,724-740 -- out = (silu(x W1) * (x W3)) W2 */
+NS_API unsigned long long bestla_fusion_FFN_f32f32_get_workspace_size(int seq, int fin, int fmid, int fout, void* w1ptr,
+                                                                      void* w2ptr);
+NS_API bool bestla_fusion_FFN_SiLu_f32f32_support(void* w1ptr, void* w2ptr, void* w3ptr, int seq, int fin, int fmid,
+                                                  int fout);
+NS_API void bestla_fusion_FFN_SiLu_f32f32_forward(float* activation, void* w1ptr, void* w2ptr, void* w3ptr, float* tmp1,
+                                                  float* tmp2, float* output, int seq, int fin, int fmid, int fout,
+                                                  void* workspace);
+/* ne_bestla.h:75 / ne_bestla.cpp:74 -- dequantise a blob to fp32 [n][ld] (ld >= k) */
+NS_API void bestla_unpackweight_fp32(void* wptr, int n, int k, float* fp32data, int ld);
+
+/* ------------------------------------------------------------------ 2. device-resident set (NS_SYCL analogue) */
+/* ne_bestla.h:86-95.  device = opaque context owning one CUDA stream on cuda:<current>; queue = cudaStream_t */
+NS_API void* bestla_create_device(bool profile);
+NS_API void* bestla_get_device_queue(void* device);
+NS_API void bestla_release_device(void* device);
+NS_API size_t bestla_device_gmem_size(void* device);
+NS_API void* bestla_device_malloc(size_t size, void* queue);
+NS_API void bestla_device_free(void* ptr, void* queue);
+NS_API void bestla_device_memcpy(void* dstptr, const void* srcptr, size_t size, void* queue);
+NS_API void bestla_device_memcpy_sync(void* dstptr, const void* srcptr, size_t size, void* queue);
+NS_API void bestla_device_sync(void* queue);
+/* ne_bestla.h:96-97 / ne_bestla_sycl.cpp:94.  hoststor = serialized blob (host); devstor = host descriptor of
+ * bestla_device_storage_size() bytes filled by the call; deviceptr = device buffer of at least
+ * ns_device_storage_bytes(hoststor) bytes that receives the repacked weight. */
+NS_API size_t bestla_device_storage_size(void);
+NS_API size_t ns_device_storage_bytes(const void* hoststor);
+NS_API void bestla_device_load_storage(void* hoststor, void* devstor, void* deviceptr, void* queue);
+/* ne_bestla.h:98-99 / ne_bestla_sycl.cpp:152.  activation/output are DEVICE fp32; weiptr = devstor descriptor.
+ * workspace: device scratch of >= ns_device_workspace_bytes(m, k) bytes (or NULL: library-owned scratch). */
+NS_API size_t ns_device_workspace_bytes(int m, int k);
+NS_API void bestla_device_f32f32_forward(float* activation, void* weiptr, float* output, int m, int n, int k, int lda,
+                                         int ldo, void* workspace, void* queue);
+
+/* ------------------------------------------------------------------ 3a. weight handles (device resident) */
+typedef struct ns_weight ns_weight; /* opaque: repacked weight in HBM + metadata */
+
+/* ggml rows: src0 of ne_compute_forward_mul_mat_q_f32 (ne_layers.c:7085): n rows of k/32 block_q4_0
+ * (data_types.h:79-83), row stride nb01 bytes.  `rows` may be a host or a device pointer (rows_on_device). */
+NS_API ns_weight* ns_weight_from_q4_0(const void* rows, int n, int k, size_t nb01, int rows_on_device, void* queue);
+/* serialized BesTLA blob (host memory), StorageWeightKBlockNInteger / NFloat */
+NS_API ns_weight* ns_weight_from_btla_blob(const void* blob, void* queue);
+/* canonical unpacked container as BTLAGemmPackB takes it (bestla_gemm.h:46-50): q int8 [k][n] (values, e.g.
+ * nibble-8), scales f32 [k/g][n], zp int8 [k/g][n] or NULL, shuffle int[k] or NULL.  Host pointers. */
+NS_API ns_weight* ns_weight_from_unpacked(const int8_t* q, const float* scales, const int8_t* zp, const int* shuffle, int n,
+                                          int k, int group, int wfmt, int stype, int comp, void* queue);
+NS_API void ns_weight_free(ns_weight* w);
+NS_API int ns_weight_info(const ns_weight* w, int* n, int* k, int* group, int* wfmt, int* stype, int* comp, int* asym);
+NS_API int ns_weight_set_comp(ns_weight* w, int comp);
+/* packed bytes one GEMV must read from HBM for this weight (roofline numerator) */
+NS_API size_t ns_weight_algorithmic_bytes(const ns_weight* w);
+/* dequantise to device fp32 [n][ld] (debug / parity; replaces bestla_unpackweight_fp32 on device) */
+NS_API int ns_weight_dequant_f32(const ns_weight* w, float* dst_dev, int ld, void* queue);
+
+/* ------------------------------------------------------------------ 3b. device matmuls on handles */
+/* dst[m][n] (ldo) = act[m][k] (lda) . W^T ; act/dst device fp32.  flags: NS_MM_* ; bias/residual may be NULL. */
+#define NS_MM_BIAS_BCAST 1   /* bias is [n] broadcast over m (else [m][ldo]) */
+#define NS_MM_FORCE_GEMV 2   /* always use the dp4a/FMA GEMV path (exact-integer numerics) regardless of m */
+#define NS_MM_FORCE_TC 4     /* always use the tcgen05 tensor-core path (bf16 numerics) */
+NS_API int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* bias,
+                      const float* residual, int flags, void* workspace, void* queue);
+/* three weights sharing one activation (ne_mul_qkv): dst = [3][m][ldo], weights may differ in n */
+NS_API int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_weight* wv, const float* act, int lda, float* dst,
+                      int ldo, int m, void* workspace, void* queue);
+/* ne_ffn_silu: tmp = silu(act.W1^T) * (act.W3^T) [m][fmid];  dst = tmp.W2^T [m][fout] */
+NS_API int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda, float* tmp,
+                       float* dst, int ldo, int m, void* workspace, void* queue);
+
+/* ggml drop-in with HOST buffers: ne_compute_forward_mul_mat_q_f32 (ne_layers.c:7085) for NE_TYPE_Q4_0:
+ * dst[ne11][ne01] = src1[ne11][ne00] x src0 rows.  src0 is uploaded/repacked once and cached by address. */
+NS_API int ns_mul_mat_q4_0_f32_host(const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01,
+                                    int ne11);
+
+/* ------------------------------------------------------------------ 3c. quantisers / packing API */
+/* device RTN->Q4_0 (quantize_row_q4_0_reference, quantize.h:243): src f32 [n][k] device -> dst block_q4_0 rows device */
+NS_API int ns_device_quantize_q4_0(const float* src_dev, void* dst_dev, int n, int k, void* queue);
+/* device activation quantiser exposed for parity tests: one of ns_comp; outputs are device buffers
+ * q: [m][k] (int8/uint8), scale: [m][k/g] f32, zp: [m][k/g] int32 (u8 mode, else untouched) */
+NS_API int ns_device_quantize_act(const float* act_dev, int lda, int m, int k, int group, int comp, void* q_dev,
+                                  float* scale_dev, int* zp_dev, void* queue);
+
+/* core/layers/bestla_gemm.h:37-56 (C++ in the reference; same names/argument meaning, extern "C" here).
+ * QuantType/ScaleDtype are raw BTLA_DTYPE values, CompType an ne_comp_type.  ThreadPool is ignored. */
+NS_API size_t BTLAGemmPackBSize(size_t N, size_t K, size_t BlkSize, uint32_t QuantType, uint32_t ScaleDtype, bool isAsym,
+                                int CompType, int* shuffle_indice);
+NS_API bool BTLAGemmQuantPackB(void* PackedBuf, const float* FpData, size_t N, size_t K, size_t ldb, size_t BlkSize,
+                               uint32_t QuantType, uint32_t ScaleDtype, bool isAsym, int CompType, bool isTrans,
+                               void* ThreadPool);
+NS_API bool BTLAGemmPackB(void* PackedBuf, const int8_t* QData, const float* Scales, const int8_t* Zp, size_t N, size_t K,
+                          size_t ldb, size_t BlkSize, uint32_t QuantType, uint32_t ScaleDtype, bool isAsym, int CompType,
+                          int* shuffle_indice, void* ThreadPool);
+NS_API bool BTLAGemmUnPackB(float* FpData, const void* PackedBuf, size_t N, size_t K, size_t ldb, void* ThreadPool);
+/* host Q4_0 row quantiser (ne_quantize_q4_0 path; quantize.h:243) for the weight-packing API */
+NS_API void ns_quantize_row_q4_0(const float* x, void* y, int k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NS_B200_H */

@@ -1,0 +1,884 @@
+// abi.cu -- the C-ABI of libns_b200.so (see include/ns_b200.h): device context, weight handles, blob parsing,
+// host-buffer drop-ins for neural_speed/core/ne_bestla.h and the device set modelled on its NS_SYCL block.
+// There is NO CPU compute path in this file: without a usable CUDA device every compute entry point fails loudly.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "nsb.cuh"
+
+// ---------------------------------------------------------------------------------------------------- errors / context
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void ns_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+[[noreturn]] void ns_fatal(const char* fmt, ...) {
+  // the reference prints and assert(0)s on bad input (core/layers/inner_product.cpp:31-35)
+  va_list ap;
+  va_start(ap, fmt);
+  fprintf(stderr, "Err: ");
+  vfprintf(stderr, fmt, ap);
+  fprintf(stderr, "\n");
+  va_end(ap);
+  abort();
+}
+bool ns_cuda_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  ns_set_error("CUDA error %s: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e), what);
+  return false;
+}
+void ns_count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+extern "C" const char* ns_last_error(void) { return g_err; }
+extern "C" const char* ns_version(void) { return "ns_b200 0.1 (sm_100a)"; }
+extern "C" unsigned long long ns_launch_count(void) { return g_launches.load(); }
+
+struct ns_device {
+  int dev;
+  cudaStream_t stream;
+  bool profile;
+};
+
+static std::mutex g_mu;
+static int g_dev_state = 0;  // 0 unknown, 1 ok, -1 none
+static ns_device g_default = {0, nullptr, false};
+// library-owned scratch per stream
+struct Scratch {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+static std::unordered_map<cudaStream_t, Scratch> g_scratch;
+
+int ns_ensure_device() {
+  if (g_dev_state == 1) return NS_OK;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_dev_state == 1) return NS_OK;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    ns_set_error("no CUDA device available (%s); libns_b200 has no CPU fallback", cudaGetErrorString(e));
+    cudaGetLastError();
+    g_dev_state = -1;
+    return NS_E_NODEVICE;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+    ns_set_error("device %d is sm_%d%d; this library carries sm_100a code only", dev, prop.major, prop.minor);
+    g_dev_state = -1;
+    return NS_E_NODEVICE;
+  }
+  g_default.dev = dev;
+  if (cudaStreamCreateWithFlags(&g_default.stream, cudaStreamNonBlocking) != cudaSuccess) {
+    ns_set_error("cudaStreamCreate failed");
+    g_dev_state = -1;
+    return NS_E_CUDA;
+  }
+  g_dev_state = 1;
+  return NS_OK;
+}
+
+static cudaStream_t default_stream() { return g_default.stream; }
+static cudaStream_t stream_of(void* queue) { return queue ? (cudaStream_t)queue : default_stream(); }
+
+static void* scratch_get(cudaStream_t st, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Scratch& s = g_scratch[st];
+  if (s.bytes < bytes) {
+    if (s.p) {
+      cudaStreamSynchronize(st);
+      cudaFree(s.p);
+    }
+    size_t nb = ns_round_up(bytes + bytes / 4, 1 << 20);
+    if (cudaMalloc(&s.p, nb) != cudaSuccess) {
+      s.p = nullptr;
+      s.bytes = 0;
+      ns_set_error("cudaMalloc(%zu) for scratch failed", nb);
+      return nullptr;
+    }
+    s.bytes = nb;
+  }
+  return s.p;
+}
+
+// ---------------------------------------------------------------------------------------------------- weight handles
+static size_t stype_size(int stype) { return stype == NS_S_F32 ? 4 : 2; }
+
+static void weight_layout(ns_weight* w) {
+  w->kpad = (int)ns_round_up((size_t)w->k, 32);
+  if (w->group <= 0 || w->group > w->k) w->group = w->k;
+  w->ngroups = (w->k + w->group - 1) / w->group;
+  w->row_bytes = (w->wfmt == NS_W_S8) ? (size_t)w->kpad : (size_t)w->kpad / 2;
+}
+static size_t weight_image_bytes(const ns_weight* w, bool with_shuffle) {
+  size_t b = ns_round_up((size_t)w->n * w->row_bytes, 256);
+  b += ns_round_up((size_t)w->n * w->ngroups * stype_size(w->stype), 256);
+  if (w->asym) b += ns_round_up((size_t)w->n * w->ngroups, 256);
+  if (with_shuffle) b += ns_round_up((size_t)w->k * 4, 256);
+  return b;
+}
+static void weight_carve(ns_weight* w, void* base, bool with_shuffle) {
+  char* p = (char*)base;
+  w->q = (uint8_t*)p;
+  p += ns_round_up((size_t)w->n * w->row_bytes, 256);
+  w->scales = p;
+  p += ns_round_up((size_t)w->n * w->ngroups * stype_size(w->stype), 256);
+  w->zp = nullptr;
+  if (w->asym) {
+    w->zp = (int8_t*)p;
+    p += ns_round_up((size_t)w->n * w->ngroups, 256);
+  }
+  w->shuffle = with_shuffle ? (int*)p : nullptr;
+}
+static int weight_alloc(ns_weight* w, bool with_shuffle) {
+  w->total_bytes = weight_image_bytes(w, with_shuffle);
+  NS_CUDA_TRY(cudaMalloc(&w->base, w->total_bytes));
+  w->external = 0;
+  weight_carve(w, w->base, with_shuffle);
+  return NS_OK;
+}
+
+extern "C" void ns_weight_free(ns_weight* w) {
+  if (!w) return;
+  if (w->base && !w->external) cudaFree(w->base);
+  delete w;
+}
+
+extern "C" int ns_weight_info(const ns_weight* w, int* n, int* k, int* group, int* wfmt, int* stype, int* comp, int* asym) {
+  if (!w) return NS_E_INVALID;
+  if (n) *n = w->n;
+  if (k) *k = w->k;
+  if (group) *group = w->group;
+  if (wfmt) *wfmt = w->wfmt;
+  if (stype) *stype = w->stype;
+  if (comp) *comp = w->comp;
+  if (asym) *asym = w->asym;
+  return NS_OK;
+}
+extern "C" int ns_weight_set_comp(ns_weight* w, int comp) {
+  if (!w || comp < 0 || comp > NS_COMP_INT8_S8) return NS_E_INVALID;
+  if (w->wfmt == NS_W_NF4 && !(comp == NS_COMP_F32 || comp == NS_COMP_BF16)) {
+    ns_set_error("NF4 weights support float compute only (docs/advanced_usage.md:82-83)");
+    return NS_E_UNSUPPORTED;
+  }
+  w->comp = comp;
+  return NS_OK;
+}
+extern "C" size_t ns_weight_algorithmic_bytes(const ns_weight* w) {
+  // N*K*bits/8 + N*ceil(K/g)*(scale_bytes [+1 if asym])
+  const size_t bits = (w->wfmt == NS_W_S8) ? 8 : 4;
+  return (size_t)w->n * w->k * bits / 8 + (size_t)w->n * w->ngroups * (stype_size(w->stype) + (w->asym ? 1 : 0));
+}
+
+extern "C" ns_weight* ns_weight_from_q4_0(const void* rows, int n, int k, size_t nb01, int rows_on_device, void* queue) {
+  if (ns_ensure_device()) return nullptr;
+  if (!rows || n <= 0 || k <= 0 || k % 32 != 0 || nb01 < (size_t)k / 32 * 18) {
+    ns_set_error("ns_weight_from_q4_0: invalid arguments (n=%d k=%d nb01=%zu)", n, k, nb01);
+    return nullptr;
+  }
+  cudaStream_t st = stream_of(queue);
+  ns_weight* w = new ns_weight();
+  memset(w, 0, sizeof(*w));
+  w->n = n;
+  w->k = k;
+  w->group = 32;
+  w->wfmt = NS_W_S4;
+  w->stype = NS_S_F16;
+  w->comp = NS_COMP_Q8_0;
+  w->asym = 0;
+  weight_layout(w);
+  if (weight_alloc(w, false)) {
+    delete w;
+    return nullptr;
+  }
+  const void* src = rows;
+  void* tmp = nullptr;
+  if (!rows_on_device) {
+    const size_t bytes = (size_t)n * nb01;
+    if (!ns_cuda_ok(cudaMalloc(&tmp, bytes), "cudaMalloc(q4_0 staging)") ||
+        !ns_cuda_ok(cudaMemcpyAsync(tmp, rows, bytes, cudaMemcpyHostToDevice, st), "H2D q4_0 rows")) {
+      if (tmp) cudaFree(tmp);
+      ns_weight_free(w);
+      return nullptr;
+    }
+    src = tmp;
+  }
+  int rc = ns_launch_repack_q4_0(src, nb01, w, st);
+  if (tmp) {
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+  }
+  if (rc) {
+    ns_weight_free(w);
+    return nullptr;
+  }
+  return w;
+}
+
+extern "C" ns_weight* ns_weight_from_unpacked(const int8_t* q, const float* scales, const int8_t* zp, const int* shuffle,
+                                              int n, int k, int group, int wfmt, int stype, int comp, void* queue) {
+  if (ns_ensure_device()) return nullptr;
+  if (!q || !scales || n <= 0 || k <= 0 || wfmt < 0 || wfmt > NS_W_NF4 || stype < 0 || stype > NS_S_F16) {
+    ns_set_error("ns_weight_from_unpacked: invalid arguments");
+    return nullptr;
+  }
+  cudaStream_t st = stream_of(queue);
+  ns_weight* w = new ns_weight();
+  memset(w, 0, sizeof(*w));
+  w->n = n;
+  w->k = k;
+  w->group = group;
+  w->wfmt = wfmt;
+  w->stype = stype;
+  w->comp = comp;
+  w->asym = zp ? 1 : 0;
+  weight_layout(w);
+  if ((w->group % 32 != 0 && w->group != w->k) || (wfmt == NS_W_NF4 && !(comp == NS_COMP_F32 || comp == NS_COMP_BF16))) {
+    ns_set_error("ns_weight_from_unpacked: unsupported group %d / comp %d", group, comp);
+    delete w;
+    return nullptr;
+  }
+  if (weight_alloc(w, shuffle != nullptr)) {
+    delete w;
+    return nullptr;
+  }
+  const size_t qb = (size_t)k * n, sb = (size_t)w->ngroups * n * 4, zb = (size_t)w->ngroups * n;
+  char* tmp = nullptr;
+  const size_t tot = ns_round_up(qb, 256) + ns_round_up(sb, 256) + ns_round_up(zb, 256);
+  bool ok = ns_cuda_ok(cudaMalloc((void**)&tmp, tot), "cudaMalloc(staging)");
+  int8_t* dq = (int8_t*)tmp;
+  float* ds = (float*)(tmp + ns_round_up(qb, 256));
+  int8_t* dz = (int8_t*)(tmp + ns_round_up(qb, 256) + ns_round_up(sb, 256));
+  ok = ok && ns_cuda_ok(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, st), "H2D q");
+  ok = ok && ns_cuda_ok(cudaMemcpyAsync(ds, scales, sb, cudaMemcpyHostToDevice, st), "H2D scales");
+  if (zp) ok = ok && ns_cuda_ok(cudaMemcpyAsync(dz, zp, zb, cudaMemcpyHostToDevice, st), "H2D zp");
+  if (shuffle) ok = ok && ns_cuda_ok(cudaMemcpyAsync(w->shuffle, shuffle, (size_t)k * 4, cudaMemcpyHostToDevice, st), "H2D shuffle");
+  if (ok) ok = ns_launch_repack_canonical(dq, ds, zp ? dz : nullptr, w, st) == NS_OK;
+  cudaStreamSynchronize(st);
+  if (tmp) cudaFree(tmp);
+  if (!ok) {
+    ns_weight_free(w);
+    return nullptr;
+  }
+  return w;
+}
+
+// ---- serialized BesTLA blob (bestla/bestla/bestla_storage.h) -----------------------------------------------------------
+struct BlobView {
+  size_t size;
+  uint32_t prologue;
+  uint64_t core_id;
+  int npad, kpad, n, k;
+  uint32_t dtype;
+  int blocksize, dqblocksize;
+  const uint8_t* qbuf;
+  size_t qbytes;
+  uint32_t sca_t, zp_t, red_t;
+  int cstep;
+  size_t csize;
+  const uint8_t* scale;
+  size_t scale_bytes;
+  const uint8_t* zp;
+  size_t zp_bytes;
+  const uint8_t* red;
+  size_t red_bytes;
+  const uint8_t* dq;
+  size_t dq_bytes;
+  const int* shuffle;
+  size_t shuffle_bytes;
+  // derived
+  int ntile, packrow, comp_b, comp_a;
+};
+
+namespace {
+struct Reader {
+  const uint8_t* base;
+  const uint8_t* p;
+  const uint8_t* end;
+  bool ok = true;
+  template <typename T>
+  T get() {
+    T v{};
+    if (p + sizeof(T) > end) {
+      ok = false;
+      return v;
+    }
+    memcpy(&v, p, sizeof(T));
+    p += sizeof(T);
+    return v;
+  }
+  // ObjectAlignedBuffer<64>::deserializeBuffer (bestla_storage.h:98-110)
+  void aligned_buf(const uint8_t** data, size_t* bytes) {
+    const size_t sz = get<size_t>();
+    const size_t off = get<size_t>();
+    if (!ok || p + off + sz > end) {
+      ok = false;
+      return;
+    }
+    p += off;
+    *data = p;
+    *bytes = sz;
+    p += sz;
+  }
+  // ObjectOptionalBuffer<64> (bestla_storage.h:113-146): bool flag first
+  void optional_buf(const uint8_t** data, size_t* bytes) {
+    *data = nullptr;
+    *bytes = 0;
+    const uint8_t flag = get<uint8_t>();
+    if (ok && flag) aligned_buf(data, bytes);
+  }
+};
+}  // namespace
+
+static bool parse_blob(const void* blob, BlobView* v) {
+  if (!blob) return false;
+  memset(v, 0, sizeof(*v));
+  size_t msize;
+  memcpy(&msize, blob, sizeof(size_t));
+  if (msize < 64 || msize > ((size_t)1 << 40)) {
+    ns_set_error("blob: implausible size field %zu", msize);
+    return false;
+  }
+  Reader r{(const uint8_t*)blob, (const uint8_t*)blob, (const uint8_t*)blob + msize};
+  v->size = r.get<size_t>();
+  v->prologue = r.get<uint32_t>();
+  v->core_id = r.get<uint64_t>();
+  v->npad = r.get<int>();
+  v->kpad = r.get<int>();
+  v->n = r.get<int>();
+  v->k = r.get<int>();
+  v->dtype = r.get<uint32_t>();
+  v->blocksize = r.get<int>();
+  v->dqblocksize = r.get<int>();
+  if (!r.ok || (v->prologue != 1 && v->prologue != 2)) {  // BTLA_PROLOGUEB_IDS (bestla.h:91-102)
+    ns_set_error("blob: prologue id %u is not WeightKBlockNInteger/NFloat", v->prologue);
+    return false;
+  }
+  r.aligned_buf(&v->qbuf, &v->qbytes);
+  v->sca_t = r.get<uint32_t>();
+  v->zp_t = r.get<uint32_t>();
+  v->red_t = r.get<uint32_t>();
+  v->cstep = r.get<int>();
+  v->csize = r.get<size_t>();
+  r.aligned_buf(&v->scale, &v->scale_bytes);
+  r.optional_buf(&v->zp, &v->zp_bytes);
+  r.optional_buf(&v->red, &v->red_bytes);
+  r.optional_buf(&v->dq, &v->dq_bytes);
+  const uint8_t* sh = nullptr;
+  r.optional_buf(&sh, &v->shuffle_bytes);
+  v->shuffle = (const int*)sh;
+  if (!r.ok) {
+    ns_set_error("blob: truncated or corrupt (size field %zu)", msize);
+    return false;
+  }
+  // CoreAttr (bestla_gemm.h:83-125)
+  v->ntile = (int)(v->core_id & 0xff);
+  v->packrow = (int)((v->core_id >> 8) & 0xff);
+  const unsigned comp = (unsigned)((v->core_id >> 16) & 0xffff);
+  v->comp_a = comp & 0xf;
+  v->comp_b = (comp >> 4) & 0xf;
+  if (v->n <= 0 || v->k <= 0 || v->npad < v->n || v->kpad < v->k || v->ntile <= 0 ||
+      !(v->packrow == 1 || v->packrow == 2 || v->packrow == 4) || v->npad % v->ntile != 0) {
+    ns_set_error("blob: inconsistent header (N=%d K=%d NPad=%d KPad=%d NTile=%d PackRow=%d)", v->n, v->k, v->npad,
+                 v->kpad, v->ntile, v->packrow);
+    return false;
+  }
+  return true;
+}
+
+static int blob_to_weight_meta(const BlobView& v, ns_weight* w) {
+  memset(w, 0, sizeof(*w));
+  w->n = v.n;
+  w->k = v.k;
+  w->group = v.blocksize;
+  if (v.dtype == NS_BTLA_S4_CLIP) w->wfmt = NS_W_S4;
+  else if (v.dtype == NS_BTLA_S8) w->wfmt = NS_W_S8;
+  else if (v.dtype == NS_BTLA_F4_NF4) w->wfmt = NS_W_NF4;
+  else {
+    ns_set_error("blob: weight dtype 0x%x not supported (int4 / int8 / nf4 are)", v.dtype);
+    return NS_E_UNSUPPORTED;
+  }
+  if (v.sca_t == NS_BTLA_F32) w->stype = NS_S_F32;
+  else if (v.sca_t == NS_BTLA_BF16) w->stype = NS_S_BF16;
+  else if (v.sca_t == NS_BTLA_F16) w->stype = NS_S_F16;
+  else {
+    ns_set_error("blob: scale dtype 0x%x not supported (f32 / bf16 / f16 are)", v.sca_t);
+    return NS_E_UNSUPPORTED;
+  }
+  // CompType B: tFP32=0 tBF16=1 tFP16=2 tS8=3 tU8=4 ; A: tU8=4 / tS8=3 (bestla_gemm.h:22-49)
+  if (v.comp_b == 0) w->comp = NS_COMP_F32;
+  else if (v.comp_b == 1) w->comp = NS_COMP_BF16;
+  else if (v.comp_b == 2) w->comp = NS_COMP_F32;  // fp16 compute cores: evaluated in fp32 here (superset precision)
+  else if (v.comp_b == 3 || v.comp_b == 4) w->comp = (v.comp_a == 3) ? NS_COMP_INT8_S8 : NS_COMP_INT8;
+  else {
+    ns_set_error("blob: compute type %d not supported", v.comp_b);
+    return NS_E_UNSUPPORTED;
+  }
+  if (w->wfmt == NS_W_NF4 && !(w->comp == NS_COMP_F32 || w->comp == NS_COMP_BF16)) w->comp = NS_COMP_F32;
+  w->asym = v.zp ? 1 : 0;
+  weight_layout(w);
+  if (w->group % 32 != 0 && w->group != w->k) {
+    ns_set_error("blob: block size %d is not a multiple of 32", w->group);
+    return NS_E_UNSUPPORTED;
+  }
+  const size_t need_q = (size_t)v.npad * v.kpad * (w->wfmt == NS_W_S8 ? 2 : 1) / 2;
+  const int ngroups_src = (v.kpad + v.blocksize - 1) / v.blocksize;
+  if (v.qbytes < need_q || v.scale_bytes < (size_t)ngroups_src * v.cstep * stype_size(w->stype) || v.cstep < v.n ||
+      (v.zp && v.zp_bytes < (size_t)ngroups_src * v.cstep) || (v.shuffle && v.shuffle_bytes < (size_t)v.k * 4)) {
+    ns_set_error("blob: buffer sizes do not match the header");
+    return NS_E_INVALID;
+  }
+  return NS_OK;
+}
+
+// upload the pieces of a blob and repack into w (whose device pointers are already carved)
+static int blob_upload_repack(const BlobView& v, ns_weight* w, cudaStream_t st) {
+  const size_t qb = ns_round_up(v.qbytes, 256), sb = ns_round_up(v.scale_bytes, 256), zb = ns_round_up(v.zp_bytes, 256);
+  char* tmp = nullptr;
+  NS_CUDA_TRY(cudaMalloc((void**)&tmp, qb + sb + zb + 256));
+  bool ok = ns_cuda_ok(cudaMemcpyAsync(tmp, v.qbuf, v.qbytes, cudaMemcpyHostToDevice, st), "H2D qbuf");
+  ok = ok && ns_cuda_ok(cudaMemcpyAsync(tmp + qb, v.scale, v.scale_bytes, cudaMemcpyHostToDevice, st), "H2D scales");
+  if (v.zp) ok = ok && ns_cuda_ok(cudaMemcpyAsync(tmp + qb + sb, v.zp, v.zp_bytes, cudaMemcpyHostToDevice, st), "H2D zp");
+  if (v.shuffle && w->shuffle)
+    ok = ok && ns_cuda_ok(cudaMemcpyAsync(w->shuffle, v.shuffle, (size_t)v.k * 4, cudaMemcpyHostToDevice, st), "H2D shuffle");
+  int rc = NS_E_CUDA;
+  if (ok)
+    rc = ns_launch_repack_btla(tmp, tmp + qb, w->stype, v.zp ? (const int8_t*)(tmp + qb + sb) : nullptr, v.cstep, v.kpad,
+                               v.ntile, v.packrow, w->wfmt == NS_W_NF4, w, st);
+  cudaStreamSynchronize(st);
+  cudaFree(tmp);
+  return rc;
+}
+
+extern "C" ns_weight* ns_weight_from_btla_blob(const void* blob, void* queue) {
+  if (ns_ensure_device()) return nullptr;
+  BlobView v;
+  if (!parse_blob(blob, &v)) return nullptr;
+  ns_weight* w = new ns_weight();
+  if (blob_to_weight_meta(v, w) || weight_alloc(w, v.shuffle != nullptr)) {
+    delete w;
+    return nullptr;
+  }
+  if (blob_upload_repack(v, w, stream_of(queue))) {
+    ns_weight_free(w);
+    return nullptr;
+  }
+  return w;
+}
+
+extern "C" int ns_weight_dequant_f32(const ns_weight* w, float* dst_dev, int ld, void* queue) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!w || !dst_dev || ld < w->k) return NS_E_INVALID;
+  return ns_launch_dequant(w, dst_dev, ld, stream_of(queue));
+}
+
+// ---------------------------------------------------------------------------------------------------- device matmuls
+extern "C" size_t ns_device_workspace_bytes(int m, int k) {
+  const int kpad = (int)ns_round_up((size_t)k, 32);
+  (void)m;
+  return ns_act_workspace_bytes(4, kpad);  // activations are prepared in tiles of <= 4 rows
+}
+
+static void* pick_ws(void* workspace, cudaStream_t st, size_t bytes) { return workspace ? workspace : scratch_get(st, bytes); }
+
+extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* bias,
+                          const float* residual, int flags, void* workspace, void* queue) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!w || !act || !dst || m <= 0 || lda < w->k || ldo < w->n) {
+    ns_set_error("ns_mul_mat: invalid arguments (m=%d lda=%d ldo=%d)", m, lda, ldo);
+    return NS_E_INVALID;
+  }
+  cudaStream_t st = stream_of(queue);
+  void* ws = pick_ws(workspace, st, ns_act_workspace_bytes(4, w->kpad));
+  if (!ws) return NS_E_CUDA;
+  const int tile = ns_gemv_tile_rows(w);
+  const int bcast = (flags & NS_MM_BIAS_BCAST) ? 1 : 0;
+  for (int m0 = 0; m0 < m; m0 += tile) {
+    const int mt = (m - m0 < tile) ? (m - m0) : tile;
+    if (int rc = ns_launch_act_prep(act + (size_t)m0 * lda, lda, mt, w, ws, st)) return rc;
+    if (int rc = ns_launch_gemv(&w, 1, NS_GEMV_PLAIN, ws, dst + (size_t)m0 * ldo, ldo, mt, m,
+                                bias ? (bcast ? bias : bias + (size_t)m0 * ldo) : nullptr, bcast,
+                                residual ? residual + (size_t)m0 * ldo : nullptr, nullptr, st))
+      return rc;
+  }
+  return NS_OK;
+}
+
+extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_weight* wv, const float* act, int lda,
+                          float* dst, int ldo, int m, void* workspace, void* queue) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!wq || !wk || !wv || !act || !dst || m <= 0) return NS_E_INVALID;
+  cudaStream_t st = stream_of(queue);
+  void* ws = pick_ws(workspace, st, ns_act_workspace_bytes(4, wq->kpad));
+  if (!ws) return NS_E_CUDA;
+  const ns_weight* wl[3] = {wq, wk, wv};
+  const int tile = ns_gemv_tile_rows(wq);
+  for (int m0 = 0; m0 < m; m0 += tile) {
+    const int mt = (m - m0 < tile) ? (m - m0) : tile;
+    if (int rc = ns_launch_act_prep(act + (size_t)m0 * lda, lda, mt, wq, ws, st)) return rc;
+    if (int rc = ns_launch_gemv(wl, 3, NS_GEMV_CONCAT, ws, dst + (size_t)m0 * ldo, ldo, mt, m, nullptr, 0, nullptr,
+                                nullptr, st))
+      return rc;
+  }
+  return NS_OK;
+}
+
+extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda,
+                           float* tmp, float* dst, int ldo, int m, void* workspace, void* queue) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!w1 || !w2 || !w3 || !act || !tmp || !dst || m <= 0 || w2->k != w1->n) return NS_E_INVALID;
+  cudaStream_t st = stream_of(queue);
+  const int kmax = w1->kpad > w2->kpad ? w1->kpad : w2->kpad;
+  void* ws = pick_ws(workspace, st, ns_act_workspace_bytes(4, kmax));
+  if (!ws) return NS_E_CUDA;
+  const ns_weight* gu[2] = {w1, w3};
+  const int fmid = w1->n;
+  int tile = ns_gemv_tile_rows(w1);
+  for (int m0 = 0; m0 < m; m0 += tile) {
+    const int mt = (m - m0 < tile) ? (m - m0) : tile;
+    if (int rc = ns_launch_act_prep(act + (size_t)m0 * lda, lda, mt, w1, ws, st)) return rc;
+    if (int rc = ns_launch_gemv(gu, 2, NS_GEMV_GATE_UP_SILU, ws, tmp + (size_t)m0 * fmid, fmid, mt, m, nullptr, 0, nullptr,
+                                nullptr, st))
+      return rc;
+  }
+  tile = ns_gemv_tile_rows(w2);
+  for (int m0 = 0; m0 < m; m0 += tile) {
+    const int mt = (m - m0 < tile) ? (m - m0) : tile;
+    if (int rc = ns_launch_act_prep(tmp + (size_t)m0 * fmid, fmid, mt, w2, ws, st)) return rc;
+    if (int rc = ns_launch_gemv(&w2, 1, NS_GEMV_PLAIN, ws, dst + (size_t)m0 * ldo, ldo, mt, m, nullptr, 0, nullptr, nullptr,
+                                st))
+      return rc;
+  }
+  return NS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- device set
+extern "C" void bestla_init(void) { (void)ns_ensure_device(); }
+extern "C" int bestla_set_threads(int nth) { return nth; }
+extern "C" void* bestla_get_thread_handle(void) { return nullptr; }
+extern "C" void bestla_timer(bool) {}
+
+extern "C" void* bestla_create_device(bool profile) {
+  if (ns_ensure_device()) ns_fatal("bestla_create_device: %s", g_err);
+  ns_device* d = new ns_device();
+  d->dev = g_default.dev;
+  d->profile = profile;
+  if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) ns_fatal("cudaStreamCreate failed");
+  return d;
+}
+extern "C" void* bestla_get_device_queue(void* device) { return device ? (void*)((ns_device*)device)->stream : nullptr; }
+extern "C" void bestla_release_device(void* device) {
+  if (!device) return;
+  ns_device* d = (ns_device*)device;
+  cudaStreamSynchronize(d->stream);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_scratch.find(d->stream);
+    if (it != g_scratch.end()) {
+      cudaFree(it->second.p);
+      g_scratch.erase(it);
+    }
+  }
+  cudaStreamDestroy(d->stream);
+  delete d;
+}
+extern "C" size_t bestla_device_gmem_size(void* device) {
+  (void)device;
+  if (ns_ensure_device()) return 0;
+  size_t fr = 0, tot = 0;
+  cudaMemGetInfo(&fr, &tot);
+  return tot;
+}
+extern "C" void* bestla_device_malloc(size_t size, void* queue) {
+  (void)queue;
+  if (ns_ensure_device()) ns_fatal("bestla_device_malloc: %s", g_err);
+  void* p = nullptr;
+  if (cudaMalloc(&p, size) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void bestla_device_free(void* ptr, void* queue) {
+  if (!ptr) return;
+  cudaStreamSynchronize(stream_of(queue));
+  cudaFree(ptr);
+}
+extern "C" void bestla_device_memcpy(void* dstptr, const void* srcptr, size_t size, void* queue) {
+  if (ns_ensure_device()) ns_fatal("bestla_device_memcpy: %s", g_err);
+  if (cudaMemcpyAsync(dstptr, srcptr, size, cudaMemcpyDefault, stream_of(queue)) != cudaSuccess)
+    ns_fatal("bestla_device_memcpy failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
+extern "C" void bestla_device_memcpy_sync(void* dstptr, const void* srcptr, size_t size, void* queue) {
+  bestla_device_memcpy(dstptr, srcptr, size, queue);
+  cudaStreamSynchronize(stream_of(queue));
+}
+extern "C" void bestla_device_sync(void* queue) {
+  if (ns_ensure_device()) ns_fatal("bestla_device_sync: %s", g_err);
+  if (cudaStreamSynchronize(stream_of(queue)) != cudaSuccess)
+    ns_fatal("bestla_device_sync: %s", cudaGetErrorString(cudaGetLastError()));
+}
+extern "C" size_t bestla_device_storage_size(void) { return sizeof(ns_weight); }
+extern "C" size_t ns_device_storage_bytes(const void* hoststor) {
+  BlobView v;
+  ns_weight w;
+  if (!parse_blob(hoststor, &v) || blob_to_weight_meta(v, &w)) return 0;
+  return weight_image_bytes(&w, v.shuffle != nullptr);
+}
+extern "C" void bestla_device_load_storage(void* hoststor, void* devstor, void* deviceptr, void* queue) {
+  if (ns_ensure_device()) ns_fatal("bestla_device_load_storage: %s", g_err);
+  BlobView v;
+  ns_weight* w = (ns_weight*)devstor;
+  if (!devstor || !deviceptr || !parse_blob(hoststor, &v) || blob_to_weight_meta(v, w))
+    ns_fatal("bestla_device_load_storage: invalid parameters (%s)", g_err);
+  w->base = deviceptr;
+  w->external = 1;
+  w->total_bytes = weight_image_bytes(w, v.shuffle != nullptr);
+  weight_carve(w, deviceptr, v.shuffle != nullptr);
+  if (blob_upload_repack(v, w, stream_of(queue))) ns_fatal("bestla_device_load_storage: %s", g_err);
+}
+extern "C" void bestla_device_f32f32_forward(float* activation, void* weiptr, float* output, int m, int n, int k, int lda,
+                                             int ldo, void* workspace, void* queue) {
+  const ns_weight* w = (const ns_weight*)weiptr;
+  if (!w || w->n != n || w->k != k) ns_fatal("invalid parameters");
+  (void)lda;  // the reference ignores lda and uses K (bestla_gemm.cpp:44,95)
+  if (ns_mul_mat(w, activation, k, output, ldo, m, nullptr, nullptr, 0, workspace, queue))
+    ns_fatal("bestla_device_f32f32_forward: %s", g_err);
+}
+
+// ---------------------------------------------------------------------------------------------------- host drop-ins
+// Host blobs / ggml rows are uploaded and repacked once and cached by address (weights are immutable for the lifetime of
+// the model context in the reference: model_files.h:1490-1499).
+struct CacheEntry {
+  ns_weight* w;
+  size_t tag;
+};
+static std::unordered_map<const void*, CacheEntry> g_cache;
+
+static size_t blob_tag(const void* blob) {
+  // cheap identity check so a recycled address with a different tensor is re-uploaded
+  size_t t = 1469598103934665603ull;
+  const unsigned char* p = (const unsigned char*)blob;
+  for (int i = 0; i < 64; ++i) t = (t ^ p[i]) * 1099511628211ull;
+  return t;
+}
+
+static const ns_weight* cached_blob(const void* blob) {
+  if (ns_ensure_device()) ns_fatal("%s", g_err);
+  const size_t tag = blob_tag(blob);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_cache.find(blob);
+    if (it != g_cache.end() && it->second.tag == tag) return it->second.w;
+  }
+  ns_weight* w = ns_weight_from_btla_blob(blob, nullptr);
+  if (!w) return nullptr;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_cache.find(blob);
+  if (it != g_cache.end()) ns_weight_free(it->second.w);
+  g_cache[blob] = CacheEntry{w, tag};
+  return w;
+}
+
+struct HostIO {  // device staging for host-buffer calls
+  float* act = nullptr;
+  float* out = nullptr;
+  float* tmp = nullptr;
+  size_t act_elems = 0, out_elems = 0, tmp_elems = 0;
+};
+static HostIO g_io;
+static bool io_reserve(float** p, size_t* have, size_t need) {
+  if (*have >= need) return true;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *have = 0;
+  if (cudaMalloc((void**)p, need * sizeof(float)) != cudaSuccess) return false;
+  *have = need;
+  return true;
+}
+
+extern "C" unsigned long long bestla_f32f32_get_workspace_size(int m, int n, int k, void* wptr) {
+  (void)n;
+  (void)wptr;
+  return (unsigned long long)m * ns_round_up((size_t)k, 128) * 4;  // inner_product.cpp:20-25
+}
+
+static void host_forward(float* activation, const ns_weight* w, float* bias, bool bias_bcast, float* output, int m, int n,
+                         int k, int ldo) {
+  cudaStream_t st = default_stream();
+  if (!io_reserve(&g_io.act, &g_io.act_elems, (size_t)m * k) || !io_reserve(&g_io.out, &g_io.out_elems, (size_t)m * n + (bias ? (size_t)m * n : 0)))
+    ns_fatal("device staging allocation failed");
+  float* dbias = nullptr;
+  if (cudaMemcpyAsync(g_io.act, activation, (size_t)m * k * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) ns_fatal("H2D failed");
+  if (bias) {
+    dbias = g_io.out + (size_t)m * n;
+    const size_t nb = bias_bcast ? (size_t)n : (size_t)m * n;
+    if (bias_bcast) {
+      cudaMemcpyAsync(dbias, bias, nb * 4, cudaMemcpyHostToDevice, st);
+    } else {
+      cudaMemcpy2DAsync(dbias, (size_t)n * 4, bias, (size_t)ldo * 4, (size_t)n * 4, m, cudaMemcpyHostToDevice, st);
+    }
+  }
+  if (ns_mul_mat(w, g_io.act, k, g_io.out, n, m, dbias, nullptr, bias_bcast ? NS_MM_BIAS_BCAST : 0, nullptr, st))
+    ns_fatal("%s", g_err);
+  if (cudaMemcpy2DAsync(output, (size_t)ldo * 4, g_io.out, (size_t)n * 4, (size_t)n * 4, m, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    ns_fatal("D2H failed");
+  if (cudaStreamSynchronize(st) != cudaSuccess) ns_fatal("kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
+
+extern "C" void bestla_f32f32_forward(float* activation, void* weiptr, float* output, int m, int n, int k, int lda, int ldo,
+                                      void* workspace) {
+  (void)lda;
+  (void)workspace;
+  const ns_weight* w = cached_blob(weiptr);
+  if (!w || w->n != n || w->k != k || !activation || !output || m <= 0 || ldo < n) {
+    printf("Err: invalid parameters\n");
+    ns_fatal("bestla_f32f32_forward(m=%d n=%d k=%d): %s", m, n, k, g_err);
+  }
+  host_forward(activation, w, nullptr, false, output, m, n, k, ldo);
+}
+
+extern "C" bool bestla_fusion_add_f32f32_support(void* weiptr, int m, int n, int k) {
+  (void)m;
+  BlobView v;
+  ns_weight w;
+  return parse_blob(weiptr, &v) && blob_to_weight_meta(v, &w) == NS_OK && v.n == n && v.k == k;
+}
+extern "C" void bestla_fusion_add_f32f32_forward(float* activation, void* weiptr, float* bias, float* output, int m, int n,
+                                                 int k, int lda, int ldo, bool boardcast_bias, void* workspace) {
+  (void)lda;
+  (void)workspace;
+  const ns_weight* w = cached_blob(weiptr);
+  if (!w || w->n != n || w->k != k || !activation || !output || !bias) ns_fatal("invalid parameters (%s)", g_err);
+  host_forward(activation, w, bias, boardcast_bias, output, m, n, k, ldo);
+}
+
+extern "C" unsigned long long bestla_fusion_QKV_f32f32_get_workspace_size(int m, int n, int k, void* w1ptr) {
+  return bestla_f32f32_get_workspace_size(m, n, k, w1ptr);  // ip_fusion_qkv.cpp:155-161
+}
+extern "C" bool bestla_fusion_QKV_f32f32_support(void* wqptr, void* wkptr, void* wvptr, int m, int n, int k) {
+  (void)m;
+  BlobView v[3];
+  ns_weight w[3];
+  void* ptrs[3] = {wqptr, wkptr, wvptr};
+  for (int i = 0; i < 3; ++i) {
+    if (!parse_blob(ptrs[i], &v[i]) || blob_to_weight_meta(v[i], &w[i]) != NS_OK) return false;
+    if (v[i].n != n || v[i].k != k) return false;
+    // same core / prologue for all three and no activation shuffle (ip_fusion_qkv.cpp:170-186)
+    if (v[i].core_id != v[0].core_id || v[i].prologue != v[0].prologue || v[i].shuffle) return false;
+    if (w[i].group != w[0].group || w[i].wfmt != w[0].wfmt || w[i].stype != w[0].stype || w[i].asym != w[0].asym) return false;
+  }
+  return (n % 2) == 0;
+}
+extern "C" void bestla_fusion_QKV_f32f32_forward(float* activation, void* wqptr, void* wkptr, void* wvptr, float* output,
+                                                 int m, int n, int k, int lda, int ldo, void* workspace) {
+  (void)lda;
+  (void)workspace;
+  const ns_weight* wq = cached_blob(wqptr);
+  const ns_weight* wk = cached_blob(wkptr);
+  const ns_weight* wv = cached_blob(wvptr);
+  if (!wq || !wk || !wv || wq->n != n || wq->k != k) ns_fatal("invalid parameters (%s)", g_err);
+  cudaStream_t st = default_stream();
+  if (!io_reserve(&g_io.act, &g_io.act_elems, (size_t)m * k) || !io_reserve(&g_io.out, &g_io.out_elems, (size_t)3 * m * ldo))
+    ns_fatal("device staging allocation failed");
+  cudaMemcpyAsync(g_io.act, activation, (size_t)m * k * 4, cudaMemcpyHostToDevice, st);
+  if (ns_mul_qkv(wq, wk, wv, g_io.act, k, g_io.out, ldo, m, nullptr, st)) ns_fatal("%s", g_err);
+  cudaMemcpyAsync(output, g_io.out, (size_t)3 * m * ldo * 4, cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) ns_fatal("kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
+
+extern "C" unsigned long long bestla_fusion_FFN_f32f32_get_workspace_size(int seq, int fin, int fmid, int fout, void* w1ptr,
+                                                                          void* w2ptr) {
+  (void)fout;
+  (void)w1ptr;
+  (void)w2ptr;
+  const int kmax = fin > fmid ? fin : fmid;
+  return (unsigned long long)seq * ns_round_up((size_t)kmax, 128) * 4;
+}
+extern "C" bool bestla_fusion_FFN_SiLu_f32f32_support(void* w1ptr, void* w2ptr, void* w3ptr, int seq, int fin, int fmid,
+                                                      int fout) {
+  (void)seq;
+  BlobView v[3];
+  ns_weight w[3];
+  void* ptrs[3] = {w1ptr, w2ptr, w3ptr};
+  for (int i = 0; i < 3; ++i)
+    if (!parse_blob(ptrs[i], &v[i]) || blob_to_weight_meta(v[i], &w[i]) != NS_OK || v[i].shuffle) return false;
+  if (v[0].n != fmid || v[0].k != fin || v[2].n != fmid || v[2].k != fin || v[1].n != fout || v[1].k != fmid) return false;
+  if (v[0].core_id != v[2].core_id || v[0].core_id != v[1].core_id) return false;
+  return w[0].group == w[2].group && w[0].wfmt == w[2].wfmt && w[0].stype == w[2].stype && w[0].asym == w[2].asym;
+}
+extern "C" void bestla_fusion_FFN_SiLu_f32f32_forward(float* activation, void* w1ptr, void* w2ptr, void* w3ptr, float* tmp1,
+                                                      float* tmp2, float* output, int seq, int fin, int fmid, int fout,
+                                                      void* workspace) {
+  (void)workspace;
+  (void)tmp1;
+  const ns_weight* w1 = cached_blob(w1ptr);
+  const ns_weight* w2 = cached_blob(w2ptr);
+  const ns_weight* w3 = cached_blob(w3ptr);
+  if (!w1 || !w2 || !w3 || w1->n != fmid || w1->k != fin || w2->n != fout || w2->k != fmid) ns_fatal("invalid parameters (%s)", g_err);
+  cudaStream_t st = default_stream();
+  if (!io_reserve(&g_io.act, &g_io.act_elems, (size_t)seq * fin) || !io_reserve(&g_io.out, &g_io.out_elems, (size_t)seq * fout) ||
+      !io_reserve(&g_io.tmp, &g_io.tmp_elems, (size_t)seq * fmid))
+    ns_fatal("device staging allocation failed");
+  cudaMemcpyAsync(g_io.act, activation, (size_t)seq * fin * 4, cudaMemcpyHostToDevice, st);
+  if (ns_ffn_silu(w1, w2, w3, g_io.act, fin, g_io.tmp, g_io.out, fout, seq, nullptr, st)) ns_fatal("%s", g_err);
+  cudaMemcpyAsync(output, g_io.out, (size_t)seq * fout * 4, cudaMemcpyDeviceToHost, st);
+  if (tmp2) cudaMemcpyAsync(tmp2, g_io.tmp, (size_t)seq * fmid * 4, cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) ns_fatal("kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
+
+extern "C" void bestla_unpackweight_fp32(void* wptr, int n, int k, float* fp32data, int ld) {
+  const ns_weight* w = cached_blob(wptr);
+  if (!w || w->n != n || w->k != k || ld < k) ns_fatal("bestla_unpackweight_fp32: invalid parameters (%s)", g_err);
+  cudaStream_t st = default_stream();
+  float* d = nullptr;
+  if (cudaMalloc((void**)&d, (size_t)n * k * 4) != cudaSuccess) ns_fatal("cudaMalloc failed");
+  if (ns_launch_dequant(w, d, k, st)) ns_fatal("%s", g_err);
+  cudaMemcpy2DAsync(fp32data, (size_t)ld * 4, d, (size_t)k * 4, (size_t)k * 4, n, cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  cudaFree(d);
+}
+
+// ggml host drop-in
+extern "C" int ns_mul_mat_q4_0_f32_host(const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01,
+                                        int ne11) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!src0_rows || !src1 || !dst || ne00 % 32 != 0 || ne01 <= 0 || ne11 <= 0) {
+    ns_set_error("ns_mul_mat_q4_0_f32_host: invalid arguments");
+    return NS_E_INVALID;
+  }
+  const ns_weight* w = nullptr;
+  {
+    const size_t tag = blob_tag(src0_rows) ^ ((size_t)ne00 << 32) ^ (size_t)ne01;
+    std::unique_lock<std::mutex> lk(g_mu);
+    auto it = g_cache.find(src0_rows);
+    if (it != g_cache.end() && it->second.tag == tag) {
+      w = it->second.w;
+    } else {
+      lk.unlock();
+      ns_weight* nw = ns_weight_from_q4_0(src0_rows, ne01, ne00, nb01, 0, nullptr);
+      if (!nw) return NS_E_CUDA;
+      lk.lock();
+      auto it2 = g_cache.find(src0_rows);
+      if (it2 != g_cache.end()) ns_weight_free(it2->second.w);
+      g_cache[src0_rows] = CacheEntry{nw, tag};
+      w = nw;
+    }
+  }
+  cudaStream_t st = default_stream();
+  if (!io_reserve(&g_io.act, &g_io.act_elems, (size_t)ne11 * ne00) || !io_reserve(&g_io.out, &g_io.out_elems, (size_t)ne11 * ne01)) {
+    ns_set_error("device staging allocation failed");
+    return NS_E_CUDA;
+  }
+  NS_CUDA_TRY(cudaMemcpyAsync(g_io.act, src1, (size_t)ne11 * ne00 * 4, cudaMemcpyHostToDevice, st));
+  if (int rc = ns_mul_mat(w, g_io.act, ne00, g_io.out, ne01, ne11, nullptr, nullptr, 0, nullptr, st)) return rc;
+  NS_CUDA_TRY(cudaMemcpyAsync(dst, g_io.out, (size_t)ne11 * ne01 * 4, cudaMemcpyDeviceToHost, st));
+  NS_CUDA_TRY(cudaStreamSynchronize(st));
+  return NS_OK;
+}

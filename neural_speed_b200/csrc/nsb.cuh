@@ -1,0 +1,127 @@
+// nsb.cuh -- internal definitions shared by the CUDA sources of libns_b200.so (sm_100a only).
+//
+// Device ("NSB") weight layout, chosen for B200 (see DESIGN.md "Data layout in HBM"):
+//   q plane   [N][kpad/2] bytes (4-bit formats) or [N][kpad] bytes (8-bit); kpad = roundup(K, 32); rows 16-B aligned.
+//             4-bit: every 32-bit word holds 8 consecutive k (k0..k0+7); nibble position p (bits 4p..4p+3) holds
+//             element k0 + NSB4_PERM[p], NSB4_PERM = {0,2,4,6,1,3,5,7}.  Hence (w >> 4j) & 0x000F000F yields
+//             elements (2j, 2j+1) in the (low, high) half-words -- one op per bf16x2 pair for the tensor-core
+//             dequant -- and w & 0x0F0F0F0F / (w>>4) & 0x0F0F0F0F yield bytes (e0,e4,e1,e5) / (e2,e6,e3,e7) for dp4a
+//             against activations stored in the same permuted order.  Stored nibble u = q + 8 (ints) or the NF4 code.
+//   scales    [N][ngroups] (f32 | bf16 | f16), ngroups = ceil(K / group): K-groups of one row are contiguous.
+//   zp        [N][ngroups] int8 (asymmetric only), value semantics w = (u - 8 - zp) * scale.
+//   shuffle   [K] int32 (GPTQ desc_act): activation column gather applied before activation quantisation.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/ns_b200.h"
+
+struct ns_weight {
+  int n, k, kpad;
+  int group, ngroups;
+  int wfmt, stype, comp, asym;
+  uint8_t* q;
+  void* scales;
+  int8_t* zp;
+  int* shuffle;
+  size_t row_bytes;   // bytes per row of the q plane
+  void* base;         // allocation owning q/scales/zp/shuffle (NULL if external)
+  size_t total_bytes; // bytes of the device image
+  int external;       // 1: memory supplied by caller (bestla_device_load_storage)
+};
+
+// ---- error handling -------------------------------------------------------------------------------------------------
+void ns_set_error(const char* fmt, ...);
+[[noreturn]] void ns_fatal(const char* fmt, ...);
+bool ns_cuda_ok(cudaError_t e, const char* what);
+int ns_ensure_device();  // 0 ok, <0 NS_E_*
+void ns_count_launch(int n = 1);
+
+#define NS_CUDA_TRY(expr)                          \
+  do {                                             \
+    if (!ns_cuda_ok((expr), #expr)) return NS_E_CUDA; \
+  } while (0)
+
+static inline size_t ns_round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---- activation workspace layout (device scratch used between act_prep and the matmul kernels) -----------------------
+// int8 modes : aq  [m][kpad] bytes   then  meta [m][kpad/32] int2 {float bits of a_scale, (Sa & 0xffff) | za << 16}
+// fp32 modes : af  [m][kpad] float
+// bf16 GEMM  : ab  [m][kpad] bf16
+struct ns_act_view {
+  const uint8_t* aq;
+  const int2* meta;
+  const float* af;
+  int kpad;
+};
+
+size_t ns_act_workspace_bytes(int m, int kpad);
+
+// launchers implemented in the .cu files
+int ns_launch_act_prep(const float* act, int lda, int m, const ns_weight* w, void* ws, cudaStream_t st);
+int ns_gemv_tile_rows(const ns_weight* w);
+int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* act_ws, float* dst, int ldo, int m,
+                   int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st);
+int ns_launch_repack_q4_0(const void* rows_dev, size_t nb01, ns_weight* w, cudaStream_t st);
+int ns_launch_repack_canonical(const int8_t* q_kn_dev, const float* sc_dev, const int8_t* zp_dev, ns_weight* w,
+                               cudaStream_t st);
+int ns_launch_repack_btla(const void* qbuf_dev, const void* sc_dev, int src_stype, const int8_t* zp_dev, int cstep,
+                          int kpad_src, int ntile, int packrow, int is_float, ns_weight* w, cudaStream_t st);
+int ns_launch_dequant(const ns_weight* w, float* dst, int ld, cudaStream_t st);
+
+enum { NS_GEMV_PLAIN = 0, NS_GEMV_CONCAT = 1, NS_GEMV_GATE_UP_SILU = 2 };
+
+// ---- small device helpers --------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ float ns_load_scale(const void* s, int stype, size_t idx) {
+  if (stype == NS_S_F32) return __ldg(reinterpret_cast<const float*>(s) + idx);
+  if (stype == NS_S_F16) return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(s) + idx)));
+  return __uint_as_float(static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(s) + idx)) << 16);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int dp4a_uu(unsigned a, unsigned b, int c) {
+  int d;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp4a_ss(int a, int b, int c) {
+  int d;
+  asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// NF4 levels by the reference's code (kernel_ref.h:1325-1368; code 0 <-> 0.0, code 7 <-> -1.0)
+static __device__ __constant__ const float NS_NF4_LUT[16] = {0.f,
+                                                      -0.6961928009986877f,
+                                                      -0.5250730514526367f,
+                                                      -0.39491748809814453f,
+                                                      -0.28444138169288635f,
+                                                      -0.18477343022823334f,
+                                                      -0.09105003625154495f,
+                                                      -1.f,
+                                                      0.07958029955625534f,
+                                                      0.16093020141124725f,
+                                                      0.24611230194568634f,
+                                                      0.33791524171829224f,
+                                                      0.44070982933044434f,
+                                                      0.5626170039176941f,
+                                                      0.7229568362236023f,
+                                                      1.0f};
+#endif
