@@ -54,12 +54,6 @@ EXPORTS = [
 _lib = None
 
 
-def build(force: bool = False) -> str:
-    from . import build as _b
-
-    return _b.build(force=force)
-
-
 def lib() -> C.CDLL:
     """Load libns_b200.so; raises if it has not been built (no silent fallback)."""
     global _lib

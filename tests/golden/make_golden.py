@@ -1,0 +1,59 @@
+"""Generate tests/golden/*.npz from the REFERENCE's own code (oracle/_ref/*.so = /root/reference compiled in place).
+
+Run in the authoring container (needs /root/reference):  python tests/golden/make_golden.py
+The fixtures travel with the repo; the GPU box never sees /root/reference.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    assert oracle.ref_ggml() is not None and oracle.ref_btla() is not None, "needs oracle/_ref (build with /root/reference)"
+    rng = np.random.default_rng(1234)  # seed borrowed from the reference CI (--seed 1234)
+
+    # ---- ggml Q4_0 x Q8_0: ne_compute_forward_mul_mat_q_f32 on a small problem, M in {1, 5}
+    N, K, M = 64, 512, 5
+    w = rng.normal(0, 0.02, (N, K)).astype(np.float32)
+    a = rng.normal(0, 1.0, (M, K)).astype(np.float32)
+    a[1, :32] = 0.0
+    wq = oracle.quantize_q4_0(w, "ref")
+    aq = oracle.quantize_q8_0(a, "ref", "runtime")
+    out = oracle.mul_mat_q4_0_f32(wq, a, "ref", nth=1)
+    np.savez_compressed(os.path.join(HERE, "ggml_q4_0.npz"), w=w, a=a, wq=wq, aq=aq, out=out,
+                        wdq=oracle.dequantize_q4_0(wq, K, "ref"))
+
+    # ---- BesTLA: RTN quantiser, activation quantisers, NF4 (kernel_ref.h)
+    K2, N2, M2 = 256, 48, 4
+    w2 = rng.uniform(-0.5, 0.5, (K2, N2)).astype(np.float32)
+    w2[:, 1] = np.abs(w2[:, 1])
+    a2 = rng.uniform(-0.5, 0.5, (M2, K2)).astype(np.float32)
+    d = dict(w=w2, a=a2)
+    for g in (32, 128):
+        for asym in (False, True):
+            q, sc, zp = oracle.btla_quantize(w2, g, 4, asym, "ref")
+            d[f"s4_g{g}_{'asym' if asym else 'sym'}_q"] = q
+            d[f"s4_g{g}_{'asym' if asym else 'sym'}_sc"] = sc
+            if asym:
+                d[f"s4_g{g}_asym_zp"] = zp
+        q8, sc8, _ = oracle.btla_quantize(w2, g, 8, False, "ref")
+        d[f"s8_g{g}_q"], d[f"s8_g{g}_sc"] = q8, sc8
+        qn, scn = oracle.btla_quantize_nf4(w2, g, "ref")
+        d[f"nf4_g{g}_q"], d[f"nf4_g{g}_sc"] = qn, scn
+        au, asu, azu = oracle.btla_quantize_act_u8(a2, g, "ref")
+        d[f"act_u8_g{g}_q"], d[f"act_u8_g{g}_sc"], d[f"act_u8_g{g}_zp"] = au, asu, azu
+        as8, ass = oracle.btla_quantize_act_s8(a2, g, "ref")
+        d[f"act_s8_g{g}_q"], d[f"act_s8_g{g}_sc"] = as8, ass
+    np.savez_compressed(os.path.join(HERE, "btla_quant.npz"), **d)
+    print("wrote", sorted(os.listdir(HERE)))
+
+
+if __name__ == "__main__":
+    main()
