@@ -156,6 +156,24 @@ NS_API int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_weight*
 NS_API int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda, float* tmp,
                        float* dst, int ldo, int m, void* workspace, void* queue);
 
+/* The two phases of a reference matmul node, separately (ne_compute_forward_mul_mat_q_f32: NE_TASK_INIT quantises src1
+ * into wdata, NE_TASK_COMPUTE runs the dots; core/ne_layers.c:7143-7203):
+ *   ns_prepare_activation  act[m][k] (device fp32) -> activation image in `workspace` (m <= 4 rows per image)
+ *   ns_matmul_prepared     runs 1..3 weights against a prepared image.  mode: 0 plain, 1 concat ([nw][m][ldo] output,
+ *                          ne_mul_qkv), 2 gate/up + SiLU*mul (ne_ffn_silu first half; aux may receive silu(gate)). */
+NS_API int ns_prepare_activation(const ns_weight* w, const float* act, int lda, int m, void* workspace, void* queue);
+NS_API int ns_matmul_prepared(const ns_weight* const* weights, int nw, int mode, const void* workspace, float* dst, int ldo,
+                              int m, const float* bias, int bias_bcast, const float* residual, float* aux, void* queue);
+
+/* CUDA-graph capture of a sequence of calls on one queue (replaces the reference's per-token graph rebuild +
+ * ne_graph_compute, models/llama/llama.cpp:136-143 / core/ne_layers.c:11915): begin, issue ns_* device calls with
+ * caller-provided workspaces (no allocation may happen while capturing), end -> executable graph handle. */
+typedef struct ns_graph ns_graph;
+NS_API int ns_graph_begin(void* queue);
+NS_API ns_graph* ns_graph_end(void* queue);
+NS_API int ns_graph_launch(ns_graph* g, void* queue);
+NS_API void ns_graph_free(ns_graph* g);
+
 /* ggml drop-in with HOST buffers: ne_compute_forward_mul_mat_q_f32 (ne_layers.c:7085) for NE_TYPE_Q4_0:
  * dst[ne11][ne01] = src1[ne11][ne00] x src0 rows.  src0 is uploaded/repacked once and cached by address. */
 NS_API int ns_mul_mat_q4_0_f32_host(const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01,

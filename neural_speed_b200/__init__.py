@@ -47,6 +47,7 @@ EXPORTS = [
     "ns_weight_from_q4_0", "ns_weight_from_btla_blob", "ns_weight_from_unpacked", "ns_weight_free", "ns_weight_info",
     "ns_weight_set_comp", "ns_weight_algorithmic_bytes", "ns_weight_dequant_f32",
     "ns_mul_mat", "ns_mul_qkv", "ns_ffn_silu", "ns_mul_mat_q4_0_f32_host",
+    "ns_prepare_activation", "ns_matmul_prepared", "ns_graph_begin", "ns_graph_end", "ns_graph_launch", "ns_graph_free",
     "ns_device_quantize_q4_0", "ns_device_quantize_act",
     "BTLAGemmPackBSize", "BTLAGemmQuantPackB", "BTLAGemmPackB", "BTLAGemmUnPackB", "ns_quantize_row_q4_0",
 ]
@@ -119,6 +120,13 @@ def lib() -> C.CDLL:
     L.ns_mul_qkv.argtypes = [vp, vp, vp, vp, i, vp, i, i, vp, vp]
     L.ns_ffn_silu.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp, vp]
     L.ns_mul_mat_q4_0_f32_host.argtypes = [vp, sz, vp, vp, i, i, i]
+    L.ns_prepare_activation.argtypes = [vp, vp, i, i, vp, vp]
+    L.ns_matmul_prepared.argtypes = [vp, i, i, vp, vp, i, i, vp, i, vp, vp, vp]
+    L.ns_graph_begin.argtypes = [vp]
+    L.ns_graph_end.restype = vp
+    L.ns_graph_end.argtypes = [vp]
+    L.ns_graph_launch.argtypes = [vp, vp]
+    L.ns_graph_free.argtypes = [vp]
     L.ns_device_quantize_q4_0.argtypes = [vp, vp, i, i, vp]
     L.ns_device_quantize_act.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp]
     L.BTLAGemmPackBSize.restype = sz

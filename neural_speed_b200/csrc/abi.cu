@@ -561,6 +561,61 @@ extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_we
   return NS_OK;
 }
 
+extern "C" int ns_prepare_activation(const ns_weight* w, const float* act, int lda, int m, void* workspace, void* queue) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!w || !act || !workspace || m < 1 || m > ns_gemv_tile_rows(w) || lda < w->k) {
+    ns_set_error("ns_prepare_activation: invalid arguments (m=%d)", m);
+    return NS_E_INVALID;
+  }
+  return ns_launch_act_prep(act, lda, m, w, workspace, stream_of(queue));
+}
+
+extern "C" int ns_matmul_prepared(const ns_weight* const* weights, int nw, int mode, const void* workspace, float* dst,
+                                  int ldo, int m, const float* bias, int bias_bcast, const float* residual, float* aux,
+                                  void* queue) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!weights || nw < 1 || nw > 3 || mode < 0 || mode > 2 || !workspace || !dst) {
+    ns_set_error("ns_matmul_prepared: invalid arguments");
+    return NS_E_INVALID;
+  }
+  return ns_launch_gemv(weights, nw, mode, workspace, dst, ldo, m, m, bias, bias_bcast, residual, aux, stream_of(queue));
+}
+
+// ---------------------------------------------------------------------------------------------------- CUDA graphs
+struct ns_graph {
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+};
+extern "C" int ns_graph_begin(void* queue) {
+  if (int rc = ns_ensure_device()) return rc;
+  NS_CUDA_TRY(cudaStreamBeginCapture(stream_of(queue), cudaStreamCaptureModeThreadLocal));
+  return NS_OK;
+}
+extern "C" ns_graph* ns_graph_end(void* queue) {
+  cudaGraph_t g = nullptr;
+  if (!ns_cuda_ok(cudaStreamEndCapture(stream_of(queue), &g), "cudaStreamEndCapture") || !g) return nullptr;
+  cudaGraphExec_t e = nullptr;
+  if (!ns_cuda_ok(cudaGraphInstantiate(&e, g, 0), "cudaGraphInstantiate")) {
+    cudaGraphDestroy(g);
+    return nullptr;
+  }
+  ns_graph* r = new ns_graph();
+  r->graph = g;
+  r->exec = e;
+  return r;
+}
+extern "C" int ns_graph_launch(ns_graph* g, void* queue) {
+  if (!g) return NS_E_INVALID;
+  NS_CUDA_TRY(cudaGraphLaunch(g->exec, stream_of(queue)));
+  return NS_OK;
+}
+extern "C" void ns_graph_free(ns_graph* g) {
+  if (!g) return;
+  cudaGraphExecDestroy(g->exec);
+  cudaGraphDestroy(g->graph);
+  delete g;
+}
+
 // ---------------------------------------------------------------------------------------------------- device set
 extern "C" void bestla_init(void) { (void)ns_ensure_device(); }
 extern "C" int bestla_set_threads(int nth) { return nth; }

@@ -29,6 +29,7 @@ __device__ __forceinline__ int warp_isum(int v) {
 
 // utils::cast<float,uint8_t> (bestla_utils.h:515-521)
 __device__ __forceinline__ int cast_u8(float x) {
+  if (x != x) return 0;  // NaN -> 0 as on x86 (see cast_s8)
   x += 0.5f;
   x = fminf(x, 255.f);
   x = fmaxf(x, 0.f);
@@ -36,6 +37,9 @@ __device__ __forceinline__ int cast_u8(float x) {
 }
 // utils::cast<float,int8_t> (bestla_utils.h:507-513)
 __device__ __forceinline__ int cast_s8(float x) {
+  // all-zero block: scale is denormal, 1/scale = inf, 0*inf = NaN.  On the reference's x86 build the NaN survives
+  // std::min/std::max and converts to 0 (cvttss2si -> INT_MIN -> int8 0); CUDA's fminf would return 127 instead.
+  if (x != x) return 0;
   x = roundf(x);
   x = fminf(x, 127.f);
   x = fmaxf(x, -128.f);
