@@ -29,6 +29,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+os.environ.setdefault("OMP_PROC_BIND", "false")
 
 N_EMBD, N_FF, N_LAYER, N_VOCAB = 4096, 11008, 32, 32000
 METRIC = "decode tokens/s, Llama-2-7B Q4_0, batch=1 (weight-only matmul path)"
@@ -87,10 +89,28 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------------------- reference arm
 def host_threads():
+    """usable host cores: scheduler affinity, capped by the cgroup CPU quota (a 128-CPU box may grant this container far
+    fewer; oversubscribed OpenMP barriers would then make the reference look absurdly slow)"""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    env = os.environ.get("NS_REF_THREADS")
+    return int(env) if env else n
 
 
 class CpuReference:

@@ -87,6 +87,17 @@ int ns_ensure_device() {
   return NS_OK;
 }
 
+int ns_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
 static cudaStream_t default_stream() { return g_default.stream; }
 static cudaStream_t stream_of(void* queue) { return queue ? (cudaStream_t)queue : default_stream(); }
 
@@ -111,37 +122,24 @@ static void* scratch_get(cudaStream_t st, size_t bytes) {
 }
 
 // ---------------------------------------------------------------------------------------------------- weight handles
-static size_t stype_size(int stype) { return stype == NS_S_F32 ? 4 : 2; }
-
-static void weight_layout(ns_weight* w) {
-  w->kpad = (int)ns_round_up((size_t)w->k, 32);
-  if (w->group <= 0 || w->group > w->k) w->group = w->k;
-  w->ngroups = (w->k + w->group - 1) / w->group;
-  w->row_bytes = (w->wfmt == NS_W_S8) ? (size_t)w->kpad : (size_t)w->kpad / 2;
-}
+static size_t stype_size(int stype) { return (size_t)ns_stype_size(stype); }
+static void weight_layout(ns_weight* w) { ns_weight_layout(w); }
 static size_t weight_image_bytes(const ns_weight* w, bool with_shuffle) {
-  size_t b = ns_round_up((size_t)w->n * w->row_bytes, 256);
-  b += ns_round_up((size_t)w->n * w->ngroups * stype_size(w->stype), 256);
-  if (w->asym) b += ns_round_up((size_t)w->n * w->ngroups, 256);
+  size_t b = ns_round_up((size_t)w->n * w->pitch, 256);
   if (with_shuffle) b += ns_round_up((size_t)w->k * 4, 256);
   return b;
 }
 static void weight_carve(ns_weight* w, void* base, bool with_shuffle) {
   char* p = (char*)base;
-  w->q = (uint8_t*)p;
-  p += ns_round_up((size_t)w->n * w->row_bytes, 256);
-  w->scales = p;
-  p += ns_round_up((size_t)w->n * w->ngroups * stype_size(w->stype), 256);
-  w->zp = nullptr;
-  if (w->asym) {
-    w->zp = (int8_t*)p;
-    p += ns_round_up((size_t)w->n * w->ngroups, 256);
-  }
+  w->rows = (uint8_t*)p;
+  p += ns_round_up((size_t)w->n * w->pitch, 256);
   w->shuffle = with_shuffle ? (int*)p : nullptr;
 }
 static int weight_alloc(ns_weight* w, bool with_shuffle) {
   w->total_bytes = weight_image_bytes(w, with_shuffle);
   NS_CUDA_TRY(cudaMalloc(&w->base, w->total_bytes));
+  // padding bytes of each row are streamed by the GEMV too: keep them defined
+  NS_CUDA_TRY(cudaMemset(w->base, 0, w->total_bytes));
   w->external = 0;
   weight_carve(w, w->base, with_shuffle);
   return NS_OK;
@@ -696,6 +694,7 @@ extern "C" void bestla_device_load_storage(void* hoststor, void* devstor, void* 
   w->external = 1;
   w->total_bytes = weight_image_bytes(w, v.shuffle != nullptr);
   weight_carve(w, deviceptr, v.shuffle != nullptr);
+  if (cudaMemsetAsync(deviceptr, 0, w->total_bytes, stream_of(queue)) != cudaSuccess) ns_fatal("cudaMemset failed");
   if (blob_upload_repack(v, w, stream_of(queue))) ns_fatal("bestla_device_load_storage: %s", g_err);
 }
 extern "C" void bestla_device_f32f32_forward(float* activation, void* weiptr, float* output, int m, int n, int k, int lda,

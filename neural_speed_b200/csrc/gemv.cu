@@ -1,4 +1,5 @@
-// gemv.cu -- decode-shape (M <= 4) weight-only matmul: HBM-bound streaming GEMV, no tensor cores.
+// gemv.cu -- decode-shape (M <= 4) weight-only matmul: launcher + the register-staged GEMV used for the formats the
+// TMA-ring kernel (gemv_ring.cu) does not cover: fp32/bf16 compute (BesTLA CompFp32/CompBf16), NF4 and 8-bit weights.
 //
 // Replaces, for M <= 4 (the reference's own GEMV cut-off, bestla_wrapper.h:283/568 "M<=4"):
 //   ggml   ne_compute_forward_mul_mat_q_f32 + ne_vec_dot_q4_0_q8_0   (core/ne_layers.c:7085, core/layers/vec_dot.h:131)
@@ -6,14 +7,9 @@
 //          (bestla/bestla/bestla_wrapper.h:568-729, bestla/bestla/kernel_ref.h:2372-2531)
 //   and the fused callers ne_mul_qkv / ne_ffn_silu (core/layers/ip_fusion_qkv.cpp:194, ip_fusion_ffn.cpp:734).
 //
-// Mapping to B200: one warp owns a PAIR of weight rows at a time; lanes stride K in 16-byte chunks (32 nibbles) so a
-// warp-wide load is 512 contiguous bytes per row (ld.global.nc.L1::no_allocate.v4).  Each lane keeps 2 rows x U=4
-// chunks (8 x 16 B) in flight; 2 CTAs x 8 warps per SM => 64 KB of loads in flight per SM (Little's law needs ~32 KB at
-// 6.6 TB/s).  Activations are staged once per CTA in shared memory in the exact byte image act_prep.cu produced
-// (int8 + per-chunk {scale, sum, zp}); integer dots use dp4a, so every K-block partial sum is an exact integer,
-// identical to the reference's integer arithmetic; only the fp32 summation order differs.
-// Programmatic dependent launch: the first batch of weight loads is issued BEFORE griddepcontrol.wait, so the
-// HBM stream of kernel i+1 overlaps the tail of kernel i (weights never depend on the previous kernel).
+// This kernel: one warp owns a PAIR of weight rows at a time; lanes stride K in 32-element chunks (16 B of nibbles,
+// ld.global.nc.L1::no_allocate.v4), 2 rows x U=4 chunks in flight per lane; activations staged once per CTA in shared
+// memory in the byte image act_prep.cu produced.  fp32 modes: w = (float)(q - zp) * scale (or lut[q] * scale), FMA.
 // Roofline: HBM.  Algorithmic bytes per launch = N*K*bits/8 + N*ceil(K/g)*(scale_bytes [+1 if asym]).
 #include "nsb.cuh"
 
@@ -21,32 +17,7 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-constexpr int U = 4;  // 16-byte chunks per row per lane per batch
-
-enum { A_S8 = 0, A_U8 = 1, A_F32 = 2 };
-
-struct GemvParams {
-  const uint8_t* q[3];
-  const void* sc[3];
-  const int8_t* zp[3];
-  int n[3];
-  long long dst_off[3];
-  int nw, mode;
-  int k, kpad, group, ngroups, stype;
-  int cpg;  // 32-element chunks per scale group
-  size_t row_bytes;
-  const void* act;  // prepared activation image (device)
-  int act_bytes;    // bytes to stage in shared memory
-  int meta_off;     // byte offset of the meta array inside the image (int8 modes)
-  int meta_stride;  // int2 per activation row
-  float* dst;
-  int ldo, m;
-  const float* bias;
-  int bias_bcast;
-  const float* residual;
-  float* aux;
-  int npairs;
-};
+constexpr int U = 4;  // chunks per row per lane per batch
 
 template <int WFMT>
 struct WChunk {  // one 32-element chunk of one row
@@ -65,24 +36,17 @@ struct Batch {
 };
 
 struct RowRef {
-  const uint8_t* q;
-  const void* sc;
-  const int8_t* zp;
-  long long out;  // element offset in dst for m == 0
-  int srow;       // row index inside its own weight (indexes scales / zp)
+  const uint8_t* row;  // start of the NSB row
+  long long out;       // element offset in dst for m == 0
   bool valid;
 };
 
-// Resolve the two rows of pair p.
 __device__ __forceinline__ void resolve_pair(const GemvParams& P, int p, RowRef rr[2]) {
   if (P.mode == NS_GEMV_GATE_UP_SILU) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      rr[r].q = P.q[r] + (size_t)p * P.row_bytes;
-      rr[r].sc = P.sc[r];
-      rr[r].zp = P.zp[r];
+      rr[r].row = P.rows[r] + (size_t)p * P.pitch;
       rr[r].out = (long long)p;
-      rr[r].srow = p;
       rr[r].valid = true;
     }
     return;
@@ -101,11 +65,8 @@ __device__ __forceinline__ void resolve_pair(const GemvParams& P, int p, RowRef 
     }
     const bool valid = row < P.n[wi];
     if (!valid) row = P.n[wi] - 1;
-    rr[r].q = P.q[wi] + (size_t)row * P.row_bytes;
-    rr[r].sc = P.sc[wi];
-    rr[r].zp = P.zp[wi];
+    rr[r].row = P.rows[wi] + (size_t)row * P.pitch;
     rr[r].out = P.dst_off[wi] + row;
-    rr[r].srow = row;
     rr[r].valid = valid;
   }
 }
@@ -121,15 +82,15 @@ __device__ __forceinline__ void load_batch(const GemvParams& P, const RowRef rr[
     for (int r = 0; r < 2; ++r) {
       if (ok) {
         if constexpr (WFMT == NS_W_S8) {
-          const uint4* src = reinterpret_cast<const uint4*>(rr[r].q) + 2 * c;
+          const uint4* src = reinterpret_cast<const uint4*>(rr[r].row) + 2 * c;
           B.w[r][u].a = ld_nc_v4(src);
           B.w[r][u].b = ld_nc_v4(src + 1);
         } else {
-          B.w[r][u].a = ld_nc_v4(reinterpret_cast<const uint4*>(rr[r].q) + c);
+          B.w[r][u].a = ld_nc_v4(reinterpret_cast<const uint4*>(rr[r].row) + c);
         }
-        const size_t gi = (size_t)rr[r].srow * P.ngroups + (P.cpg == 1 ? c : c / P.cpg);
-        B.s[r][u] = ns_load_scale(rr[r].sc, P.stype, gi);
-        if (ASYM) B.z[r][u] = (int)__ldg(rr[r].zp + gi);
+        const int gi = (P.cpg == 1) ? c : c / P.cpg;
+        B.s[r][u] = ns_scale_at(rr[r].row + P.sc_off, P.stype, gi);
+        if (ASYM) B.z[r][u] = (int)(signed char)rr[r].row[P.zp_off + gi];
       } else {
         B.w[r][u].a = make_uint4(0, 0, 0, 0);
         if constexpr (WFMT == NS_W_S8) B.w[r][u].b = make_uint4(0, 0, 0, 0);
@@ -168,7 +129,6 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvParams P) {
 
   pdl_wait();  // activations (and dst/residual) are produced by earlier kernels
 
-  // stage the prepared activation image
   {
     const uint4* src = reinterpret_cast<const uint4*>(P.act);
     uint4* dstv = reinterpret_cast<uint4*>(smem);
@@ -195,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvParams P) {
         const int c = lane + 32 * (b * U + u);
         if (c >= nchunks) continue;
         if constexpr (AMODE != A_F32) {
-          // ---------------- integer path: exact block dots via dp4a ----------------
+          // ---------------- integer path: exact chunk dots via dp4a ----------------
           uint32_t lo[2][4], hi[2][4];
           int su[2] = {0, 0};
 #pragma unroll
@@ -213,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvParams P) {
                 hi[r][i] = (ww[i] >> 4) & 0x0F0F0F0Fu;
               }
             }
-            if (AMODE == A_U8) {  // sum of weight codes, needed for the activation zero point
+            if (AMODE == A_U8) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 su[r] = dp4a_ss(0x01010101, (int)lo[r][i], su[r]);
@@ -235,24 +195,15 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvParams P) {
               if constexpr (WFMT == NS_W_S8) {
                 // natural order: lo = k 0..15, hi = k 16..31
                 if (AMODE == A_U8) {
-                  // u8 activations x s8 weights
-                  asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(ps) : "r"(a0.x), "r"(lo[r][0]));
-                  asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(ps) : "r"(a0.y), "r"(lo[r][1]));
-                  asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(ps) : "r"(a0.z), "r"(lo[r][2]));
-                  asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(ps) : "r"(a0.w), "r"(lo[r][3]));
-                  asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(ps) : "r"(a1.x), "r"(hi[r][0]));
-                  asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(ps) : "r"(a1.y), "r"(hi[r][1]));
-                  asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(ps) : "r"(a1.z), "r"(hi[r][2]));
-                  asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(ps) : "r"(a1.w), "r"(hi[r][3]));
+                  ps = dp4a_us(a0.x, (int)lo[r][0], ps); ps = dp4a_us(a0.y, (int)lo[r][1], ps);
+                  ps = dp4a_us(a0.z, (int)lo[r][2], ps); ps = dp4a_us(a0.w, (int)lo[r][3], ps);
+                  ps = dp4a_us(a1.x, (int)hi[r][0], ps); ps = dp4a_us(a1.y, (int)hi[r][1], ps);
+                  ps = dp4a_us(a1.z, (int)hi[r][2], ps); ps = dp4a_us(a1.w, (int)hi[r][3], ps);
                 } else {
-                  ps = dp4a_ss((int)a0.x, (int)lo[r][0], ps);
-                  ps = dp4a_ss((int)a0.y, (int)lo[r][1], ps);
-                  ps = dp4a_ss((int)a0.z, (int)lo[r][2], ps);
-                  ps = dp4a_ss((int)a0.w, (int)lo[r][3], ps);
-                  ps = dp4a_ss((int)a1.x, (int)hi[r][0], ps);
-                  ps = dp4a_ss((int)a1.y, (int)hi[r][1], ps);
-                  ps = dp4a_ss((int)a1.z, (int)hi[r][2], ps);
-                  ps = dp4a_ss((int)a1.w, (int)hi[r][3], ps);
+                  ps = dp4a_ss((int)a0.x, (int)lo[r][0], ps); ps = dp4a_ss((int)a0.y, (int)lo[r][1], ps);
+                  ps = dp4a_ss((int)a0.z, (int)lo[r][2], ps); ps = dp4a_ss((int)a0.w, (int)lo[r][3], ps);
+                  ps = dp4a_ss((int)a1.x, (int)hi[r][0], ps); ps = dp4a_ss((int)a1.y, (int)hi[r][1], ps);
+                  ps = dp4a_ss((int)a1.z, (int)hi[r][2], ps); ps = dp4a_ss((int)a1.w, (int)hi[r][3], ps);
                 }
               } else {
                 // NSB4: word i pairs with activation words (Alo_i, Ahi_i) = ((a0,a4,a1,a5),(a2,a6,a3,a7)) of 8-group i
@@ -326,7 +277,6 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvParams P) {
     }
     first = false;
 
-    // ---- reduce across lanes and write ----
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -362,23 +312,6 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvParams P) {
   }
 }
 
-template <typename... Args>
-cudaError_t launch_pdl(void (*kern)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, args...);
-}
-
-int g_num_sms = 0;
-
 template <int WFMT, int AMODE, int M, bool ASYM>
 int launch_one(const GemvParams& P, size_t smem, cudaStream_t st) {
   auto kern = gemv_kernel<WFMT, AMODE, M, ASYM>;
@@ -387,18 +320,12 @@ int launch_one(const GemvParams& P, size_t smem, cudaStream_t st) {
     NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
   const int need = (P.npairs + kWarps - 1) / kWarps;
   const int ctas_per_sm = smem > 100 * 1024 ? 1 : 2;
-  int grid = g_num_sms * ctas_per_sm;
+  int grid = ns_num_sms() * ctas_per_sm;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  NS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, st, P));
+  NS_CUDA_TRY(ns_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, st, P));
   ns_count_launch();
   return NS_OK;
 }
@@ -422,10 +349,11 @@ int launch_asym(const GemvParams& P, bool asym, int mt, size_t smem, cudaStream_
 // Largest activation-row tile one GEMV launch can take for this weight (bounded by shared memory).
 int ns_gemv_tile_rows(const ns_weight* w) {
   const bool fmode = (w->comp == NS_COMP_F32 || w->comp == NS_COMP_BF16);
-  const size_t meta_stride = ns_round_up((size_t)(w->kpad >> 5), 2);
-  const size_t per_row = fmode ? (size_t)w->kpad * 4 : (size_t)w->kpad + meta_stride * 8;
+  const size_t per_row = fmode ? (size_t)w->kpad * 4 : (size_t)w->kpad + (size_t)ns_meta_stride(w->kpad) * 8;
   int mt = 4;
-  while (mt > 1 && per_row * mt > 96 * 1024) mt >>= 1;
+  // int8 activations of 4 rows must leave room for a useful ring next to them (two CTAs per SM)
+  const size_t cap = fmode ? 96 * 1024 : 64 * 1024;
+  while (mt > 1 && per_row * mt > cap) mt >>= 1;
   return mt;
 }
 
@@ -461,14 +389,12 @@ int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* ac
     ns_set_error("NF4 weights need a float compute type");
     return NS_E_UNSUPPORTED;
   }
-  const int meta_stride = (int)ns_round_up((size_t)(kpad >> 5), 2);
+  const int meta_stride = ns_meta_stride(kpad);
 
   GemvParams P = {};
   long long ntot = 0;
   for (int i = 0; i < nw; ++i) {
-    P.q[i] = ws_[i]->q;
-    P.sc[i] = ws_[i]->scales;
-    P.zp[i] = ws_[i]->zp;
+    P.rows[i] = ws_[i]->rows;
     P.n[i] = ws_[i]->n;
     // QKV convention of the reference: dst = [nw][M][ldo] (ip_fusion_qkv.cpp:84-86)
     P.dst_off[i] = (mode == NS_GEMV_CONCAT) ? (long long)i * m_total * ldo : 0;
@@ -486,7 +412,10 @@ int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* ac
   P.ngroups = w0->ngroups;
   P.stype = w0->stype;
   P.cpg = (w0->group + 31) / 32;
-  P.row_bytes = w0->row_bytes;
+  P.pitch = w0->pitch;
+  P.q_bytes = w0->q_bytes;
+  P.sc_off = w0->sc_off;
+  P.zp_off = w0->zp_off;
   P.dst = dst;
   P.ldo = ldo;
   P.m = m;
@@ -512,11 +441,9 @@ int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* ac
   }
   smem = ns_round_up(smem, 16);
   const bool asym = w0->asym != 0;
-  if (w0->wfmt == NS_W_S4) {
-    return amode == A_F32  ? launch_asym<NS_W_S4, A_F32>(P, asym, mt, smem, st)
-           : amode == A_U8 ? launch_asym<NS_W_S4, A_U8>(P, asym, mt, smem, st)
-                           : launch_asym<NS_W_S4, A_S8>(P, asym, mt, smem, st);
-  } else if (w0->wfmt == NS_W_S8) {
+  if (w0->wfmt == NS_W_S4 && !fmode) return ns_launch_gemv_ring(P, amode, asym, mt, st);  // the hot decode path
+  if (w0->wfmt == NS_W_S4) return launch_asym<NS_W_S4, A_F32>(P, asym, mt, smem, st);
+  if (w0->wfmt == NS_W_S8) {
     return amode == A_F32  ? launch_asym<NS_W_S8, A_F32>(P, asym, mt, smem, st)
            : amode == A_U8 ? launch_asym<NS_W_S8, A_U8>(P, asym, mt, smem, st)
                            : launch_asym<NS_W_S8, A_S8>(P, asym, mt, smem, st);

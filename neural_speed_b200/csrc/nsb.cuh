@@ -1,15 +1,19 @@
 // nsb.cuh -- internal definitions shared by the CUDA sources of libns_b200.so (sm_100a only).
 //
 // Device ("NSB") weight layout, chosen for B200 (see DESIGN.md "Data layout in HBM"):
-//   q plane   [N][kpad/2] bytes (4-bit formats) or [N][kpad] bytes (8-bit); kpad = roundup(K, 32); rows 16-B aligned.
-//             4-bit: every 32-bit word holds 8 consecutive k (k0..k0+7); nibble position p (bits 4p..4p+3) holds
-//             element k0 + NSB4_PERM[p], NSB4_PERM = {0,2,4,6,1,3,5,7}.  Hence (w >> 4j) & 0x000F000F yields
-//             elements (2j, 2j+1) in the (low, high) half-words -- one op per bf16x2 pair for the tensor-core
-//             dequant -- and w & 0x0F0F0F0F / (w>>4) & 0x0F0F0F0F yield bytes (e0,e4,e1,e5) / (e2,e6,e3,e7) for dp4a
-//             against activations stored in the same permuted order.  Stored nibble u = q + 8 (ints) or the NF4 code.
-//   scales    [N][ngroups] (f32 | bf16 | f16), ngroups = ceil(K / group): K-groups of one row are contiguous.
-//   zp        [N][ngroups] int8 (asymmetric only), value semantics w = (u - 8 - zp) * scale.
-//   shuffle   [K] int32 (GPTQ desc_act): activation column gather applied before activation quantisation.
+//   N self-contained rows of `pitch` bytes (16-B multiple), row n at rows + n*pitch:
+//     [ q      : q_bytes = kpad/2 (4-bit) or kpad (8-bit), kpad = roundup(K, 32)           ]
+//     [ scales : ngroups x {f32|bf16|f16}, ngroups = ceil(K/group)  (at sc_off = q_bytes)  ]
+//     [ zp     : ngroups x int8, asymmetric only                    (at zp_off)            ]
+//   Everything one output row needs is ONE contiguous byte range, so the decode GEMV streams whole rows with
+//   cp.async.bulk (TMA 1-D) into a shared-memory ring, and the prefill GEMM sees the q part as a 2-D tensor of pitch
+//   `pitch` for cp.async.bulk.tensor.
+//   4-bit q: every 32-bit word holds 8 consecutive k (k0..k0+7); nibble position p (bits 4p..4p+3) holds element
+//   k0 + {0,2,4,6,1,3,5,7}[p].  Hence (w >> 4j) & 0x000F000F yields elements (2j, 2j+1) in the (low, high) half-words
+//   -- one op per bf16x2 pair for the tensor-core dequant -- and w & 0x0F0F0F0F / (w>>4) & 0x0F0F0F0F yield bytes
+//   (e0,e4,e1,e5) / (e2,e6,e3,e7) for dp4a against activations stored in the same permuted order.
+//   Stored nibble u = q + 8 (ints) or the NF4 code; value semantics w = (u - 8 - zp) * scale.
+//   shuffle [K] int32 (GPTQ desc_act): activation column gather applied before activation quantisation.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -24,15 +28,27 @@ struct ns_weight {
   int n, k, kpad;
   int group, ngroups;
   int wfmt, stype, comp, asym;
-  uint8_t* q;
-  void* scales;
-  int8_t* zp;
+  uint8_t* rows;  // device: n * pitch bytes
+  int pitch, q_bytes, sc_off, zp_off;
   int* shuffle;
-  size_t row_bytes;   // bytes per row of the q plane
-  void* base;         // allocation owning q/scales/zp/shuffle (NULL if external)
-  size_t total_bytes; // bytes of the device image
-  int external;       // 1: memory supplied by caller (bestla_device_load_storage)
+  void* base;          // allocation owning rows/shuffle (NULL if external)
+  size_t total_bytes;  // bytes of the device image
+  int external;        // 1: memory supplied by caller (bestla_device_load_storage)
 };
+
+static inline size_t ns_round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+static inline int ns_stype_size(int stype) { return stype == NS_S_F32 ? 4 : 2; }
+
+// fills kpad/group/ngroups/pitch/offsets from n,k,group,wfmt,stype,asym
+static inline void ns_weight_layout(ns_weight* w) {
+  w->kpad = (int)ns_round_up((size_t)w->k, 32);
+  if (w->group <= 0 || w->group > w->k) w->group = w->k;
+  w->ngroups = (w->k + w->group - 1) / w->group;
+  w->q_bytes = (w->wfmt == NS_W_S8) ? w->kpad : w->kpad / 2;
+  w->sc_off = w->q_bytes;
+  w->zp_off = w->sc_off + w->ngroups * ns_stype_size(w->stype);
+  w->pitch = (int)ns_round_up((size_t)w->zp_off + (w->asym ? w->ngroups : 0), 16);
+}
 
 // ---- error handling -------------------------------------------------------------------------------------------------
 void ns_set_error(const char* fmt, ...);
@@ -40,26 +56,18 @@ void ns_set_error(const char* fmt, ...);
 bool ns_cuda_ok(cudaError_t e, const char* what);
 int ns_ensure_device();  // 0 ok, <0 NS_E_*
 void ns_count_launch(int n = 1);
+int ns_num_sms();
 
-#define NS_CUDA_TRY(expr)                          \
-  do {                                             \
+#define NS_CUDA_TRY(expr)                             \
+  do {                                                \
     if (!ns_cuda_ok((expr), #expr)) return NS_E_CUDA; \
   } while (0)
 
-static inline size_t ns_round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
-
-// ---- activation workspace layout (device scratch used between act_prep and the matmul kernels) -----------------------
-// int8 modes : aq  [m][kpad] bytes   then  meta [m][kpad/32] int2 {float bits of a_scale, (Sa & 0xffff) | za << 16}
+// ---- activation workspace layout (device scratch between act_prep and the matmul kernels) ----------------------------
+// int8 modes : aq  [m][kpad] bytes (16-B padded)  then  meta [m][meta_stride] int2 {a_scale bits, (Sa & 0xffff) | za << 16}
 // fp32 modes : af  [m][kpad] float
-// bf16 GEMM  : ab  [m][kpad] bf16
-struct ns_act_view {
-  const uint8_t* aq;
-  const int2* meta;
-  const float* af;
-  int kpad;
-};
-
 size_t ns_act_workspace_bytes(int m, int kpad);
+static inline int ns_meta_stride(int kpad) { return (int)ns_round_up((size_t)(kpad >> 5), 2); }
 
 // launchers implemented in the .cu files
 int ns_launch_act_prep(const float* act, int lda, int m, const ns_weight* w, void* ws, cudaStream_t st);
@@ -74,6 +82,46 @@ int ns_launch_repack_btla(const void* qbuf_dev, const void* sc_dev, int src_styp
 int ns_launch_dequant(const ns_weight* w, float* dst, int ld, cudaStream_t st);
 
 enum { NS_GEMV_PLAIN = 0, NS_GEMV_CONCAT = 1, NS_GEMV_GATE_UP_SILU = 2 };
+enum { A_S8 = 0, A_U8 = 1, A_F32 = 2 };
+
+// shared by both GEMV kernels
+struct GemvParams {
+  const uint8_t* rows[3];  // row base of each weight
+  int n[3];
+  long long dst_off[3];
+  int nw, mode;
+  int k, kpad, group, ngroups, stype;
+  int cpg;  // 32-element chunks per scale group
+  int pitch, q_bytes, sc_off, zp_off;
+  const void* act;  // prepared activation image (device)
+  int act_bytes;    // bytes to stage in shared memory
+  int meta_off;     // byte offset of the meta array inside the image (int8 modes)
+  int meta_stride;  // int2 per activation row
+  float* dst;
+  int ldo, m;
+  const float* bias;
+  int bias_bcast;
+  const float* residual;
+  float* aux;
+  int npairs;
+};
+int ns_launch_gemv_ring(const GemvParams& P, int amode, bool asym, int mt, cudaStream_t st);  // gemv_ring.cu
+
+template <typename... Args>
+static inline cudaError_t ns_launch_pdl(void (*kern)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 
 // ---- small device helpers --------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -87,10 +135,11 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-__device__ __forceinline__ float ns_load_scale(const void* s, int stype, size_t idx) {
-  if (stype == NS_S_F32) return __ldg(reinterpret_cast<const float*>(s) + idx);
-  if (stype == NS_S_F16) return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(s) + idx)));
-  return __uint_as_float(static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(s) + idx)) << 16);
+// scale idx of a row whose scale array starts at `s` (global or shared memory, generic pointer)
+__device__ __forceinline__ float ns_scale_at(const void* s, int stype, int idx) {
+  if (stype == NS_S_F32) return reinterpret_cast<const float*>(s)[idx];
+  if (stype == NS_S_F16) return __half2float(__ushort_as_half(reinterpret_cast<const unsigned short*>(s)[idx]));
+  return __uint_as_float(static_cast<uint32_t>(reinterpret_cast<const unsigned short*>(s)[idx]) << 16);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -107,21 +156,26 @@ __device__ __forceinline__ int dp4a_ss(int a, int b, int c) {
   asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 // NF4 levels by the reference's code (kernel_ref.h:1325-1368; code 0 <-> 0.0, code 7 <-> -1.0)
 static __device__ __constant__ const float NS_NF4_LUT[16] = {0.f,
-                                                      -0.6961928009986877f,
-                                                      -0.5250730514526367f,
-                                                      -0.39491748809814453f,
-                                                      -0.28444138169288635f,
-                                                      -0.18477343022823334f,
-                                                      -0.09105003625154495f,
-                                                      -1.f,
-                                                      0.07958029955625534f,
-                                                      0.16093020141124725f,
-                                                      0.24611230194568634f,
-                                                      0.33791524171829224f,
-                                                      0.44070982933044434f,
-                                                      0.5626170039176941f,
-                                                      0.7229568362236023f,
-                                                      1.0f};
+                                                             -0.6961928009986877f,
+                                                             -0.5250730514526367f,
+                                                             -0.39491748809814453f,
+                                                             -0.28444138169288635f,
+                                                             -0.18477343022823334f,
+                                                             -0.09105003625154495f,
+                                                             -1.f,
+                                                             0.07958029955625534f,
+                                                             0.16093020141124725f,
+                                                             0.24611230194568634f,
+                                                             0.33791524171829224f,
+                                                             0.44070982933044434f,
+                                                             0.5626170039176941f,
+                                                             0.7229568362236023f,
+                                                             1.0f};
 #endif

@@ -19,7 +19,7 @@ __host__ __device__ constexpr int nsb4_perm(int p) { return p < 4 ? 2 * p : 2 * 
 
 // ---- ggml Q4_0 rows -> NSB -------------------------------------------------------------------------------------------
 __global__ void repack_q4_0_kernel(const uint8_t* __restrict__ rows, size_t nb01, int n, int nblocks,
-                                   uint8_t* __restrict__ q, size_t row_bytes, unsigned short* __restrict__ scales) {
+                                   uint8_t* __restrict__ q, size_t row_bytes, int sc_off) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * nblocks) return;
   const int row = (int)(idx / nblocks), b = (int)(idx - (size_t)row * nblocks);
@@ -43,7 +43,7 @@ __global__ void repack_q4_0_kernel(const uint8_t* __restrict__ rows, size_t nb01
     w[i] = v;
   }
   *reinterpret_cast<uint4*>(q + (size_t)row * row_bytes + (size_t)b * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-  scales[(size_t)row * nblocks + b] = h[0];
+  *reinterpret_cast<unsigned short*>(q + (size_t)row * row_bytes + sc_off + (size_t)b * 2) = h[0];
 }
 
 // ---- generic element accessors ---------------------------------------------------------------------------------------
@@ -110,44 +110,46 @@ __global__ void repack_q_kernel(Src src, int n, int k, int kpad, int wfmt, uint8
   }
 }
 
-// scales/zp: src [ngroups][ld_src] (f32 | bf16 | f16 by src_stype) -> dst [n][ngroups] in dst_stype
+// scales/zp: src [ngroups][ld_src] (f32 | bf16 | f16 by src_stype) -> into each NSB row at sc_off / zp_off
 __global__ void repack_scales_kernel(const void* __restrict__ sc, int src_stype, const int8_t* __restrict__ zp,
-                                     int ld_src, int n, int ngroups, void* __restrict__ sc_out, int dst_stype,
-                                     int8_t* __restrict__ zp_out) {
+                                     int ld_src, int n, int ngroups, uint8_t* __restrict__ rows, size_t pitch, int sc_off,
+                                     int zp_off, int dst_stype, int has_zp) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * ngroups) return;
   const int nn = (int)(idx % n), g = (int)(idx / n);
-  const size_t si = (size_t)g * ld_src + nn, di = (size_t)nn * ngroups + g;
-  if (src_stype == dst_stype) {
-    if (src_stype == NS_S_F32) reinterpret_cast<float*>(sc_out)[di] = reinterpret_cast<const float*>(sc)[si];
-    else reinterpret_cast<unsigned short*>(sc_out)[di] = reinterpret_cast<const unsigned short*>(sc)[si];
+  const size_t si = (size_t)g * ld_src + nn;
+  uint8_t* row = rows + (size_t)nn * pitch;
+  float v;
+  if (src_stype == NS_S_F32) v = reinterpret_cast<const float*>(sc)[si];
+  else if (src_stype == NS_S_F16) v = __half2float(__ushort_as_half(reinterpret_cast<const unsigned short*>(sc)[si]));
+  else v = __uint_as_float((uint32_t) reinterpret_cast<const unsigned short*>(sc)[si] << 16);
+  if (dst_stype == NS_S_F32) {
+    reinterpret_cast<float*>(row + sc_off)[g] = v;
+  } else if (src_stype == dst_stype) {
+    reinterpret_cast<unsigned short*>(row + sc_off)[g] = reinterpret_cast<const unsigned short*>(sc)[si];  // bit copy
+  } else if (dst_stype == NS_S_F16) {
+    reinterpret_cast<__half*>(row + sc_off)[g] = __float2half_rn(v);
   } else {
-    float v;
-    if (src_stype == NS_S_F32) v = reinterpret_cast<const float*>(sc)[si];
-    else if (src_stype == NS_S_F16) v = __half2float(__ushort_as_half(reinterpret_cast<const unsigned short*>(sc)[si]));
-    else v = __uint_as_float((uint32_t) reinterpret_cast<const unsigned short*>(sc)[si] << 16);
-    if (dst_stype == NS_S_F32) reinterpret_cast<float*>(sc_out)[di] = v;
-    else if (dst_stype == NS_S_F16) reinterpret_cast<__half*>(sc_out)[di] = __float2half_rn(v);
-    else reinterpret_cast<__nv_bfloat16*>(sc_out)[di] = __float2bfloat16_rn(v);  // RNE, as bestla_utils.h:146-153
+    reinterpret_cast<__nv_bfloat16*>(row + sc_off)[g] = __float2bfloat16_rn(v);  // RNE, as bestla_utils.h:146-153
   }
-  if (zp && zp_out) zp_out[di] = zp[si];
+  if (has_zp) row[zp_off + g] = zp ? (uint8_t)zp[si] : 0;
 }
 
 // ---- NSB -> fp32 [n][ld] ---------------------------------------------------------------------------------------------
-__global__ void dequant_kernel(const uint8_t* __restrict__ q, size_t row_bytes, const void* __restrict__ sc, int stype,
-                               const int8_t* __restrict__ zp, int n, int k, int group, int ngroups, int wfmt,
-                               float* __restrict__ dst, int ld) {
+__global__ void dequant_kernel(const uint8_t* __restrict__ rows, size_t pitch, int sc_off, int zp_off, int stype, int asym,
+                               int n, int k, int group, int wfmt, float* __restrict__ dst, int ld) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * k) return;
   const int row = (int)(idx / k), kk = (int)(idx - (size_t)row * k);
-  const size_t gi = (size_t)row * ngroups + kk / group;
-  const float s = ns_load_scale(sc, stype, gi);
-  const int z = zp ? zp[gi] : 0;
+  const uint8_t* r = rows + (size_t)row * pitch;
+  const int gi = kk / group;
+  const float s = ns_scale_at(r + sc_off, stype, gi);
+  const int z = asym ? (int)(signed char)r[zp_off + gi] : 0;
   float v;
   if (wfmt == NS_W_S8) {
-    v = (float)((int)(signed char)q[(size_t)row * row_bytes + kk] - z) * s;
+    v = (float)((int)(signed char)r[kk] - z) * s;
   } else {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(q + (size_t)row * row_bytes + (size_t)(kk >> 3) * 4);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(r + (size_t)(kk >> 3) * 4);
     const int e = kk & 7;
     const int sh = ((e >> 1) << 2) + ((e & 1) << 4);
     const int u = (w >> sh) & 0xf;
@@ -201,8 +203,8 @@ __global__ void quantize_q4_0_kernel(const float* __restrict__ src, int n, int k
 int ns_launch_repack_q4_0(const void* rows_dev, size_t nb01, ns_weight* w, cudaStream_t st) {
   const int nblocks = w->k / 32;
   const size_t total = (size_t)w->n * nblocks;
-  repack_q4_0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint8_t*)rows_dev, nb01, w->n, nblocks, w->q,
-                                                                      w->row_bytes, (unsigned short*)w->scales);
+  repack_q4_0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint8_t*)rows_dev, nb01, w->n, nblocks,
+                                                                      w->rows, (size_t)w->pitch, w->sc_off);
   NS_CUDA_TRY(cudaGetLastError());
   ns_count_launch();
   return NS_OK;
@@ -211,7 +213,8 @@ int ns_launch_repack_q4_0(const void* rows_dev, size_t nb01, ns_weight* w, cudaS
 static int launch_scales(const void* sc, int src_stype, const int8_t* zp, int ld_src, ns_weight* w, cudaStream_t st) {
   const size_t total = (size_t)w->n * w->ngroups;
   repack_scales_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sc, src_stype, zp, ld_src, w->n, w->ngroups,
-                                                                        w->scales, w->stype, w->zp);
+                                                                        w->rows, (size_t)w->pitch, w->sc_off, w->zp_off,
+                                                                        w->stype, w->asym);
   NS_CUDA_TRY(cudaGetLastError());
   ns_count_launch();
   return NS_OK;
@@ -221,7 +224,7 @@ int ns_launch_repack_canonical(const int8_t* q_kn_dev, const float* sc_dev, cons
                                cudaStream_t st) {
   const size_t total = (size_t)w->n * (w->kpad >> 3);
   SrcCanonical src{q_kn_dev, w->n};
-  repack_q_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, w->n, w->k, w->kpad, w->wfmt, w->q, w->row_bytes);
+  repack_q_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, w->n, w->k, w->kpad, w->wfmt, w->rows, (size_t)w->pitch);
   NS_CUDA_TRY(cudaGetLastError());
   ns_count_launch();
   return launch_scales(sc_dev, NS_S_F32, zp_dev, w->n, w, st);
@@ -234,10 +237,10 @@ int ns_launch_repack_btla(const void* qbuf_dev, const void* sc_dev, int src_styp
   const unsigned blocks = (unsigned)((total + 255) / 256);
   if (w->wfmt == NS_W_S8) {
     SrcBtlaS8 src{(const int8_t*)qbuf_dev, kpad_src, ntile, packrow};
-    repack_q_kernel<<<blocks, 256, 0, st>>>(src, w->n, w->k, w->kpad, w->wfmt, w->q, w->row_bytes);
+    repack_q_kernel<<<blocks, 256, 0, st>>>(src, w->n, w->k, w->kpad, w->wfmt, w->rows, (size_t)w->pitch);
   } else {
     SrcBtlaS4 src{(const uint8_t*)qbuf_dev, kpad_src, ntile, packrow, is_float};
-    repack_q_kernel<<<blocks, 256, 0, st>>>(src, w->n, w->k, w->kpad, w->wfmt, w->q, w->row_bytes);
+    repack_q_kernel<<<blocks, 256, 0, st>>>(src, w->n, w->k, w->kpad, w->wfmt, w->rows, (size_t)w->pitch);
   }
   NS_CUDA_TRY(cudaGetLastError());
   ns_count_launch();
@@ -246,8 +249,8 @@ int ns_launch_repack_btla(const void* qbuf_dev, const void* sc_dev, int src_styp
 
 int ns_launch_dequant(const ns_weight* w, float* dst, int ld, cudaStream_t st) {
   const size_t total = (size_t)w->n * w->k;
-  dequant_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w->q, w->row_bytes, w->scales, w->stype, w->zp, w->n,
-                                                                  w->k, w->group, w->ngroups, w->wfmt, dst, ld);
+  dequant_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w->rows, (size_t)w->pitch, w->sc_off, w->zp_off,
+                                                                  w->stype, w->asym, w->n, w->k, w->group, w->wfmt, dst, ld);
   NS_CUDA_TRY(cudaGetLastError());
   ns_count_launch();
   return NS_OK;
