@@ -482,11 +482,21 @@ extern "C" int ns_weight_dequant_f32(const ns_weight* w, float* dst_dev, int ld,
 // ---------------------------------------------------------------------------------------------------- device matmuls
 extern "C" size_t ns_device_workspace_bytes(int m, int k) {
   const int kpad = (int)ns_round_up((size_t)k, 32);
-  (void)m;
-  return ns_act_workspace_bytes(4, kpad);  // activations are prepared in tiles of <= 4 rows
+  const size_t gemv = ns_act_workspace_bytes(4, kpad);  // GEMV path: activations are prepared in tiles of <= 4 rows
+  const size_t tc = m > 4 ? ns_gemm_tc_workspace_bytes(m, kpad) : 0;  // tensor-core path: bf16 [m][kpad]
+  return gemv > tc ? gemv : tc;
 }
 
 static void* pick_ws(void* workspace, cudaStream_t st, size_t bytes) { return workspace ? workspace : scratch_get(st, bytes); }
+
+static bool use_tc(const ns_weight* w, int m, int flags) {
+  if (flags & NS_MM_FORCE_GEMV) return false;
+  if (!ns_gemm_tc_supported(w)) return false;
+  return m > 4 || (flags & NS_MM_FORCE_TC);
+}
+static size_t ws_need(const ns_weight* w, int m, bool tc) {
+  return tc ? ns_gemm_tc_workspace_bytes(m, w->kpad) : ns_act_workspace_bytes(4, w->kpad);
+}
 
 extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* bias,
                           const float* residual, int flags, void* workspace, void* queue) {
@@ -496,10 +506,16 @@ extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* 
     return NS_E_INVALID;
   }
   cudaStream_t st = stream_of(queue);
-  void* ws = pick_ws(workspace, st, ns_act_workspace_bytes(4, w->kpad));
+  const bool tc = use_tc(w, m, flags);
+  void* ws = pick_ws(workspace, st, ws_need(w, m, tc));
   if (!ws) return NS_E_CUDA;
-  const int tile = ns_gemv_tile_rows(w);
   const int bcast = (flags & NS_MM_BIAS_BCAST) ? 1 : 0;
+  if (tc) {
+    // M > 4: tcgen05 tensor-core GEMM, bf16 numerics (the reference switches from GEMV to GEMM at M > 4 as well)
+    if (int rc = ns_launch_act_bf16(w, act, lda, m, ws, st)) return rc;
+    return ns_launch_gemm_tc(w, ws, dst, ldo, m, bias, bcast, residual, st);
+  }
+  const int tile = ns_gemv_tile_rows(w);
   for (int m0 = 0; m0 < m; m0 += tile) {
     const int mt = (m - m0 < tile) ? (m - m0) : tile;
     if (int rc = ns_launch_act_prep(act + (size_t)m0 * lda, lda, mt, w, ws, st)) return rc;
@@ -516,9 +532,17 @@ extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_wei
   if (int rc = ns_ensure_device()) return rc;
   if (!wq || !wk || !wv || !act || !dst || m <= 0) return NS_E_INVALID;
   cudaStream_t st = stream_of(queue);
-  void* ws = pick_ws(workspace, st, ns_act_workspace_bytes(4, wq->kpad));
+  const bool tc = use_tc(wq, m, 0) && ns_gemm_tc_supported(wk) && ns_gemm_tc_supported(wv) && wk->k == wq->k &&
+                  wv->k == wq->k && !wq->shuffle && !wk->shuffle && !wv->shuffle;
+  void* ws = pick_ws(workspace, st, ws_need(wq, m, tc));
   if (!ws) return NS_E_CUDA;
   const ns_weight* wl[3] = {wq, wk, wv};
+  if (tc) {
+    if (int rc = ns_launch_act_bf16(wq, act, lda, m, ws, st)) return rc;
+    for (int i = 0; i < 3; ++i)
+      if (int rc = ns_launch_gemm_tc(wl[i], ws, dst + (size_t)i * m * ldo, ldo, m, nullptr, 0, nullptr, st)) return rc;
+    return NS_OK;
+  }
   const int tile = ns_gemv_tile_rows(wq);
   for (int m0 = 0; m0 < m; m0 += tile) {
     const int mt = (m - m0 < tile) ? (m - m0) : tile;
@@ -530,16 +554,28 @@ extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_wei
   return NS_OK;
 }
 
+// tmp: [2][m][fmid] floats when m > 4 (gate and up GEMM outputs; the product lands in the first half), else [m][fmid]
 extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda,
                            float* tmp, float* dst, int ldo, int m, void* workspace, void* queue) {
   if (int rc = ns_ensure_device()) return rc;
   if (!w1 || !w2 || !w3 || !act || !tmp || !dst || m <= 0 || w2->k != w1->n) return NS_E_INVALID;
   cudaStream_t st = stream_of(queue);
-  const int kmax = w1->kpad > w2->kpad ? w1->kpad : w2->kpad;
-  void* ws = pick_ws(workspace, st, ns_act_workspace_bytes(4, kmax));
-  if (!ws) return NS_E_CUDA;
-  const ns_weight* gu[2] = {w1, w3};
   const int fmid = w1->n;
+  const bool tc = use_tc(w1, m, 0) && ns_gemm_tc_supported(w2) && ns_gemm_tc_supported(w3) && !w1->shuffle && !w3->shuffle;
+  const int kmax = w1->kpad > w2->kpad ? w1->kpad : w2->kpad;
+  void* ws = pick_ws(workspace, st, tc ? ns_gemm_tc_workspace_bytes(m, kmax) : ns_act_workspace_bytes(4, kmax));
+  if (!ws) return NS_E_CUDA;
+  if (tc) {
+    float* gate = tmp;
+    float* up = tmp + (size_t)m * fmid;
+    if (int rc = ns_launch_act_bf16(w1, act, lda, m, ws, st)) return rc;
+    if (int rc = ns_launch_gemm_tc(w1, ws, gate, fmid, m, nullptr, 0, nullptr, st)) return rc;
+    if (int rc = ns_launch_gemm_tc(w3, ws, up, fmid, m, nullptr, 0, nullptr, st)) return rc;
+    if (int rc = ns_launch_silu_mul(gate, up, gate, nullptr, (size_t)m * fmid, st)) return rc;
+    if (int rc = ns_launch_act_bf16(w2, gate, fmid, m, ws, st)) return rc;
+    return ns_launch_gemm_tc(w2, ws, dst, ldo, m, nullptr, 0, nullptr, st);
+  }
+  const ns_weight* gu[2] = {w1, w3};
   int tile = ns_gemv_tile_rows(w1);
   for (int m0 = 0; m0 < m; m0 += tile) {
     const int mt = (m - m0 < tile) ? (m - m0) : tile;
@@ -878,7 +914,7 @@ extern "C" void bestla_fusion_FFN_SiLu_f32f32_forward(float* activation, void* w
   if (!w1 || !w2 || !w3 || w1->n != fmid || w1->k != fin || w2->n != fout || w2->k != fmid) ns_fatal("invalid parameters (%s)", g_err);
   cudaStream_t st = default_stream();
   if (!io_reserve(&g_io.act, &g_io.act_elems, (size_t)seq * fin) || !io_reserve(&g_io.out, &g_io.out_elems, (size_t)seq * fout) ||
-      !io_reserve(&g_io.tmp, &g_io.tmp_elems, (size_t)seq * fmid))
+      !io_reserve(&g_io.tmp, &g_io.tmp_elems, (size_t)2 * seq * fmid))
     ns_fatal("device staging allocation failed");
   cudaMemcpyAsync(g_io.act, activation, (size_t)seq * fin * 4, cudaMemcpyHostToDevice, st);
   if (ns_ffn_silu(w1, w2, w3, g_io.act, fin, g_io.tmp, g_io.out, fout, seq, nullptr, st)) ns_fatal("%s", g_err);

@@ -51,7 +51,7 @@ template <int COMP>
 __global__ void __launch_bounds__(256) act_quant_kernel(const float* __restrict__ A, int lda, int M, int K, int kpad,
                                                         int group, int ngroups, const int* __restrict__ shuffle,
                                                         int perm8, uint8_t* __restrict__ aq, int2* __restrict__ meta,
-                                                        int meta_stride) {
+                                                        int meta_stride, int act_row, int ring_layout) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) act_quant_kernel(const float* __restrict_
   }
 
   // pass 2: quantise 32 elements (one chunk) per iteration, emit permuted bytes + chunk meta
-  uint8_t* qrow = aq + (size_t)m * kpad;
+  uint8_t* qrow = aq + (size_t)m * act_row;
   for (int kc = k0; kc < kend_pad; kc += 32) {
     const int k = kc + lane;
     int q;
@@ -114,7 +114,13 @@ __global__ void __launch_bounds__(256) act_quant_kernel(const float* __restrict_
     }
     const int sa = warp_isum(q);
     const int pos = perm8 ? ((lane & ~7) | perm8_pos(lane & 7)) : lane;
-    qrow[kc + pos] = (uint8_t)q;
+    if (ring_layout) {
+      // gemv_ring.cu image: per super-block of 32 chunks, the first 16 bytes of every chunk, then the second 16 bytes
+      const int c = kc >> 5;
+      qrow[(c >> 5) * 1024 + (pos >> 4) * 512 + (c & 31) * 16 + (pos & 15)] = (uint8_t)q;
+    } else {
+      qrow[kc + pos] = (uint8_t)q;
+    }
     if (lane == 0) meta[(size_t)m * meta_stride + (kc >> 5)] = make_int2(__float_as_int(scale), (sa & 0xffff) | (za << 16));
   }
 }
@@ -190,7 +196,7 @@ __global__ void act_quant_plain_kernel(const float* __restrict__ A, int lda, int
 static size_t meta_stride_of(int kpad) { return ns_round_up((size_t)(kpad >> 5), 2); }  // int2 units, 16-B multiple
 
 size_t ns_act_workspace_bytes(int m, int kpad) {
-  const size_t i8 = ns_round_up((size_t)m * kpad, 16) + (size_t)m * meta_stride_of(kpad) * sizeof(int2);
+  const size_t i8 = (size_t)m * ns_round_up((size_t)kpad, 1024) + (size_t)m * meta_stride_of(kpad) * sizeof(int2);
   const size_t f32 = (size_t)m * kpad * sizeof(float);
   return ns_round_up(i8 > f32 ? i8 : f32, 256);
 }
@@ -221,7 +227,9 @@ int ns_launch_act_prep(const float* act, int lda, int m, const ns_weight* w, voi
     return NS_OK;
   }
   uint8_t* aq = (uint8_t*)ws;
-  int2* meta = (int2*)((char*)ws + ns_round_up((size_t)m * kpad, 16));
+  const int ring_layout = (w->wfmt == NS_W_S4) ? 1 : 0;  // consumed by gemv_ring.cu; other formats use natural rows
+  const int act_row = ring_layout ? (int)ns_round_up((size_t)kpad, 1024) : kpad;
+  int2* meta = (int2*)((char*)ws + ns_round_up((size_t)m * act_row, 16));
   const int ms = (int)meta_stride_of(kpad);
   // activation blocks: ggml Q8_0 is always 32; BesTLA uses the weight's K-block (bestla_prologue_a.h:133)
   const int group = (w->comp == NS_COMP_Q8_0) ? 32 : w->group;
@@ -232,13 +240,13 @@ int ns_launch_act_prep(const float* act, int lda, int m, const ns_weight* w, voi
   cudaError_t e;
   if (w->comp == NS_COMP_Q8_0)
     e = launch_pdl(act_quant_kernel<NS_COMP_Q8_0>, dim3(blocks), dim3(256), 0, st, act, lda, m, w->k, kpad, group,
-                   ngroups, (const int*)w->shuffle, perm8, aq, meta, ms);
+                   ngroups, (const int*)w->shuffle, perm8, aq, meta, ms, act_row, ring_layout);
   else if (w->comp == NS_COMP_INT8)
     e = launch_pdl(act_quant_kernel<NS_COMP_INT8>, dim3(blocks), dim3(256), 0, st, act, lda, m, w->k, kpad, group,
-                   ngroups, (const int*)w->shuffle, perm8, aq, meta, ms);
+                   ngroups, (const int*)w->shuffle, perm8, aq, meta, ms, act_row, ring_layout);
   else
     e = launch_pdl(act_quant_kernel<NS_COMP_INT8_S8>, dim3(blocks), dim3(256), 0, st, act, lda, m, w->k, kpad, group,
-                   ngroups, (const int*)w->shuffle, perm8, aq, meta, ms);
+                   ngroups, (const int*)w->shuffle, perm8, aq, meta, ms, act_row, ring_layout);
   NS_CUDA_TRY(e);
   ns_count_launch();
   return NS_OK;

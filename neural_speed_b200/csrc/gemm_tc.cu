@@ -1,0 +1,460 @@
+// gemm_tc.cu -- prefill / batched weight-only matmul on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), M > 4 rows.
+//
+// Replaces the reference's blocked GEMM for int4 weights: LauncherBase::run_block / LauncherIntKBlock::run_block
+// (bestla/bestla/bestla_wrapper.h:501,768) with WeightKBlockNInteger::getWeight + decompress_kblock_s4_fp
+// (bestla_prologue_b.h:642-733, kernel_ref.h:1113) feeding the JIT AMX/AVX512 micro-kernels (bestla_gemm.h), and the
+// ggml Q4_0 mul_mat for prompt batches (core/ne_layers.c:7085).  Numerics: weights are dequantised to bf16
+// ((u - 8 - zp) exactly in bf16, times the bf16-rounded scale), activations rounded to bf16, fp32 accumulation in TMEM --
+// the reference's own CompBf16 numerics (BF16 tolerance 2e-2 at K=4096, bestla_ut.h:80-94); logits stay within the
+// north-star's 1e-2 relative bar of the CPU path (tests/test_gpu_gemm_tc.py).
+//
+// Orientation ("swap-AB"): the WEIGHT tile is the UMMA M operand (128 output channels = 128 TMEM lanes) and the token tile
+// is the UMMA N operand (T = 32..256 columns), so small batches do not waste the 128-row MMA and the epilogue's stores
+// are coalesced along n.  Per CTA and per 64-wide k block:
+//   warp 0   TMA producer: packed nibbles [128 rows][32 B] (cp.async.bulk.tensor 2-D over the NSB rows, row pitch = pitch)
+//            and bf16 activations [T][64] (128B-swizzled) into two mbarrier rings
+//   warps 8-11  dequant: 1 thread = 1 weight row: 2 x LDS.128 of nibbles -> 64 bf16 via (w >> 4j) & 0x000F000F | 0x4300
+//            (bf16 128+u), HSUB2 (exact), HMUL2 by the group scale -> 8 x STS.128 into the 128B-swizzled K-major tile,
+//            fence.proxy.async, arrive
+//   warp 1   MMA issuer: 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=T, K=16) per k block, accumulator in TMEM,
+//            tcgen05.commit releases the smem slots
+//   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> (+bias, +residual) -> fp32 global stores, coalesced over n
+//   warp 2   TMEM alloc / dealloc
+// Roofline: tensor (bf16, fp32 accumulate): flops = 2*M*N*K per launch.
+#include <cuda.h>
+
+#include "nsb.cuh"
+
+namespace {
+
+constexpr int BLOCK_N = 128;  // weight rows per CTA (UMMA M)
+constexpr int BLOCK_K = 64;   // bf16 elements per k block (one 128-byte swizzle atom)
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 384;
+constexpr int SP = 6;  // packed-weight stages (4 KB)
+constexpr int SD = 3;  // dequantised-weight stages (16 KB)
+constexpr int PACKED_STAGE = BLOCK_N * (BLOCK_K / 2);  // 4096
+constexpr int DEQ_STAGE = BLOCK_N * BLOCK_K * 2;       // 16384
+
+struct GemmParams {
+  const uint8_t* rows;
+  int pitch, sc_off, zp_off, stype, asym, group, ngroups;
+  int n, k, kpad, m;
+  float* dst;
+  int ldo;
+  const float* bias;
+  int bias_bcast;
+  const float* residual;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// TMA 2-D tile load (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate (SASS: UTCHMMA)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128B-swizzled tile: 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1 (Blackwell), layout SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// c_format f32 (1<<4), a/b format bf16 (1<<7, 1<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+#define TMEM_LD_32X32B_X32(taddr, r)                                                                                        \
+  asm volatile(                                                                                                             \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                             \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                              \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                              \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),         \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), \
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),             \
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                        \
+      : "r"(taddr)                                                                                                          \
+      : "memory")
+
+template <int T>
+struct Smem {
+  static constexpr int SA = (T >= 256) ? 4 : 6;  // activation stages
+  static constexpr int ACT_STAGE = T * BLOCK_K * 2;
+  static constexpr int off_deq = 0;
+  static constexpr int off_act = off_deq + SD * DEQ_STAGE;
+  static constexpr int off_packed = off_act + SA * ACT_STAGE;
+  static constexpr int off_bar = off_packed + SP * PACKED_STAGE;
+  static constexpr int num_bars = 2 * SP + 2 * SA + 2 * SD + 1;
+  static constexpr int off_tmem_ptr = off_bar + num_bars * 8;
+  static constexpr int total = off_tmem_ptr + 16 + 1024;  // + slack for manual 1024-B alignment
+};
+
+template <int T>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_w4_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const GemmParams P) {
+  using L = Smem<T>;
+  constexpr int SA = L::SA;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  unsigned char* deq = smem + L::off_deq;
+  unsigned char* act = smem + L::off_act;
+  unsigned char* packed = smem + L::off_packed;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::off_bar);
+  uint64_t* p_full = bars;
+  uint64_t* p_empty = p_full + SP;
+  uint64_t* a_full = p_empty + SP;
+  uint64_t* a_empty = a_full + SA;
+  uint64_t* d_full = a_empty + SA;
+  uint64_t* d_empty = d_full + SD;
+  uint64_t* tmem_full = d_empty + SD;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::off_tmem_ptr);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_N;
+  const int t0 = blockIdx.y * T;
+  const int num_kb = (P.kpad + BLOCK_K - 1) / BLOCK_K;
+
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SP; ++i) {
+      mbar_init(&p_full[i], 1);
+      mbar_init(&p_empty[i], 4);
+    }
+    for (int i = 0; i < SA; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < SD; ++i) {
+      mbar_init(&d_full[i], 4);
+      mbar_init(&d_empty[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)T)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      // packed weights never depend on the previous kernel: prefetch the first ring before griddepcontrol.wait
+      const int pre = num_kb < SP ? num_kb : SP;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_expect_tx(&p_full[kb], PACKED_STAGE);
+        tma_load_2d(packed + kb * PACKED_STAGE, &tmap_w, kb * (BLOCK_K / 2), n0, &p_full[kb]);
+      }
+      pdl_wait();  // activations were written by the preceding kernel
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int sa = kb % SA;
+        if (kb >= SA) mbar_wait(&a_empty[sa], ((kb / SA) - 1) & 1);
+        mbar_expect_tx(&a_full[sa], L::ACT_STAGE);
+        tma_load_2d(act + sa * L::ACT_STAGE, &tmap_a, kb * BLOCK_K, t0, &a_full[sa]);
+        const int kp = kb + SP;  // keep the packed ring SP blocks ahead
+        if (kp < num_kb) {
+          const int sp = kp % SP;
+          mbar_wait(&p_empty[sp], ((kp / SP) - 1) & 1);
+          mbar_expect_tx(&p_full[sp], PACKED_STAGE);
+          tma_load_2d(packed + sp * PACKED_STAGE, &tmap_w, kp * (BLOCK_K / 2), n0, &p_full[sp]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    const uint32_t idesc = make_idesc_bf16(BLOCK_N, T);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int sd = kb % SD, sa = kb % SA;
+      mbar_wait(&d_full[sd], (kb / SD) & 1);
+      mbar_wait(&a_full[sa], (kb / SA) & 1);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(deq + sd * DEQ_STAGE);
+        const uint32_t b_addr = smem_u32(act + sa * L::ACT_STAGE);
+#pragma unroll
+        for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4) {
+          umma_bf16(tmem_base, make_desc_sw128(a_addr + k4 * UMMA_K * 2), make_desc_sw128(b_addr + k4 * UMMA_K * 2), idesc,
+                    (uint32_t)((kb | k4) != 0));
+        }
+        umma_commit(&d_empty[sd]);  // fires when the MMAs above have finished reading shared memory
+        umma_commit(&a_empty[sa]);
+        if (kb == num_kb - 1) umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 8) {
+    // ============================ dequant: one thread per weight row ============================
+    const int r = threadIdx.x - 256;
+    int grow = n0 + r;
+    if (grow >= P.n) grow = P.n - 1;  // rows past N are zero-filled by TMA; keep the scale loads in bounds
+    const uint8_t* rowp = P.rows + (size_t)grow * P.pitch;
+    const int swz = r & 7;
+    unsigned char* drow_base = nullptr;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int sp = kb % SP, sd = kb % SD;
+      // group scale / zero point of the two 32-element halves of this k block
+      int g0 = (kb * BLOCK_K) / P.group, g1 = (kb * BLOCK_K + 32) / P.group;
+      if (g0 >= P.ngroups) g0 = P.ngroups - 1;
+      if (g1 >= P.ngroups) g1 = P.ngroups - 1;
+      const float sc0 = ns_scale_at(rowp + P.sc_off, P.stype, g0);
+      const float sc1 = (g1 == g0) ? sc0 : ns_scale_at(rowp + P.sc_off, P.stype, g1);
+      float of0 = 136.f, of1 = 136.f;  // 128 (bf16 magic) + 8 (nibble bias) [+ zero point]
+      if (P.asym) {
+        of0 += (float)(int)(signed char)rowp[P.zp_off + g0];
+        of1 += (float)(int)(signed char)rowp[P.zp_off + g1];
+      }
+      const __nv_bfloat162 s2[2] = {__float2bfloat162_rn(sc0), __float2bfloat162_rn(sc1)};
+      const __nv_bfloat162 o2[2] = {__float2bfloat162_rn(of0), __float2bfloat162_rn(of1)};
+
+      mbar_wait(&p_full[sp], (kb / SP) & 1);
+      const uint4* pk = reinterpret_cast<const uint4*>(packed + sp * PACKED_STAGE + r * 32);
+      const uint4 q0 = pk[0], q1 = pk[1];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_empty[sp]);  // nibbles are in registers
+      if (kb >= SD) mbar_wait(&d_empty[sd], ((kb / SD) - 1) & 1);
+      drow_base = deq + sd * DEQ_STAGE + (r >> 3) * 1024 + swz * 128;
+      const uint32_t words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {  // packed word c = k 8c..8c+7 = 16-byte chunk c of the bf16 row
+        const int h = c >> 2;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t t = ((words[c] >> (4 * j)) & 0x000F000Fu) | 0x43004300u;  // bf16x2 (128 + e(2j), 128 + e(2j+1))
+          __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&t);
+          v = __hmul2(__hsub2(v, o2[h]), s2[h]);
+          o[j] = *reinterpret_cast<uint32_t*>(&v);
+        }
+        *reinterpret_cast<uint4*>(drow_base + ((c ^ swz) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d_full[sd]);
+    }
+  } else if (warp >= 4) {
+    // ============================ epilogue: TMEM -> registers -> global ============================
+    const int q = warp - 4;  // TMEM lane quarter == warp % 4
+    const int nrow = n0 + q * 32 + lane;
+    const bool nvalid = nrow < P.n;
+    pdl_wait();  // dst / residual may still be in use by the preceding kernel
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const float bcast_bias = (P.bias && P.bias_bcast && nvalid) ? P.bias[nrow] : 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < T; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      TMEM_LD_32X32B_X32(taddr, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int t = t0 + c0 + j;
+        if (nvalid && t < P.m) {
+          const size_t o = (size_t)t * P.ldo + nrow;
+          float x = __uint_as_float(v[j]) + bcast_bias;
+          if (P.bias && !P.bias_bcast) x += P.bias[o];
+          if (P.residual) x += P.residual[o];
+          P.dst[o] = x;
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)T) : "memory");
+  }
+}
+
+// fp32 -> bf16 activations [m][kpad], zero padded, optional column gather
+__global__ void __launch_bounds__(256) act_to_bf16_kernel(const float* __restrict__ A, int lda, int M, int K, int kpad,
+                                                          const int* __restrict__ shuffle, __nv_bfloat16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 2 elements
+  const size_t total = (size_t)M * (kpad >> 1);
+  if (idx >= total) return;
+  const int m = (int)(idx / (kpad >> 1)), k = (int)(idx - (size_t)m * (kpad >> 1)) * 2;
+  float a = 0.f, b = 0.f;
+  if (k < K) a = A[(size_t)m * lda + (shuffle ? shuffle[k] : k)];
+  if (k + 1 < K) b = A[(size_t)m * lda + (shuffle ? shuffle[k + 1] : k + 1)];
+  reinterpret_cast<__nv_bfloat162*>(out)[idx] = __floats2bfloat162_rn(a, b);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+template <int T>
+int launch_t(const CUtensorMap& mw, const CUtensorMap& ma, const GemmParams& P, cudaStream_t st) {
+  auto kern = gemm_w4_tc_kernel<T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<T>::total));
+    attr_set = true;
+  }
+  dim3 grid((P.n + BLOCK_N - 1) / BLOCK_N, (P.m + T - 1) / T);
+  NS_CUDA_TRY(ns_launch_pdl(kern, grid, dim3(kThreads), (size_t)Smem<T>::total, st, mw, ma, P));
+  ns_count_launch();
+  return NS_OK;
+}
+
+}  // namespace
+
+size_t ns_gemm_tc_workspace_bytes(int m, int kpad) { return ns_round_up((size_t)m * kpad * 2, 256); }
+
+bool ns_gemm_tc_supported(const ns_weight* w) { return w->wfmt == NS_W_S4 && (w->group % 32 == 0 || w->group == w->k); }
+
+// phase 1: fp32 activations -> bf16 [m][kpad] in ws (ns_gemm_tc_workspace_bytes(m, kpad) bytes)
+int ns_launch_act_bf16(const ns_weight* w, const float* act, int lda, int m, void* ws, cudaStream_t st) {
+  const size_t total = (size_t)m * (w->kpad >> 1);
+  NS_CUDA_TRY(ns_launch_pdl(act_to_bf16_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, act, lda, m, w->k,
+                            w->kpad, (const int*)w->shuffle, (__nv_bfloat16*)ws));
+  ns_count_launch();
+  return NS_OK;
+}
+
+// silu(gate) * up, elementwise (epilogues Swish alpha=-1 + Mul of ip_fusion_ffn.cpp:408-470, kernel_ref.h:1574)
+__global__ void __launch_bounds__(256) silu_mul_kernel(const float* __restrict__ g, const float* __restrict__ u,
+                                                       float* __restrict__ out, float* __restrict__ aux, size_t total) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float x = g[i];
+  const float sg = x / (1.f + expf(-x));
+  if (aux) aux[i] = sg;
+  out[i] = sg * u[i];
+}
+int ns_launch_silu_mul(const float* g, const float* u, float* out, float* aux, size_t total, cudaStream_t st) {
+  NS_CUDA_TRY(ns_launch_pdl(silu_mul_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, g, u, out, aux, total));
+  ns_count_launch();
+  return NS_OK;
+}
+
+// phase 2: weights x bf16 activations already in ws
+int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, int m, const float* bias, int bias_bcast,
+                      const float* residual, cudaStream_t st) {
+  if (!ns_gemm_tc_supported(w)) {
+    ns_set_error("tensor-core GEMM: only 4-bit integer weights with 32-multiple groups are supported");
+    return NS_E_UNSUPPORTED;
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    ns_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return NS_E_CUDA;
+  }
+  const __nv_bfloat16* abf = (const __nv_bfloat16*)ws;
+  int T = m <= 32 ? 32 : (m <= 64 ? 64 : (m <= 128 ? 128 : 256));
+  CUtensorMap mw, ma;
+  {
+    // packed nibbles: uint8 [n][q_bytes] with row pitch `pitch`; box = 32 bytes (64 k) x 128 rows, no swizzle
+    cuuint64_t dims[2] = {(cuuint64_t)w->q_bytes, (cuuint64_t)w->n};
+    cuuint64_t strides[1] = {(cuuint64_t)w->pitch};
+    cuuint32_t box[2] = {BLOCK_K / 2, BLOCK_N};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)w->rows, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ns_set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+      return NS_E_CUDA;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)w->kpad, (cuuint64_t)m};
+    cuuint64_t strides[1] = {(cuuint64_t)w->kpad * 2};
+    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)T};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)abf, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ns_set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+      return NS_E_CUDA;
+    }
+  }
+  GemmParams P;
+  P.rows = w->rows;
+  P.pitch = w->pitch;
+  P.sc_off = w->sc_off;
+  P.zp_off = w->zp_off;
+  P.stype = w->stype;
+  P.asym = w->asym;
+  P.group = w->group;
+  P.ngroups = w->ngroups;
+  P.n = w->n;
+  P.k = w->k;
+  P.kpad = w->kpad;
+  P.m = m;
+  P.dst = dst;
+  P.ldo = ldo;
+  P.bias = bias;
+  P.bias_bcast = bias_bcast;
+  P.residual = residual;
+  switch (T) {
+    case 32: return launch_t<32>(mw, ma, P, st);
+    case 64: return launch_t<64>(mw, ma, P, st);
+    case 128: return launch_t<128>(mw, ma, P, st);
+    default: return launch_t<256>(mw, ma, P, st);
+  }
+}

@@ -349,7 +349,8 @@ int launch_asym(const GemvParams& P, bool asym, int mt, size_t smem, cudaStream_
 // Largest activation-row tile one GEMV launch can take for this weight (bounded by shared memory).
 int ns_gemv_tile_rows(const ns_weight* w) {
   const bool fmode = (w->comp == NS_COMP_F32 || w->comp == NS_COMP_BF16);
-  const size_t per_row = fmode ? (size_t)w->kpad * 4 : (size_t)w->kpad + (size_t)ns_meta_stride(w->kpad) * 8;
+  const size_t per_row =
+      fmode ? (size_t)w->kpad * 4 : ns_round_up((size_t)w->kpad, 1024) + (size_t)ns_meta_stride(w->kpad) * 8;
   int mt = 4;
   // int8 activations of 4 rows must leave room for a useful ring next to them (two CTAs per SM)
   const size_t cap = fmode ? 96 * 1024 : 64 * 1024;
@@ -434,10 +435,12 @@ int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* ac
     P.meta_stride = 0;
     smem = (size_t)mt * kpad * 4;
   } else {
-    P.meta_off = (int)ns_round_up((size_t)m * kpad, 16);
+    // int8 image: [m][act_row] bytes then [m][meta_stride] int2; 4-bit weights use the ring layout (act_prep.cu)
+    const size_t act_row = (w0->wfmt == NS_W_S4) ? ns_round_up((size_t)kpad, 1024) : (size_t)kpad;
+    P.meta_off = (int)ns_round_up((size_t)m * act_row, 16);
     P.meta_stride = meta_stride;
     P.act_bytes = (int)(P.meta_off + (size_t)m * meta_stride * 8);
-    smem = ns_round_up((size_t)mt * kpad, 16) + (size_t)mt * meta_stride * 8;
+    smem = ns_round_up((size_t)mt * act_row, 16) + (size_t)mt * meta_stride * 8;
   }
   smem = ns_round_up(smem, 16);
   const bool asym = w0->asym != 0;

@@ -7,30 +7,30 @@
 // Why a ring: at 6.6 TB/s each of the 148 SMs must keep >= ~45-90 KB of loads in flight (Little's law, ~1-2 us loaded
 // HBM latency); register-staged loads cap that at occupancy x 128 B per thread.  Here one elected producer thread per CTA
 // issues cp.async.bulk (UBLKCP) copies of whole weight-row PAIRS -- a row of the NSB layout is one contiguous
-// [nibbles | scales | zero-points] byte range -- into a ring of `stages` slots guarded by full/empty mbarriers; ~100 KB
-// per CTA, 2 CTAs per SM, stay in flight regardless of what the consumer warps are doing.  Each of the 8 consumer warps
-// owns a whole stage at a time (two rows), so there is no cross-warp reduction and rows are dealt round-robin over
-// CTAs (perfect balance at any N).  The producer starts streaming BEFORE griddepcontrol.wait: under programmatic
-// dependent launch the next kernel's ring fills while the previous kernel drains.
+// [nibbles | scales | zero-points] byte range -- into a ring of slots guarded by full/empty mbarriers.  Each consumer warp
+// owns a whole stage at a time (two rows): no cross-warp reduction, rows dealt round-robin over CTAs (balanced at any N).
+// Occupancy is planned for programmatic dependent launch: a CTA takes <= 1/4 of an SM (4 consumer warps + 1 producer
+// warp, <= 56 KB) and a launch uses 2 CTAs per SM, so the NEXT kernel's CTAs are co-resident while this one runs; their
+// producers stream BEFORE griddepcontrol.wait and the hand-over between dependent kernels costs no HBM idle time.
 // Roofline: HBM.  Algorithmic bytes per launch = sum over weights of N*K/2 + N*ceil(K/g)*(scale_bytes [+1 if asym]).
 #include "nsb.cuh"
 
 namespace {
 
-constexpr int kConsumers = 8;
+constexpr int kConsumers = 4;
 constexpr int kThreads = (kConsumers + 1) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
     asm volatile(
@@ -40,15 +40,46 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
   } while (!ok);
 }
 // TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  unsigned short r;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ int lds8s(uint32_t a) {
+  int r;
+  asm volatile("ld.shared.s8 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
+template <int STYPE>
+__device__ __forceinline__ float lds_scale(uint32_t base, int idx) {
+  if (STYPE == NS_S_F32) return __uint_as_float(lds32(base + 4 * idx));
+  if (STYPE == NS_S_F16) return __half2float(__ushort_as_half((unsigned short)lds16(base + 2 * idx)));
+  return __uint_as_float(lds16(base + 2 * idx) << 16);
 }
 
 struct PairSrc {
@@ -85,27 +116,37 @@ __device__ __forceinline__ PairSrc resolve_pair(const GemvParams& P, int p) {
   return s;
 }
 
-template <int AMODE, int M, bool ASYM>
-__global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams P, int ring_off, int stages) {
+struct RingCfg {
+  int ring_off;     // byte offset of the ring inside dynamic shared memory
+  int stages;
+  int act_row;      // bytes per activation row in the staged image
+  uint32_t cpg_magic;  // ceil(2^32 / cpg): gi = umulhi(c, magic)
+};
+
+template <int AMODE, int M, bool ASYM, int STYPE>
+__global__ void __launch_bounds__(kThreads, 4) gemv_ring_kernel(const GemvParams P, const RingCfg R) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stage_bytes = 2 * P.pitch;
-  unsigned char* ring = smem + ring_off;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * stage_bytes);
-  uint64_t* empty = full + stages;
+  const int stages = R.stages;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring = smem_base + R.ring_off;
+  const uint32_t full0 = ring + (uint32_t)stages * stage_bytes;
+  const uint32_t empty0 = full0 + 8u * stages;
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   const int first = blockIdx.x;
-  const int my_units = first < P.npairs ? (P.npairs - first + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int gstride = (int)gridDim.x;
+  const int my_units = first < P.npairs ? (P.npairs - first + gstride - 1) / gstride : 0;
 
   if (warp == kConsumers) {
     // ===================== producer: stream whole row pairs, never touches activations =====================
@@ -113,12 +154,12 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
       int s = 0;
       uint32_t phase = 0;
       for (int j = 0; j < my_units; ++j) {
-        if (j >= stages) mbar_wait(&empty[s], phase ^ 1);
-        const PairSrc ps = resolve_pair(P, first + j * (int)gridDim.x);
-        unsigned char* dst = ring + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-        bulk_g2s(dst, ps.r0, (uint32_t)P.pitch, &full[s]);
-        bulk_g2s(dst + P.pitch, ps.r1, (uint32_t)P.pitch, &full[s]);
+        if (j >= stages) mbar_wait(empty0 + 8 * s, phase ^ 1);
+        const PairSrc ps = resolve_pair(P, first + j * gstride);
+        const uint32_t dst = ring + (uint32_t)s * stage_bytes;
+        mbar_expect_tx(full0 + 8 * s, (uint32_t)stage_bytes);
+        bulk_g2s(dst, ps.r0, (uint32_t)P.pitch, full0 + 8 * s);
+        bulk_g2s(dst + P.pitch, ps.r1, (uint32_t)P.pitch, full0 + 8 * s);
         if (++s == stages) {
           s = 0;
           phase ^= 1;
@@ -137,16 +178,20 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
     for (int i = threadIdx.x; i < nvec; i += kConsumers * 32) dstv[i] = src[i];
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kConsumers * 32) : "memory");
-  const int2* meta_s = reinterpret_cast<const int2*>(smem + P.meta_off);
+  const uint32_t meta_s = smem_base + P.meta_off;
   const int nchunks = P.kpad >> 5;
 
+  // stage bookkeeping without divisions: this warp visits units warp, warp+4, ...
+  int s = warp % stages;
+  uint32_t phase = (uint32_t)(warp / stages) & 1u;
+  const int s_step = kConsumers % stages;
+  const uint32_t wrap_extra = (uint32_t)(kConsumers / stages);
+
   for (int j = warp; j < my_units; j += kConsumers) {
-    const int s = j % stages;
-    const uint32_t phase = (uint32_t)(j / stages) & 1u;
-    const PairSrc ps = resolve_pair(P, first + j * (int)gridDim.x);
-    mbar_wait(&full[s], phase);
-    const unsigned char* r0 = ring + (size_t)s * stage_bytes;
-    const unsigned char* r1 = r0 + P.pitch;
+    const PairSrc ps = resolve_pair(P, first + j * gstride);
+    mbar_wait(full0 + 8 * s, phase);
+    const uint32_t r0 = ring + (uint32_t)s * stage_bytes;
+    const uint32_t r1 = r0 + P.pitch;
 
     float acc[2][M];
 #pragma unroll
@@ -156,14 +201,15 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
 
 #pragma unroll 2
     for (int c = lane; c < nchunks; c += 32) {
-      const uint4 wv[2] = {reinterpret_cast<const uint4*>(r0)[c], reinterpret_cast<const uint4*>(r1)[c]};
-      const int gi = (P.cpg == 1) ? c : c / P.cpg;
-      const float ws[2] = {ns_scale_at(r0 + P.sc_off, P.stype, gi), ns_scale_at(r1 + P.sc_off, P.stype, gi)};
+      const uint4 wv[2] = {lds128(r0 + 16 * c), lds128(r1 + 16 * c)};
+      const int gi = (P.cpg == 1) ? c : (int)__umulhi((uint32_t)c, R.cpg_magic);
+      const float ws[2] = {lds_scale<STYPE>(r0 + P.sc_off, gi), lds_scale<STYPE>(r1 + P.sc_off, gi)};
       int off[2] = {8, 8};
       if (ASYM) {
-        off[0] += (int)(signed char)r0[P.zp_off + gi];
-        off[1] += (int)(signed char)r1[P.zp_off + gi];
+        off[0] += lds8s(r0 + P.zp_off + gi);
+        off[1] += lds8s(r1 + P.zp_off + gi);
       }
+      // low nibbles as bytes, high nibbles as bytes * 16 (no shift): exact, divided out after the dot
       uint32_t lo[2][4], hi[2][4];
       int su[2] = {0, 0};
 #pragma unroll
@@ -172,45 +218,60 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           lo[r][i] = ww[i] & 0x0F0F0F0Fu;
-          hi[r][i] = (ww[i] >> 4) & 0x0F0F0F0Fu;
-          if (AMODE == A_U8) {  // sum of the weight codes, needed for the activation zero point
-            su[r] = dp4a_ss(0x01010101, (int)lo[r][i], su[r]);
-            su[r] = dp4a_ss(0x01010101, (int)hi[r][i], su[r]);
+          hi[r][i] = ww[i] & 0xF0F0F0F0u;
+        }
+        if (AMODE == A_U8) {  // sum of the weight codes, needed for the activation zero point
+          int sl = 0, sh = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            sl = dp4a_uu(lo[r][i], 0x01010101u, sl);
+            sh = dp4a_uu(hi[r][i], 0x01010101u, sh);
           }
+          su[r] = sl + (sh >> 4);
         }
       }
+      // activation image: per 32-chunk super-block the first 16 B of every chunk, then the second 16 B (conflict-free)
+      const uint32_t a_off = (uint32_t)(c >> 5) * 1024u + (uint32_t)(c & 31) * 16u;
 #pragma unroll
       for (int m = 0; m < M; ++m) {
-        const uint4* ap = reinterpret_cast<const uint4*>(smem + (size_t)m * P.kpad) + 2 * c;
-        const uint4 a0 = ap[0], a1 = ap[1];
-        const int2 mt = meta_s[m * P.meta_stride + c];
-        const float a_scale = __int_as_float(mt.x);
+        const uint32_t ab = smem_base + (uint32_t)m * R.act_row + a_off;
+        const uint4 a0 = lds128(ab), a1 = lds128(ab + 512);
+        const uint2 mt = lds64(meta_s + 8u * (uint32_t)(m * P.meta_stride + c));
+        const float a_scale = __uint_as_float(mt.x);
         const int sa = (int)(short)(mt.y & 0xffff);
-        const int za = (mt.y >> 16) & 0xff;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          int ps_ = 0;
+          int pl = 0, ph = 0;
           // NSB4: word i pairs with activation words (Alo_i, Ahi_i) = ((a0,a4,a1,a5),(a2,a6,a3,a7)) of 8-group i
           if (AMODE == A_U8) {
-            ps_ = dp4a_uu(a0.x, lo[r][0], ps_); ps_ = dp4a_uu(a0.y, hi[r][0], ps_);
-            ps_ = dp4a_uu(a0.z, lo[r][1], ps_); ps_ = dp4a_uu(a0.w, hi[r][1], ps_);
-            ps_ = dp4a_uu(a1.x, lo[r][2], ps_); ps_ = dp4a_uu(a1.y, hi[r][2], ps_);
-            ps_ = dp4a_uu(a1.z, lo[r][3], ps_); ps_ = dp4a_uu(a1.w, hi[r][3], ps_);
-          } else {
-            ps_ = dp4a_ss((int)a0.x, (int)lo[r][0], ps_); ps_ = dp4a_ss((int)a0.y, (int)hi[r][0], ps_);
-            ps_ = dp4a_ss((int)a0.z, (int)lo[r][1], ps_); ps_ = dp4a_ss((int)a0.w, (int)hi[r][1], ps_);
-            ps_ = dp4a_ss((int)a1.x, (int)lo[r][2], ps_); ps_ = dp4a_ss((int)a1.y, (int)hi[r][2], ps_);
-            ps_ = dp4a_ss((int)a1.z, (int)lo[r][3], ps_); ps_ = dp4a_ss((int)a1.w, (int)hi[r][3], ps_);
+            pl = dp4a_uu(a0.x, lo[r][0], pl); ph = dp4a_uu(a0.y, hi[r][0], ph);
+            pl = dp4a_uu(a0.z, lo[r][1], pl); ph = dp4a_uu(a0.w, hi[r][1], ph);
+            pl = dp4a_uu(a1.x, lo[r][2], pl); ph = dp4a_uu(a1.y, hi[r][2], ph);
+            pl = dp4a_uu(a1.z, lo[r][3], pl); ph = dp4a_uu(a1.w, hi[r][3], ph);
+          } else {  // signed activations x unsigned weight bytes
+            pl = dp4a_us(lo[r][0], (int)a0.x, pl); ph = dp4a_us(hi[r][0], (int)a0.y, ph);
+            pl = dp4a_us(lo[r][1], (int)a0.z, pl); ph = dp4a_us(hi[r][1], (int)a0.w, ph);
+            pl = dp4a_us(lo[r][2], (int)a1.x, pl); ph = dp4a_us(hi[r][2], (int)a1.y, ph);
+            pl = dp4a_us(lo[r][3], (int)a1.z, pl); ph = dp4a_us(hi[r][3], (int)a1.w, ph);
           }
           // sum (a - za)(u - off) = sum a*u - off*Sa - za*(Su - 32*off): one exact integer per 32-element chunk
-          int isum = ps_ - off[r] * sa;
-          if (AMODE == A_U8) isum -= za * (su[r] - 32 * off[r]);
+          int isum = pl + (ph >> 4) - off[r] * sa;  // ph is an exact multiple of 16
+          if (AMODE == A_U8) {
+            const int za = (int)((mt.y >> 16) & 0xff);
+            isum -= za * (su[r] - 32 * off[r]);
+          }
           acc[r][m] = fmaf((float)isum, a_scale * ws[r], acc[r][m]);
         }
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);  // slot may be refilled
+    if (lane == 0) mbar_arrive(empty0 + 8 * s);  // slot may be refilled
+    s += s_step;
+    phase ^= wrap_extra & 1u;
+    if (s >= stages) {
+      s -= stages;
+      phase ^= 1u;
+    }
 
 #pragma unroll
     for (int r = 0; r < 2; ++r)
@@ -248,53 +309,69 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
   }
 }
 
-template <int AMODE, int M, bool ASYM>
+template <int AMODE, int M, bool ASYM, int STYPE>
 int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
-  auto kern = gemv_ring_kernel<AMODE, M, ASYM>;
+  auto kern = gemv_ring_kernel<AMODE, M, ASYM, STYPE>;
   static bool attr_set = false;
   if (!attr_set) {
     NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const int stage_bytes = 2 * P.pitch;
-  const size_t act_region = ns_round_up(ns_round_up((size_t)mt * P.kpad, 16) + (size_t)mt * P.meta_stride * 8, 128);
-  const size_t budget = 110 * 1024;  // two CTAs per SM
-  int stages = 2;
-  int ctas_per_sm = 2;
-  if (act_region + 2 * (size_t)stage_bytes + 64 <= budget) {
-    stages = (int)((budget - act_region - 64) / (stage_bytes + 16));
-    if (stages > 64) stages = 64;
-  } else {
-    // very long rows: one CTA per SM with whatever ring fits
-    ctas_per_sm = 1;
-    stages = (int)((200 * 1024 - act_region - 64) / (stage_bytes + 16));
-    if (stages < 1) {
-      ns_set_error("gemv_ring: row pitch %d too large for shared memory", P.pitch);
-      return NS_E_UNSUPPORTED;
-    }
-    if (stages > 16) stages = 16;
+  const int act_row = (int)ns_round_up((size_t)P.kpad, 1024);
+  const size_t act_region = ns_round_up((size_t)mt * act_row + (size_t)mt * P.meta_stride * 8, 128);
+  // Shared-memory plan: a quarter of an SM when that still leaves >= 2 ring stages (so the next kernel co-resides under
+  // PDL), else half, else a whole SM.
+  const size_t budgets[3] = {55 * 1024, 110 * 1024, 200 * 1024};
+  int stages = 0;
+  size_t budget = 0;
+  for (int i = 0; i < 3; ++i) {
+    budget = budgets[i];
+    if (budget > act_region + 64) stages = (int)((budget - act_region - 64) / (stage_bytes + 16));
+    if (stages >= (i < 2 ? 3 : 1)) break;
+    stages = 0;
   }
+  if (stages < 1) {
+    ns_set_error("gemv_ring: row pitch %d too large for shared memory", P.pitch);
+    return NS_E_UNSUPPORTED;
+  }
+  if (stages > 32) stages = 32;
   const size_t smem = act_region + (size_t)stages * stage_bytes + (size_t)stages * 16;
+  const int ctas_per_sm = budget > 110 * 1024 ? 1 : 2;
   int grid = ns_num_sms() * ctas_per_sm;
   if (grid > P.npairs) grid = P.npairs;
   if (grid < 1) grid = 1;
-  NS_CUDA_TRY(ns_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, st, P, (int)act_region, stages));
+  RingCfg R;
+  R.ring_off = (int)act_region;
+  R.stages = stages;
+  R.act_row = act_row;
+  R.cpg_magic = P.cpg > 1 ? (uint32_t)((0x100000000ull + (uint64_t)P.cpg - 1) / (uint64_t)P.cpg) : 0u;
+  NS_CUDA_TRY(ns_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, st, P, R));
   ns_count_launch();
   return NS_OK;
 }
 
-template <int AMODE, bool ASYM>
+template <int AMODE, bool ASYM, int STYPE>
 int launch_m(const GemvParams& P, int mt, cudaStream_t st) {
   switch (mt) {
-    case 1: return launch_one<AMODE, 1, ASYM>(P, mt, st);
-    case 2: return launch_one<AMODE, 2, ASYM>(P, mt, st);
-    default: return launch_one<AMODE, 4, ASYM>(P, mt, st);
+    case 1: return launch_one<AMODE, 1, ASYM, STYPE>(P, mt, st);
+    case 2: return launch_one<AMODE, 2, ASYM, STYPE>(P, mt, st);
+    default: return launch_one<AMODE, 4, ASYM, STYPE>(P, mt, st);
+  }
+}
+
+template <int AMODE, bool ASYM>
+int launch_s(const GemvParams& P, int mt, cudaStream_t st) {
+  switch (P.stype) {
+    case NS_S_F32: return launch_m<AMODE, ASYM, NS_S_F32>(P, mt, st);
+    case NS_S_F16: return launch_m<AMODE, ASYM, NS_S_F16>(P, mt, st);
+    default: return launch_m<AMODE, ASYM, NS_S_BF16>(P, mt, st);
   }
 }
 
 }  // namespace
 
 int ns_launch_gemv_ring(const GemvParams& P, int amode, bool asym, int mt, cudaStream_t st) {
-  if (amode == A_U8) return asym ? launch_m<A_U8, true>(P, mt, st) : launch_m<A_U8, false>(P, mt, st);
-  return asym ? launch_m<A_S8, true>(P, mt, st) : launch_m<A_S8, false>(P, mt, st);
+  if (amode == A_U8) return asym ? launch_s<A_U8, true>(P, mt, st) : launch_s<A_U8, false>(P, mt, st);
+  return asym ? launch_s<A_S8, true>(P, mt, st) : launch_s<A_S8, false>(P, mt, st);
 }

@@ -81,6 +81,14 @@ int ns_launch_repack_btla(const void* qbuf_dev, const void* sc_dev, int src_styp
                           int kpad_src, int ntile, int packrow, int is_float, ns_weight* w, cudaStream_t st);
 int ns_launch_dequant(const ns_weight* w, float* dst, int ld, cudaStream_t st);
 
+// tensor-core path (gemm_tc.cu)
+size_t ns_gemm_tc_workspace_bytes(int m, int kpad);
+bool ns_gemm_tc_supported(const ns_weight* w);
+int ns_launch_act_bf16(const ns_weight* w, const float* act, int lda, int m, void* ws, cudaStream_t st);
+int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, int m, const float* bias, int bias_bcast,
+                      const float* residual, cudaStream_t st);
+int ns_launch_silu_mul(const float* g, const float* u, float* out, float* aux, size_t total, cudaStream_t st);
+
 enum { NS_GEMV_PLAIN = 0, NS_GEMV_CONCAT = 1, NS_GEMV_GATE_UP_SILU = 2 };
 enum { A_S8 = 0, A_U8 = 1, A_F32 = 2 };
 
