@@ -246,9 +246,14 @@ def run_ours(args):
     torch.cuda.synchronize()
     wsp = C.c_void_p(ws.data_ptr())
 
+    dbg = os.environ.get("NS_SYNC_EACH") is not None
+
     def step_calls():
         """one token's matmuls: fused QKV, o-proj, fused gate/up+SiLU*mul -> down, lm_head"""
-        for lay in layers:
+        for li, lay in enumerate(layers):
+            if dbg:
+                L.bestla_device_sync(queue)
+                print("layer", li, flush=True)
             rc = L.ns_mul_qkv(lay["wq"].h, lay["wk"].h, lay["wv"].h, C.c_void_p(x.data_ptr()), N_EMBD, C.c_void_p(qkv.data_ptr()),
                               N_EMBD, 1, wsp, queue)
             rc |= L.ns_mul_mat(lay["wo"].h, C.c_void_p(attn.data_ptr()), N_EMBD, C.c_void_p(o.data_ptr()), N_EMBD, 1, None, None, 0,

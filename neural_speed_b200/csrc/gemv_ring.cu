@@ -181,11 +181,11 @@ __global__ void __launch_bounds__(kThreads, 4) gemv_ring_kernel(const GemvParams
   const uint32_t meta_s = smem_base + P.meta_off;
   const int nchunks = P.kpad >> 5;
 
-  // stage bookkeeping without divisions: this warp visits units warp, warp+4, ...
-  int s = warp % stages;
-  uint32_t phase = (uint32_t)(warp / stages) & 1u;
-  const int s_step = kConsumers % stages;
-  const uint32_t wrap_extra = (uint32_t)(kConsumers / stages);
+  // This warp visits units warp, warp+4, ... .  `stages` is a multiple of kConsumers (launcher), so stage s is only ever
+  // consumed by warp s % kConsumers: every mbarrier is waited on by ONE warp that observes all of its phases in order.
+  // (A parity wait issued a whole phase early returns true immediately -- waiters must never run ahead of a barrier.)
+  int s = warp;
+  uint32_t phase = 0;
 
   for (int j = warp; j < my_units; j += kConsumers) {
     const PairSrc ps = resolve_pair(P, first + j * gstride);
@@ -266,8 +266,7 @@ __global__ void __launch_bounds__(kThreads, 4) gemv_ring_kernel(const GemvParams
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + 8 * s);  // slot may be refilled
-    s += s_step;
-    phase ^= wrap_extra & 1u;
+    s += kConsumers;
     if (s >= stages) {
       s -= stages;
       phase ^= 1u;
@@ -328,10 +327,11 @@ int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
   for (int i = 0; i < 3; ++i) {
     budget = budgets[i];
     if (budget > act_region + 64) stages = (int)((budget - act_region - 64) / (stage_bytes + 16));
-    if (stages >= (i < 2 ? 3 : 1)) break;
+    stages -= stages % kConsumers;  // one consumer warp per stage residue class (see kernel)
+    if (stages >= kConsumers) break;
     stages = 0;
   }
-  if (stages < 1) {
+  if (stages < kConsumers) {
     ns_set_error("gemv_ring: row pitch %d too large for shared memory", P.pitch);
     return NS_E_UNSUPPORTED;
   }

@@ -126,8 +126,9 @@ static inline cudaError_t ns_launch_pdl(void (*kern)(Args...), dim3 grid, dim3 b
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("NS_NO_PDL") != nullptr;  // debugging aid: plain stream order
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = no_pdl ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 

@@ -66,8 +66,9 @@ def test_tc_gemm_int4_vs_oracle(m, n, k, g, asym):
     scale = np.abs(want).max()
     assert np.abs(got - want).max() <= 2e-3 * scale
     ref32 = oracle.gemm_f64acc(a, oracle.btla_dequant(q, sc, zp, g))
-    assert np.abs(got - ref32).max() <= 2e-2 * max(1.0, k / 4096)          # CompBf16 UT tolerance
-    assert np.abs(got - ref32).max() <= 1e-2 * np.abs(ref32).max()         # north-star logits bar
+    # vs fp32 GEMM on the dequantised weights: bf16 operand rounding only (the reference's CompBf16 UT allows 2e-2 abs on
+    # outputs of magnitude ~10 at K=4096, bestla_ut.h:80-94); north-star logits bar = 1e-2 of the output range
+    assert np.abs(got - ref32).max() <= 1e-2 * np.abs(ref32).max()
 
 
 def test_tc_gemm_q4_0_prefill_vs_cpu_path():

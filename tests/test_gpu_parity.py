@@ -124,7 +124,8 @@ def test_q4_0_mul_mat_vs_oracle(n, k, m):
     a = rng.normal(0, 1.0, (m, k)).astype(np.float32)
     rows = oracle.quantize_q4_0(w)
     want = oracle.mul_mat_q4_0_f32(rows, a)
-    got = run_mul_mat(ns.Weight.from_q4_0_host(rows, n, k), a)
+    # exact-integer GEMV path (M <= 4 by default; forced for larger M, where the default is the bf16 tensor-core GEMM)
+    got = run_mul_mat(ns.Weight.from_q4_0_host(rows, n, k), a, flags=ns.MM_FORCE_GEMV)
     close(got, want)
     # greedy pick parity on this "logit" row
     assert oracle.argmax(got[0]) == oracle.argmax(want[0])
@@ -138,7 +139,12 @@ def test_q4_0_golden_fixture_through_host_abi():
     rc = ns.lib().ns_mul_mat_q4_0_f32_host(wq.ctypes.data_as(C.c_void_p), wq.shape[1], a.ctypes.data_as(C.c_void_p),
                                            out.ctypes.data_as(C.c_void_p), k, n, a.shape[0])
     assert rc == 0, ns.last_error()
-    close(out, want)
+    close(out, want, 1e-2)  # 5 rows > 4: the host ABI takes the bf16 tensor-core GEMM (north-star logits bar)
+    out4 = np.zeros((4, n), np.float32)
+    rc = ns.lib().ns_mul_mat_q4_0_f32_host(wq.ctypes.data_as(C.c_void_p), wq.shape[1], a.ctypes.data_as(C.c_void_p),
+                                           out4.ctypes.data_as(C.c_void_p), k, n, 4)
+    assert rc == 0, ns.last_error()
+    close(out4, want[:4])  # <= 4 rows: exact-integer GEMV path
 
 
 def test_q4_0_block_sums_are_exact_integers():
@@ -194,7 +200,7 @@ def test_btla_s4_s8_activations(asym, m):
     q, sc, zp = oracle.btla_quantize(w, g, 4, asym)
     a8, asc = oracle.btla_quantize_act_s8(a, g)
     want = oracle.btla_gemv_s8s8(a8, asc, q, sc, zp, g)
-    got = run_mul_mat(ns.Weight.from_unpacked(q, sc, zp, g, ns.W_S4, ns.S_F32, ns.COMP_INT8_S8), a)
+    got = run_mul_mat(ns.Weight.from_unpacked(q, sc, zp, g, ns.W_S4, ns.S_F32, ns.COMP_INT8_S8), a, flags=ns.MM_FORCE_GEMV)
     close(got, want)
 
 
