@@ -9,15 +9,16 @@
 // issues cp.async.bulk (UBLKCP) copies of whole weight-row PAIRS -- a row of the NSB layout is one contiguous
 // [nibbles | scales | zero-points] byte range -- into a ring of slots guarded by full/empty mbarriers.  Each consumer warp
 // owns a whole stage at a time (two rows): no cross-warp reduction, rows dealt round-robin over CTAs (balanced at any N).
-// Occupancy is planned for programmatic dependent launch: a CTA takes <= 1/4 of an SM (4 consumer warps + 1 producer
-// warp, <= 56 KB) and a launch uses 2 CTAs per SM, so the NEXT kernel's CTAs are co-resident while this one runs; their
-// producers stream BEFORE griddepcontrol.wait and the hand-over between dependent kernels costs no HBM idle time.
+// 8 consumer warps + 1 producer warp per CTA, 2 CTAs per SM (~105 KB ring each).  The producer streams BEFORE
+// griddepcontrol.wait, so under programmatic dependent launch a CTA starts filling its ring the moment it becomes
+// resident.  (Measured alternative, r01: quarter-SM CTAs that let the next kernel co-reside were slower -- 8 consumer
+// warps per SM cannot keep up with HBM; the launch-boundary cost is removed instead by the persistent multi-op kernel.)
 // Roofline: HBM.  Algorithmic bytes per launch = sum over weights of N*K/2 + N*ceil(K/g)*(scale_bytes [+1 if asym]).
 #include "nsb.cuh"
 
 namespace {
 
-constexpr int kConsumers = 4;
+constexpr int kConsumers = 8;
 constexpr int kThreads = (kConsumers + 1) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,7 +125,7 @@ struct RingCfg {
 };
 
 template <int AMODE, int M, bool ASYM, int STYPE>
-__global__ void __launch_bounds__(kThreads, 4) gemv_ring_kernel(const GemvParams P, const RingCfg R) {
+__global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams P, const RingCfg R) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stage_bytes = 2 * P.pitch;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 4) gemv_ring_kernel(const GemvParams
   const uint32_t meta_s = smem_base + P.meta_off;
   const int nchunks = P.kpad >> 5;
 
-  // This warp visits units warp, warp+4, ... .  `stages` is a multiple of kConsumers (launcher), so stage s is only ever
+  // This warp visits units warp, warp+kConsumers, ... .  `stages` is a multiple of kConsumers (launcher), so stage s is only ever
   // consumed by warp s % kConsumers: every mbarrier is waited on by ONE warp that observes all of its phases in order.
   // (A parity wait issued a whole phase early returns true immediately -- waiters must never run ahead of a barrier.)
   int s = warp;
@@ -319,12 +320,11 @@ int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
   const int stage_bytes = 2 * P.pitch;
   const int act_row = (int)ns_round_up((size_t)P.kpad, 1024);
   const size_t act_region = ns_round_up((size_t)mt * act_row + (size_t)mt * P.meta_stride * 8, 128);
-  // Shared-memory plan: a quarter of an SM when that still leaves >= 2 ring stages (so the next kernel co-resides under
-  // PDL), else half, else a whole SM.
-  const size_t budgets[3] = {55 * 1024, 110 * 1024, 200 * 1024};
+  // Shared-memory plan: half an SM (two CTAs per SM), or a whole SM for very long rows.
+  const size_t budgets[2] = {110 * 1024, 200 * 1024};
   int stages = 0;
   size_t budget = 0;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 2; ++i) {
     budget = budgets[i];
     if (budget > act_region + 64) stages = (int)((budget - act_region - 64) / (stage_bytes + 16));
     stages -= stages % kConsumers;  // one consumer warp per stage residue class (see kernel)
