@@ -298,6 +298,18 @@ def run_ours(args):
         assert g, ns.last_error()
         return C.c_void_p(g)
 
+    # persistent multi-op kernel: the same 129 matmul nodes, every node waiting (grid barrier) for the previous one
+    prog = ns.Program(1)
+    for lay in layers:
+        prog.add([lay["wq"], lay["wk"], lay["wv"]], ns.Program.CONCAT, x.data_ptr(), N_EMBD, qkv.data_ptr(), 3 * N_EMBD)
+        prog.add([lay["wo"]], ns.Program.PLAIN, attn.data_ptr(), N_EMBD, o.data_ptr(), N_EMBD)
+        prog.add([lay["w1"], lay["w3"]], ns.Program.GATE_UP_SILU, x.data_ptr(), N_EMBD, tmp.data_ptr(), N_FF)
+        prog.add([lay["w2"]], ns.Program.PLAIN, tmp.data_ptr(), N_FF, ffn.data_ptr(), N_EMBD)
+    prog.add([lm_head], ns.Program.PLAIN, x.data_ptr(), N_EMBD, logits.data_ptr(), N_VOCAB)
+    prog.finalize(queue)
+    prog.run(queue)
+    L.bestla_device_sync(queue)
+
     use_graph = not args.no_graph
     g_step = capture(step_calls) if use_graph else None
     g_gemv = capture(gemv_only_calls) if use_graph else None
@@ -335,8 +347,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_step = timed(run_step, args.steps, args.warmup)
+    ms_prog = timed(lambda: prog.run(queue), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    ms_perop = timed(run_step, args.steps, args.warmup)
+    ms_step = ms_prog
     # dominant kernel alone (graph of GEMV launches on pre-quantised activations)
     n_gemv = 4 * n_layers + 1
     if use_graph:
@@ -345,6 +359,7 @@ def run_ours(args):
         ms_gemv = timed(gemv_only_calls, args.steps, args.warmup)
     gemv_gbs = alg_bytes / (ms_gemv * 1e-3) / 1e9
     step_gbs = alg_bytes / (ms_step * 1e-3) / 1e9
+    prog_gbs = alg_bytes / (ms_prog * 1e-3) / 1e9
 
     # ---- e2e: the same token through the host-buffer C-ABI (per-op, H2D activations + D2H results every call)
     e2e = None
@@ -408,16 +423,22 @@ def run_ours(args):
             "dtype": "int8xint4->f32 (q8_0 x q4_0)" if args.fmt == "q4_0" else "u8xint4->f32",
             "data": "synthetic: W~N(0,0.02^2) seed 1234, quantised on device; activations N(0,1)",
             "config": {"workload": f"llama2-7b {args.fmt} decode matmul path, batch 1: {n_gemv} fused weight-only matmuls/token "
-                                   f"({n_layers} layers x [QKV, o, gate/up+SiLU*mul, down] + lm_head), CUDA graph={use_graph}",
+                                   f"({n_layers} layers x [QKV, o, gate/up+SiLU*mul, down] + lm_head), each waiting for the "
+                                   "previous one, activation quantisation fused, ONE persistent cooperative launch per token",
                        "weights": int(n_weights), "packed_bytes_per_step": int(alg_bytes),
                        "l2_policy": "inputs (3.7 GB of weights per step) exceed the 126 MB L2; no flush needed",
                        "parallelism": "replicas" if world > 1 else "single"},
-            "roofline": {"bound": "hbm", "achieved": gemv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gemv_gbs / hbm_peak,
-                         "traffic": None, "kernel": "gemv_kernel<S4,A_S8,M=1>", "launches_per_step": n_gemv,
-                         "avg_launch_us": ms_gemv * 1e3 / n_gemv, "peak_source": peak_kind,
-                         "whole_step_gbs": step_gbs, "whole_step_frac": step_gbs / hbm_peak},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "launches_per_step": launches_per_step, "clocks": clocks, "setup_s": setup_s,
+            "roofline": {"bound": "hbm", "achieved": prog_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": prog_gbs / hbm_peak,
+                         "traffic": None, "kernel": "program_kernel<Q8_0,M=1,sym,f16> (1 launch = 1 token = the whole timed step)",
+                         "launches_per_step": 1, "avg_launch_us": ms_prog * 1e3, "peak_source": peak_kind,
+                         "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "per_op_gemv_only": {"kernel": "gemv_ring_kernel<S8,M=1,sym,f16>", "achieved": gemv_gbs,
+                                              "frac": gemv_gbs / hbm_peak, "avg_launch_us": ms_gemv * 1e3 / n_gemv,
+                                              "launches": n_gemv}},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 1 * args.steps,
+            "launches_per_step": 1, "clocks": clocks, "setup_s": setup_s,
+            "per_op_path": {"tokens_per_s": world * 1000.0 / ms_perop, "ms_per_step": ms_perop, "launches_per_step": launches_per_step,
+                            "note": "same matmuls as 258 separate kernels (act-quant + GEMV) in one CUDA graph with PDL"},
         }
         if n_layers != N_LAYER:
             line["config"]["note"] = f"REDUCED run: {n_layers} of 32 layers (debug only, not a valid bench value)"

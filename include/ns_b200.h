@@ -174,6 +174,23 @@ NS_API ns_graph* ns_graph_end(void* queue);
 NS_API int ns_graph_launch(ns_graph* g, void* queue);
 NS_API void ns_graph_free(ns_graph* g);
 
+/* Persistent multi-op decode kernel: the matmul nodes of one token (M <= 4 rows) executed by ONE cooperative launch --
+ * replaces the per-node walk of ne_graph_compute (core/ne_layers.c:11915) over the llama graph
+ * (models/llama/llama.cpp:217-231,586,612-618,718).  Each op = one ne_mul_mat / ne_mul_qkv / ne_ffn_silu(first half) node:
+ * fp32 device input -> (activation quantisation fused, same arithmetic as the reference's NE_TASK_INIT) -> GEMV ->
+ * epilogue.  mode: 0 plain, 1 concat (outputs of the 1..3 weights concatenated along n in one [m][ldo] row),
+ * 2 gate/up + SiLU*mul.  barrier_before != 0: the op's input is produced by the previous op (grid-wide dependency).
+ * All weights of a program share format / scale type / compute type (4-bit integer weights, integer activations). */
+typedef struct ns_program ns_program;
+NS_API ns_program* ns_program_create(int m);
+NS_API int ns_program_add_matmul(ns_program* p, const ns_weight* const* weights, int nw, int mode, const float* in, int lda,
+                                 float* dst, int ldo, const float* bias, int bias_bcast, const float* residual, float* aux,
+                                 int barrier_before);
+NS_API int ns_program_finalize(ns_program* p, void* queue);
+NS_API int ns_program_run(ns_program* p, void* queue);
+NS_API size_t ns_program_algorithmic_bytes(const ns_program* p);
+NS_API void ns_program_free(ns_program* p);
+
 /* ggml drop-in with HOST buffers: ne_compute_forward_mul_mat_q_f32 (ne_layers.c:7085) for NE_TYPE_Q4_0:
  * dst[ne11][ne01] = src1[ne11][ne00] x src0 rows.  src0 is uploaded/repacked once and cached by address. */
 NS_API int ns_mul_mat_q4_0_f32_host(const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01,

@@ -47,6 +47,8 @@ EXPORTS = [
     "ns_weight_from_q4_0", "ns_weight_from_btla_blob", "ns_weight_from_unpacked", "ns_weight_free", "ns_weight_info",
     "ns_weight_set_comp", "ns_weight_algorithmic_bytes", "ns_weight_dequant_f32",
     "ns_mul_mat", "ns_mul_qkv", "ns_ffn_silu", "ns_mul_mat_q4_0_f32_host",
+    "ns_program_create", "ns_program_add_matmul", "ns_program_finalize", "ns_program_run", "ns_program_algorithmic_bytes",
+    "ns_program_free",
     "ns_prepare_activation", "ns_matmul_prepared", "ns_graph_begin", "ns_graph_end", "ns_graph_launch", "ns_graph_free",
     "ns_device_quantize_q4_0", "ns_device_quantize_act",
     "BTLAGemmPackBSize", "BTLAGemmQuantPackB", "BTLAGemmPackB", "BTLAGemmUnPackB", "ns_quantize_row_q4_0",
@@ -122,6 +124,14 @@ def lib() -> C.CDLL:
     L.ns_mul_mat_q4_0_f32_host.argtypes = [vp, sz, vp, vp, i, i, i]
     L.ns_prepare_activation.argtypes = [vp, vp, i, i, vp, vp]
     L.ns_matmul_prepared.argtypes = [vp, i, i, vp, vp, i, i, vp, i, vp, vp, vp]
+    L.ns_program_create.restype = vp
+    L.ns_program_create.argtypes = [i]
+    L.ns_program_add_matmul.argtypes = [vp, vp, i, i, vp, i, vp, i, vp, i, vp, vp, i]
+    L.ns_program_finalize.argtypes = [vp, vp]
+    L.ns_program_run.argtypes = [vp, vp]
+    L.ns_program_algorithmic_bytes.restype = sz
+    L.ns_program_algorithmic_bytes.argtypes = [vp]
+    L.ns_program_free.argtypes = [vp]
     L.ns_graph_begin.argtypes = [vp]
     L.ns_graph_end.restype = vp
     L.ns_graph_end.argtypes = [vp]
@@ -304,3 +314,42 @@ def ffn_silu(w1: Weight, w2: Weight, w3: Weight, act_ptr: int, lda: int, tmp_ptr
              queue=None):
     _check(lib().ns_ffn_silu(w1.h, w2.h, w3.h, C.c_void_p(act_ptr), lda, C.c_void_p(tmp_ptr), C.c_void_p(dst_ptr), ldo, m,
                              None, queue), "ns_ffn_silu")
+
+
+class Program:
+    """Persistent multi-op decode kernel (ns_program_*): the matmul nodes of one token in one cooperative launch."""
+
+    PLAIN, CONCAT, GATE_UP_SILU = 0, 1, 2
+
+    def __init__(self, m: int = 1):
+        self.h = C.c_void_p(lib().ns_program_create(m))
+        if not self.h:
+            raise RuntimeError("ns_program_create failed: " + last_error())
+        self._keep = []
+
+    def add(self, weights, mode, in_ptr, lda, dst_ptr, ldo, bias_ptr=None, bias_bcast=0, residual_ptr=None, aux_ptr=None,
+            barrier_before=1):
+        arr = (C.c_void_p * 3)(*([w.h for w in weights] + [None] * (3 - len(weights))))
+        self._keep.append(weights)
+        _check(lib().ns_program_add_matmul(self.h, arr, len(weights), mode, C.c_void_p(in_ptr), lda, C.c_void_p(dst_ptr), ldo,
+                                           C.c_void_p(bias_ptr) if bias_ptr else None, bias_bcast,
+                                           C.c_void_p(residual_ptr) if residual_ptr else None,
+                                           C.c_void_p(aux_ptr) if aux_ptr else None, barrier_before), "ns_program_add_matmul")
+
+    def finalize(self, queue=None):
+        _check(lib().ns_program_finalize(self.h, queue), "ns_program_finalize")
+
+    def run(self, queue=None):
+        _check(lib().ns_program_run(self.h, queue), "ns_program_run")
+
+    @property
+    def algorithmic_bytes(self):
+        return int(lib().ns_program_algorithmic_bytes(self.h))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().ns_program_free(self.h)
+                self.h = None
+        except Exception:
+            pass

@@ -100,6 +100,7 @@ int ns_num_sms() {
 
 static cudaStream_t default_stream() { return g_default.stream; }
 static cudaStream_t stream_of(void* queue) { return queue ? (cudaStream_t)queue : default_stream(); }
+cudaStream_t ns_stream_of(void* queue) { return stream_of(queue); }
 
 static void* scratch_get(cudaStream_t st, size_t bytes) {
   std::lock_guard<std::mutex> lk(g_mu);

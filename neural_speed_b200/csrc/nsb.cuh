@@ -57,6 +57,7 @@ bool ns_cuda_ok(cudaError_t e, const char* what);
 int ns_ensure_device();  // 0 ok, <0 NS_E_*
 void ns_count_launch(int n = 1);
 int ns_num_sms();
+cudaStream_t ns_stream_of(void* queue);  // NULL -> the library's default stream
 
 #define NS_CUDA_TRY(expr)                             \
   do {                                                \

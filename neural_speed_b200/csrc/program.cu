@@ -1,0 +1,678 @@
+// program.cu -- persistent multi-op decode kernel: a whole token's worth of weight-only matmuls in ONE launch.
+//
+// What it replaces: the reference rebuilds an ne graph per token and walks it node by node (ne_graph_compute,
+// neural_speed/core/ne_layers.c:11915; llama graph, models/llama/llama.cpp:136-143,217-231,586,612-618,718); every
+// matmul node first quantises its activations (NE_TASK_INIT, ne_layers.c:7143-7157) and then runs the dots.  On B200 a
+// decode GEMV lasts 1.5-8 us, so a kernel boundary (drain + launch + refill of the load pipeline, ~2 us of idle HBM)
+// costs as much as the work.  Here an "ns_program" is the list of matmul nodes of one token; one cooperative launch
+// executes all of them:
+//   * producer warp (1 elected thread per CTA): walks the op list and streams weight-row pairs with cp.async.bulk into the
+//     shared-memory ring, never waiting for activations -- it runs ahead across op boundaries, so HBM stays busy while the
+//     consumers synchronise;
+//   * consumer warps: per op: grid barrier (release/acquire counter in global memory) -> quantise the op's fp32 input
+//     vector(s) into the shared-memory activation image (same arithmetic as act_prep.cu: Q8_0 / BesTLA u8 / s8, bit-exact)
+//     -> dp4a over their ring stages (same arithmetic as gemv_ring.cu) -> epilogue (bias / residual / SiLU*mul).
+// Activations are read with ld.global.cg (L2) because another SM rewrites them between ops within the same launch.
+// Roofline: HBM; algorithmic bytes per launch = sum over ops of N*K/2 + N*ceil(K/g)*(scale_bytes [+1 if asym]).
+#include <vector>
+
+#include "nsb.cuh"
+
+namespace {
+
+constexpr int kConsumers = 8;
+constexpr int kConsumerThreads = kConsumers * 32;
+constexpr int kThreads = kConsumerThreads + 32;
+
+struct ProgOp {
+  const uint8_t* rows[3];
+  int n[3];
+  long long dst_off[3];
+  int nw, mode;
+  int k, kpad, pitch, sc_off, zp_off, cpg, group;
+  uint32_t cpg_magic;
+  const float* in;
+  int lda;
+  float* dst;
+  int ldo;
+  const float* bias;
+  int bias_bcast;
+  const float* residual;
+  float* aux;
+  int npairs;
+  int barrier_before;
+  int act_row, meta_off, meta_stride;
+};
+
+struct ProgCfg {
+  int ring_off;
+  int stages;
+  int slot_bytes;
+  int m;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  unsigned short r;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ int lds8s(uint32_t a) {
+  int r;
+  asm volatile("ld.shared.s8 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+template <int STYPE>
+__device__ __forceinline__ float lds_scale(uint32_t base, int idx) {
+  if (STYPE == NS_S_F32) return __uint_as_float(lds32(base + 4 * idx));
+  if (STYPE == NS_S_F16) return __half2float(__ushort_as_half((unsigned short)lds16(base + 2 * idx)));
+  return __uint_as_float(lds16(base + 2 * idx) << 16);
+}
+__device__ __forceinline__ float4 ldcg4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldcg1(const float* p) {
+  float r;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct PairSrc {
+  const uint8_t* r0;
+  const uint8_t* r1;
+  long long out0, out1;
+  bool valid1;
+};
+__device__ __forceinline__ PairSrc resolve_pair(const ProgOp& P, int p) {
+  PairSrc s;
+  if (P.mode == NS_GEMV_GATE_UP_SILU) {
+    s.r0 = P.rows[0] + (size_t)p * P.pitch;
+    s.r1 = P.rows[1] + (size_t)p * P.pitch;
+    s.out0 = s.out1 = p;
+    s.valid1 = true;
+    return s;
+  }
+  int row = 2 * p, wi = 0;
+  if (P.nw > 1 && row >= P.n[0]) {
+    row -= P.n[0];
+    wi = 1;
+    if (P.nw > 2 && row >= P.n[1]) {
+      row -= P.n[1];
+      wi = 2;
+    }
+  }
+  s.valid1 = row + 1 < P.n[wi];
+  s.r0 = P.rows[wi] + (size_t)row * P.pitch;
+  s.r1 = s.valid1 ? s.r0 + P.pitch : s.r0;
+  s.out0 = P.dst_off[wi] + row;
+  s.out1 = s.out0 + 1;
+  return s;
+}
+
+// utils::cast<float,uint8_t> / <float,int8_t> (bestla_utils.h:507-521) with the x86 NaN->0 behaviour (see act_prep.cu)
+__device__ __forceinline__ int cast_u8(float x) {
+  if (x != x) return 0;
+  x += 0.5f;
+  x = fminf(x, 255.f);
+  x = fmaxf(x, 0.f);
+  return (int)x;
+}
+__device__ __forceinline__ int cast_s8(float x) {
+  if (x != x) return 0;
+  x = roundf(x);
+  x = fminf(x, 127.f);
+  x = fmaxf(x, -128.f);
+  return (int)x;
+}
+
+// Quantise the op's activations [M][K] (fp32, global, read through L2) into the shared-memory image gemv_ring.cu expects.
+// One thread owns one 8-group (8 consecutive k); TPB = group/8 consecutive threads own one quantisation block.
+// Arithmetic identical to act_quant_kernel<COMP> (act_prep.cu): bit-exact codes, scales and zero points.
+template <int COMP>
+__device__ __forceinline__ void quantise_to_smem(const ProgOp& P, int M, uint32_t smem_base) {
+  const int tpb = (COMP == NS_COMP_Q8_0 ? 32 : P.group) >> 3;  // threads per quantisation block (4..32, power of two)
+  const int ngroups8 = P.kpad >> 3;
+  const int tid = threadIdx.x;
+  for (int m = 0; m < M; ++m) {
+    const float* row = P.in + (size_t)m * P.lda;
+    const uint32_t img = smem_base + (uint32_t)m * P.act_row;
+    const uint32_t meta = smem_base + P.meta_off + 8u * (uint32_t)(m * P.meta_stride);
+    for (int e0 = 0; e0 < ngroups8; e0 += kConsumerThreads) {
+      const int e = e0 + tid;
+      const bool live = e < ngroups8;
+      float v[8];
+      const int k0 = e * 8;
+      if (live && k0 + 8 <= P.k) {
+        const float4 x0 = ldcg4(row + k0), x1 = ldcg4(row + k0 + 4);
+        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (live && k0 + i < P.k) ? ldcg1(row + k0 + i) : 0.f;
+      }
+      // block range (all lanes of the warp take part in the shuffles)
+      float vmax = (COMP == NS_COMP_Q8_0) ? 0.f : 1.17549435e-38f, vmin = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (COMP == NS_COMP_INT8) {
+          vmax = fmaxf(v[i], vmax);
+          vmin = fminf(v[i], vmin);
+        } else {
+          vmax = fmaxf(vmax, fabsf(v[i]));
+        }
+      }
+      for (int o = 1; o < tpb; o <<= 1) {
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if (COMP == NS_COMP_INT8) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+      }
+      float scale, rscale;
+      int za = 0;
+      if (COMP == NS_COMP_Q8_0) {
+        scale = __half2float(__float2half_rn(vmax / 127.f));
+        rscale = vmax != 0.f ? 127.f / vmax : 0.f;
+      } else if (COMP == NS_COMP_INT8) {
+        scale = (vmax - vmin) / 255;
+        za = cast_u8((0 - vmin) / scale);
+        rscale = 1.f / scale;
+      } else {
+        scale = vmax / 127;
+        rscale = 1.f / scale;
+      }
+      int q[8], sa = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (k0 + i < P.k) {
+          if (COMP == NS_COMP_Q8_0) q[i] = __float2int_rn(v[i] * rscale);
+          else if (COMP == NS_COMP_INT8) q[i] = cast_u8((float)za + (float)(int)roundf(v[i] * rscale));
+          else q[i] = cast_s8(v[i] * rscale);
+        } else {
+          q[i] = za;  // padding contributes (a - za) == 0
+        }
+        sa += q[i];
+      }
+      // chunk sum over the 4 threads of a 32-element chunk
+      sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+      sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+      if (live) {
+        // bytes in dp4a order: Alo = (a0,a4,a1,a5), Ahi = (a2,a6,a3,a7)
+        const uint32_t alo = (q[0] & 0xff) | ((q[4] & 0xff) << 8) | ((q[1] & 0xff) << 16) | ((uint32_t)(q[5] & 0xff) << 24);
+        const uint32_t ahi = (q[2] & 0xff) | ((q[6] & 0xff) << 8) | ((q[3] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+        const int c = e >> 2, i = e & 3;
+        sts64(img + (uint32_t)(c >> 5) * 1024u + (uint32_t)(i >> 1) * 512u + (uint32_t)(c & 31) * 16u + (uint32_t)(i & 1) * 8u, alo, ahi);
+        if (i == 0) sts64(meta + 8u * (uint32_t)c, __float_as_uint(scale), (uint32_t)((sa & 0xffff) | (za << 16)));
+      }
+    }
+  }
+}
+
+template <int COMP, int M, bool ASYM, int STYPE>
+__global__ void __launch_bounds__(kThreads, 2)
+    program_kernel(const ProgOp* __restrict__ ops, int nops, const ProgCfg R, unsigned* __restrict__ counters,
+                   unsigned* __restrict__ epoch_ptr) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ ProgOp op_s;  // the consumers' current op
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int stages = R.stages;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring = smem_base + R.ring_off;
+  const uint32_t full0 = ring + (uint32_t)stages * R.slot_bytes;
+  const uint32_t empty0 = full0 + 8u * stages;
+  const int first = blockIdx.x, gstride = (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const unsigned epoch = ld_acquire(epoch_ptr);            // launches completed so far
+  const unsigned target = (epoch + 1u) * (unsigned)gstride;  // every CTA arrives once per op per launch
+
+  if (warp == kConsumers) {
+    // ===================== producer: streams the weights of ALL ops, never waits for activations =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phase = 0;
+      long long g = 0;
+      for (int oi = 0; oi < nops; ++oi) {
+        const ProgOp& P = ops[oi];
+        const int my_units = first < P.npairs ? (P.npairs - first + gstride - 1) / gstride : 0;
+        const uint32_t bytes = 2u * (uint32_t)P.pitch;
+        for (int j = 0; j < my_units; ++j, ++g) {
+          if (g >= stages) mbar_wait(empty0 + 8 * s, phase ^ 1);
+          const PairSrc ps = resolve_pair(P, first + j * gstride);
+          const uint32_t dst = ring + (uint32_t)s * R.slot_bytes;
+          mbar_expect_tx(full0 + 8 * s, bytes);
+          bulk_g2s(dst, ps.r0, (uint32_t)P.pitch, full0 + 8 * s);
+          bulk_g2s(dst + P.pitch, ps.r1, (uint32_t)P.pitch, full0 + 8 * s);
+          if (++s == stages) {
+            s = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers =====================
+  constexpr int AMODE = (COMP == NS_COMP_INT8) ? A_U8 : A_S8;
+  int s = warp;  // stages is a multiple of kConsumers: stage class == warp (see gemv_ring.cu)
+  uint32_t phase = 0;
+  int g_mod = 0;  // (global unit index of this CTA's next op start) mod kConsumers
+  for (int oi = 0; oi < nops; ++oi) {
+    // ---- op boundary: wait for the producers of this op's input, load the op descriptor ----
+    if (threadIdx.x == 0) {
+      if (oi > 0 && ops[oi].barrier_before) {
+        while ((int)(ld_acquire(counters + (oi - 1)) - target) < 0) {
+        }
+      }
+      op_s = ops[oi];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+    const ProgOp& P = op_s;
+    quantise_to_smem<COMP>(P, R.m, smem_base);
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+
+    const int my_units = first < P.npairs ? (P.npairs - first + gstride - 1) / gstride : 0;
+    const uint32_t meta_s = smem_base + P.meta_off;
+    const int nchunks = P.kpad >> 5;
+    int u0 = warp - g_mod;
+    if (u0 < 0) u0 += kConsumers;
+    for (int j = u0; j < my_units; j += kConsumers) {
+      const PairSrc ps = resolve_pair(P, first + j * gstride);
+      mbar_wait(full0 + 8 * s, phase);
+      const uint32_t r0 = ring + (uint32_t)s * R.slot_bytes;
+      const uint32_t r1 = r0 + P.pitch;
+      float acc[2][M];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc[r][m] = 0.f;
+#pragma unroll 2
+      for (int c = lane; c < nchunks; c += 32) {
+        const uint4 wv[2] = {lds128(r0 + 16 * c), lds128(r1 + 16 * c)};
+        const int gi = (P.cpg == 1) ? c : (int)__umulhi((uint32_t)c, P.cpg_magic);
+        const float ws[2] = {lds_scale<STYPE>(r0 + P.sc_off, gi), lds_scale<STYPE>(r1 + P.sc_off, gi)};
+        int off[2] = {8, 8};
+        if (ASYM) {
+          off[0] += lds8s(r0 + P.zp_off + gi);
+          off[1] += lds8s(r1 + P.zp_off + gi);
+        }
+        uint32_t lo[2][4], hi[2][4];
+        int su[2] = {0, 0};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const uint32_t ww[4] = {wv[r].x, wv[r].y, wv[r].z, wv[r].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            lo[r][i] = ww[i] & 0x0F0F0F0Fu;
+            hi[r][i] = ww[i] & 0xF0F0F0F0u;
+          }
+          if (AMODE == A_U8) {
+            int sl = 0, sh = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              sl = dp4a_uu(lo[r][i], 0x01010101u, sl);
+              sh = dp4a_uu(hi[r][i], 0x01010101u, sh);
+            }
+            su[r] = sl + (sh >> 4);
+          }
+        }
+        const uint32_t a_off = (uint32_t)(c >> 5) * 1024u + (uint32_t)(c & 31) * 16u;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          const uint32_t ab = smem_base + (uint32_t)m * P.act_row + a_off;
+          const uint4 a0 = lds128(ab), a1 = lds128(ab + 512);
+          const uint2 mt = lds64(meta_s + 8u * (uint32_t)(m * P.meta_stride + c));
+          const float a_scale = __uint_as_float(mt.x);
+          const int sa = (int)(short)(mt.y & 0xffff);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            int pl = 0, ph = 0;
+            if (AMODE == A_U8) {
+              pl = dp4a_uu(a0.x, lo[r][0], pl); ph = dp4a_uu(a0.y, hi[r][0], ph);
+              pl = dp4a_uu(a0.z, lo[r][1], pl); ph = dp4a_uu(a0.w, hi[r][1], ph);
+              pl = dp4a_uu(a1.x, lo[r][2], pl); ph = dp4a_uu(a1.y, hi[r][2], ph);
+              pl = dp4a_uu(a1.z, lo[r][3], pl); ph = dp4a_uu(a1.w, hi[r][3], ph);
+            } else {
+              pl = dp4a_us(lo[r][0], (int)a0.x, pl); ph = dp4a_us(hi[r][0], (int)a0.y, ph);
+              pl = dp4a_us(lo[r][1], (int)a0.z, pl); ph = dp4a_us(hi[r][1], (int)a0.w, ph);
+              pl = dp4a_us(lo[r][2], (int)a1.x, pl); ph = dp4a_us(hi[r][2], (int)a1.y, ph);
+              pl = dp4a_us(lo[r][3], (int)a1.z, pl); ph = dp4a_us(hi[r][3], (int)a1.w, ph);
+            }
+            int isum = pl + (ph >> 4) - off[r] * sa;
+            if (AMODE == A_U8) {
+              const int za = (int)((mt.y >> 16) & 0xff);
+              isum -= za * (su[r] - 32 * off[r]);
+            }
+            acc[r][m] = fmaf((float)isum, a_scale * ws[r], acc[r][m]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * s);
+      s += kConsumers;
+      if (s >= stages) {
+        s -= stages;
+        phase ^= 1u;
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc[r][m] = warp_sum(acc[r][m]);
+      if (lane == 0) {
+        if (P.mode == NS_GEMV_GATE_UP_SILU) {
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            if (m < R.m) {
+              const float gt = acc[0][m], up = acc[1][m];
+              const float sg = gt / (1.f + expf(-gt));
+              if (P.aux) P.aux[(size_t)m * P.ldo + ps.out0] = sg;
+              P.dst[(size_t)m * P.ldo + ps.out0] = sg * up;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (r == 1 && !ps.valid1) continue;
+            const long long out = r ? ps.out1 : ps.out0;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+              if (m < R.m) {
+                const size_t o = (size_t)m * P.ldo + out;
+                float v = acc[r][m];
+                if (P.bias) v += P.bias_bcast ? ldcg1(P.bias + out) : ldcg1(P.bias + o);
+                if (P.residual) v += ldcg1(P.residual + o);
+                P.dst[o] = v;
+              }
+            }
+          }
+        }
+      }
+    }
+    g_mod = (g_mod + my_units) % kConsumers;
+    // ---- op done in this CTA: publish (release) ----
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(counters + oi, 1u);
+    }
+  }
+  // last op finished everywhere -> advance the epoch exactly once (block 0), so the next launch sees fresh targets
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    while ((int)(ld_acquire(counters + (nops - 1)) - target) < 0) {
+    }
+    __threadfence();
+    atomicAdd(epoch_ptr, 1u);
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------- host side
+struct ns_program {
+  int m;
+  int comp, stype, asym;
+  bool finalized;
+  std::vector<ProgOp> ops;
+  ProgOp* d_ops;
+  unsigned* d_counters;  // [nops] + epoch at [nops]
+  ProgCfg cfg;
+  size_t smem;
+  int grid;
+  size_t alg_bytes;
+};
+
+extern "C" ns_program* ns_program_create(int m) {
+  if (ns_ensure_device()) return nullptr;
+  if (m < 1 || m > 4) {
+    ns_set_error("ns_program_create: m must be 1..4 (decode batches; larger M goes through the tensor-core GEMM)");
+    return nullptr;
+  }
+  ns_program* p = new ns_program();
+  p->m = m;
+  p->comp = -1;
+  p->finalized = false;
+  p->d_ops = nullptr;
+  p->d_counters = nullptr;
+  p->alg_bytes = 0;
+  return p;
+}
+
+extern "C" int ns_program_add_matmul(ns_program* p, const ns_weight* const* weights, int nw, int mode, const float* in, int lda,
+                                     float* dst, int ldo, const float* bias, int bias_bcast, const float* residual,
+                                     float* aux, int barrier_before) {
+  if (!p || p->finalized || !weights || nw < 1 || nw > 3 || mode < 0 || mode > 2 || !in || !dst) {
+    ns_set_error("ns_program_add_matmul: invalid arguments");
+    return NS_E_INVALID;
+  }
+  const ns_weight* w0 = weights[0];
+  const bool imode = (w0->comp == NS_COMP_Q8_0 || w0->comp == NS_COMP_INT8 || w0->comp == NS_COMP_INT8_S8);
+  const int qgroup = w0->comp == NS_COMP_Q8_0 ? 32 : w0->group;
+  if (w0->wfmt != NS_W_S4 || !imode || w0->shuffle || !(qgroup == 32 || qgroup == 64 || qgroup == 128 || qgroup == 256) ||
+      (w0->group % 32 != 0) || (w0->k % qgroup != 0)) {
+    ns_set_error("ns_program: only 4-bit integer weights with integer activations and groups of 32..256 are supported");
+    return NS_E_UNSUPPORTED;
+  }
+  if (p->comp < 0) {
+    p->comp = w0->comp;
+    p->stype = w0->stype;
+    p->asym = w0->asym;
+  }
+  long long ntot = 0;
+  ProgOp op;
+  memset(&op, 0, sizeof(op));
+  for (int i = 0; i < nw; ++i) {
+    const ns_weight* wi = weights[i];
+    if (wi->comp != p->comp || wi->stype != p->stype || wi->asym != p->asym || wi->wfmt != NS_W_S4 || wi->k != w0->k ||
+        wi->group != w0->group || wi->shuffle) {
+      ns_set_error("ns_program: all weights of a program must share format, scale type and compute type");
+      return NS_E_UNSUPPORTED;
+    }
+    if (mode == NS_GEMV_CONCAT && i + 1 < nw && (wi->n & 1)) {
+      ns_set_error("ns_program: every weight but the last of a fused matmul needs an even n");
+      return NS_E_UNSUPPORTED;
+    }
+    op.rows[i] = wi->rows;
+    op.n[i] = wi->n;
+    op.dst_off[i] = (mode == NS_GEMV_CONCAT) ? ntot : 0;  // concatenated along n: [m][n0+n1+n2] with ldo
+    ntot += wi->n;
+    p->alg_bytes += ns_weight_algorithmic_bytes(wi);
+  }
+  if (mode == NS_GEMV_GATE_UP_SILU && (nw != 2 || weights[0]->n != weights[1]->n)) {
+    ns_set_error("ns_program: gate/up fusion needs two weights with equal n");
+    return NS_E_INVALID;
+  }
+  op.nw = nw;
+  op.mode = mode;
+  op.k = w0->k;
+  op.kpad = w0->kpad;
+  op.pitch = w0->pitch;
+  op.sc_off = w0->sc_off;
+  op.zp_off = w0->zp_off;
+  op.group = w0->group;
+  op.cpg = (w0->group + 31) / 32;
+  op.cpg_magic = op.cpg > 1 ? (uint32_t)((0x100000000ull + (uint64_t)op.cpg - 1) / (uint64_t)op.cpg) : 0u;
+  op.in = in;
+  op.lda = lda;
+  op.dst = dst;
+  op.ldo = ldo;
+  op.bias = bias;
+  op.bias_bcast = bias_bcast;
+  op.residual = residual;
+  op.aux = aux;
+  op.npairs = (mode == NS_GEMV_GATE_UP_SILU) ? w0->n : (int)((ntot + 1) / 2);
+  op.barrier_before = barrier_before;
+  op.act_row = (int)ns_round_up((size_t)w0->kpad, 1024);
+  op.meta_stride = ns_meta_stride(w0->kpad);
+  op.meta_off = p->m * op.act_row;
+  p->ops.push_back(op);
+  return NS_OK;
+}
+
+extern "C" size_t ns_program_algorithmic_bytes(const ns_program* p) { return p ? p->alg_bytes : 0; }
+
+extern "C" int ns_program_finalize(ns_program* p, void* queue) {
+  if (!p || p->ops.empty()) return NS_E_INVALID;
+  if (p->finalized) return NS_OK;
+  cudaStream_t st = ns_stream_of(queue);
+  const int mt = p->m >= 3 ? 4 : p->m;
+  size_t act_region = 0;
+  int slot = 0;
+  for (const ProgOp& o : p->ops) {
+    act_region = std::max(act_region, ns_round_up((size_t)mt * o.act_row + (size_t)mt * o.meta_stride * 8, 128));
+    slot = std::max(slot, 2 * o.pitch);
+  }
+  const size_t budgets[2] = {110 * 1024, 200 * 1024};
+  int stages = 0;
+  size_t budget = 0;
+  for (int i = 0; i < 2; ++i) {
+    budget = budgets[i];
+    if (budget > act_region + 64) stages = (int)((budget - act_region - 64) / ((size_t)slot + 16));
+    stages -= stages % kConsumers;
+    if (stages >= kConsumers) break;
+    stages = 0;
+  }
+  if (stages < kConsumers) {
+    ns_set_error("ns_program: rows too long for the shared-memory ring");
+    return NS_E_UNSUPPORTED;
+  }
+  if (stages > 48) stages = 48;
+  p->cfg.ring_off = (int)act_region;
+  p->cfg.stages = stages;
+  p->cfg.slot_bytes = slot;
+  p->cfg.m = p->m;
+  p->smem = act_region + (size_t)stages * slot + (size_t)stages * 16;
+  p->grid = ns_num_sms() * (budget > 110 * 1024 ? 1 : 2);
+  const size_t nops = p->ops.size();
+  NS_CUDA_TRY(cudaMalloc((void**)&p->d_ops, nops * sizeof(ProgOp)));
+  NS_CUDA_TRY(cudaMalloc((void**)&p->d_counters, (nops + 1) * sizeof(unsigned)));
+  NS_CUDA_TRY(cudaMemcpyAsync(p->d_ops, p->ops.data(), nops * sizeof(ProgOp), cudaMemcpyHostToDevice, st));
+  NS_CUDA_TRY(cudaMemsetAsync(p->d_counters, 0, (nops + 1) * sizeof(unsigned), st));
+  NS_CUDA_TRY(cudaStreamSynchronize(st));
+  p->finalized = true;
+  return NS_OK;
+}
+
+template <int COMP, int M, bool ASYM, int STYPE>
+static int run_one(ns_program* p, cudaStream_t st) {
+  auto kern = program_kernel<COMP, M, ASYM, STYPE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p->grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = p->smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs must be co-resident: they synchronise through global memory
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const ProgOp* ops = p->d_ops;
+  int nops = (int)p->ops.size();
+  unsigned* counters = p->d_counters;
+  unsigned* epoch = p->d_counters + nops;
+  NS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ops, nops, p->cfg, counters, epoch));
+  ns_count_launch();
+  return NS_OK;
+}
+template <int COMP, bool ASYM, int STYPE>
+static int run_m(ns_program* p, cudaStream_t st) {
+  switch (p->m) {
+    case 1: return run_one<COMP, 1, ASYM, STYPE>(p, st);
+    case 2: return run_one<COMP, 2, ASYM, STYPE>(p, st);
+    default: return run_one<COMP, 4, ASYM, STYPE>(p, st);
+  }
+}
+template <int COMP, bool ASYM>
+static int run_s(ns_program* p, cudaStream_t st) {
+  switch (p->stype) {
+    case NS_S_F32: return run_m<COMP, ASYM, NS_S_F32>(p, st);
+    case NS_S_F16: return run_m<COMP, ASYM, NS_S_F16>(p, st);
+    default: return run_m<COMP, ASYM, NS_S_BF16>(p, st);
+  }
+}
+template <int COMP>
+static int run_a(ns_program* p, cudaStream_t st) {
+  return p->asym ? run_s<COMP, true>(p, st) : run_s<COMP, false>(p, st);
+}
+
+extern "C" int ns_program_run(ns_program* p, void* queue) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!p || !p->finalized) {
+    ns_set_error("ns_program_run: program not finalized");
+    return NS_E_INVALID;
+  }
+  cudaStream_t st = ns_stream_of(queue);
+  switch (p->comp) {
+    case NS_COMP_Q8_0: return run_a<NS_COMP_Q8_0>(p, st);
+    case NS_COMP_INT8: return run_a<NS_COMP_INT8>(p, st);
+    default: return run_a<NS_COMP_INT8_S8>(p, st);
+  }
+}
+
+extern "C" void ns_program_free(ns_program* p) {
+  if (!p) return;
+  if (p->d_ops) cudaFree(p->d_ops);
+  if (p->d_counters) cudaFree(p->d_counters);
+  delete p;
+}
