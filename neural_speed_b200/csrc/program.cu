@@ -42,6 +42,8 @@ struct ProgOp {
   int npairs;
   int barrier_before;
   int act_row, meta_off, meta_stride;
+  int pps;     // row pairs per ring slot (small rows are packed so a slot stays full)
+  int nunits;  // ceil(npairs / pps)
 };
 
 struct ProgCfg {
@@ -190,18 +192,33 @@ __device__ __forceinline__ void quantise_to_smem(const ProgOp& P, int M, uint32_
     const float* row = P.in + (size_t)m * P.lda;
     const uint32_t img = smem_base + (uint32_t)m * P.act_row;
     const uint32_t meta = smem_base + P.meta_off + 8u * (uint32_t)(m * P.meta_stride);
-    for (int e0 = 0; e0 < ngroups8; e0 += kConsumerThreads) {
-      const int e = e0 + tid;
-      const bool live = e < ngroups8;
-      float v[8];
+    // loads of NI consecutive passes are issued back to back (L2 latency ~0.5 us each would otherwise serialise)
+    constexpr int NI = 3;
+    for (int eb = 0; eb < ngroups8; eb += NI * kConsumerThreads) {
+     float vv[NI][8];
+#pragma unroll
+     for (int it = 0; it < NI; ++it) {
+      const int e = eb + it * kConsumerThreads + tid;
       const int k0 = e * 8;
-      if (live && k0 + 8 <= P.k) {
+      if (e < ngroups8 && k0 + 8 <= P.k) {
         const float4 x0 = ldcg4(row + k0), x1 = ldcg4(row + k0 + 4);
-        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+        vv[it][0] = x0.x; vv[it][1] = x0.y; vv[it][2] = x0.z; vv[it][3] = x0.w;
+        vv[it][4] = x1.x; vv[it][5] = x1.y; vv[it][6] = x1.z; vv[it][7] = x1.w;
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (live && k0 + i < P.k) ? ldcg1(row + k0 + i) : 0.f;
+        for (int i = 0; i < 8; ++i) vv[it][i] = (e < ngroups8 && k0 + i < P.k) ? ldcg1(row + k0 + i) : 0.f;
       }
+     }
+#pragma unroll
+     for (int it = 0; it < NI; ++it) {
+      const int e0 = eb + it * kConsumerThreads;
+      if (e0 >= ngroups8) break;  // uniform across the CTA
+      const int e = e0 + tid;
+      const bool live = e < ngroups8;
+      const int k0 = e * 8;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = vv[it][i];
       // block range (all lanes of the warp take part in the shuffles)
       float vmax = (COMP == NS_COMP_Q8_0) ? 0.f : 1.17549435e-38f, vmin = 0.f;
 #pragma unroll
@@ -253,6 +270,7 @@ __device__ __forceinline__ void quantise_to_smem(const ProgOp& P, int M, uint32_
         sts64(img + (uint32_t)(c >> 5) * 1024u + (uint32_t)(i >> 1) * 512u + (uint32_t)(c & 31) * 16u + (uint32_t)(i & 1) * 8u, alo, ahi);
         if (i == 0) sts64(meta + 8u * (uint32_t)c, __float_as_uint(scale), (uint32_t)((sa & 0xffff) | (za << 16)));
       }
+     }  // it
     }
   }
 }
@@ -290,15 +308,29 @@ __global__ void __launch_bounds__(kThreads, 2)
       long long g = 0;
       for (int oi = 0; oi < nops; ++oi) {
         const ProgOp& P = ops[oi];
-        const int my_units = first < P.npairs ? (P.npairs - first + gstride - 1) / gstride : 0;
-        const uint32_t bytes = 2u * (uint32_t)P.pitch;
+        const int my_units = first < P.nunits ? (P.nunits - first + gstride - 1) / gstride : 0;
         for (int j = 0; j < my_units; ++j, ++g) {
           if (g >= stages) mbar_wait(empty0 + 8 * s, phase ^ 1);
-          const PairSrc ps = resolve_pair(P, first + j * gstride);
+          const int p0 = (first + j * gstride) * P.pps;
+          const int np = min(P.pps, P.npairs - p0);
           const uint32_t dst = ring + (uint32_t)s * R.slot_bytes;
-          mbar_expect_tx(full0 + 8 * s, bytes);
-          bulk_g2s(dst, ps.r0, (uint32_t)P.pitch, full0 + 8 * s);
-          bulk_g2s(dst + P.pitch, ps.r1, (uint32_t)P.pitch, full0 + 8 * s);
+          mbar_expect_tx(full0 + 8 * s, 2u * (uint32_t)np * (uint32_t)P.pitch);
+          if (P.mode == NS_GEMV_GATE_UP_SILU) {
+            // slot = [np gate rows][np up rows]: two contiguous ranges
+            bulk_g2s(dst, P.rows[0] + (size_t)p0 * P.pitch, (uint32_t)(np * P.pitch), full0 + 8 * s);
+            bulk_g2s(dst + np * P.pitch, P.rows[1] + (size_t)p0 * P.pitch, (uint32_t)(np * P.pitch), full0 + 8 * s);
+          } else {
+            for (int t = 0; t < np; ++t) {  // slot = [pair 0: row, row+1][pair 1: ...]
+              const PairSrc ps = resolve_pair(P, p0 + t);
+              const uint32_t d = dst + (uint32_t)t * 2u * (uint32_t)P.pitch;
+              if (ps.r1 == ps.r0 + P.pitch) {
+                bulk_g2s(d, ps.r0, 2u * (uint32_t)P.pitch, full0 + 8 * s);
+              } else {
+                bulk_g2s(d, ps.r0, (uint32_t)P.pitch, full0 + 8 * s);
+                bulk_g2s(d + P.pitch, ps.r1, (uint32_t)P.pitch, full0 + 8 * s);
+              }
+            }
+          }
           if (++s == stages) {
             s = 0;
             phase ^= 1;
@@ -316,28 +348,35 @@ __global__ void __launch_bounds__(kThreads, 2)
   int g_mod = 0;  // (global unit index of this CTA's next op start) mod kConsumers
   for (int oi = 0; oi < nops; ++oi) {
     // ---- op boundary: wait for the producers of this op's input, load the op descriptor ----
-    if (threadIdx.x == 0) {
-      if (oi > 0 && ops[oi].barrier_before) {
+    {
+      // descriptor (immutable) is fetched by many threads while thread 0 waits for the previous op to finish everywhere
+      constexpr int kWords = (int)(sizeof(ProgOp) / 4);
+      if (threadIdx.x >= 32 && threadIdx.x < 32 + kWords)
+        reinterpret_cast<uint32_t*>(&op_s)[threadIdx.x - 32] = reinterpret_cast<const uint32_t*>(ops + oi)[threadIdx.x - 32];
+      if (threadIdx.x == 0 && oi > 0 && ops[oi].barrier_before) {
         while ((int)(ld_acquire(counters + (oi - 1)) - target) < 0) {
         }
       }
-      op_s = ops[oi];
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
     const ProgOp& P = op_s;
     quantise_to_smem<COMP>(P, R.m, smem_base);
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
 
-    const int my_units = first < P.npairs ? (P.npairs - first + gstride - 1) / gstride : 0;
+    const int my_units = first < P.nunits ? (P.nunits - first + gstride - 1) / gstride : 0;
     const uint32_t meta_s = smem_base + P.meta_off;
     const int nchunks = P.kpad >> 5;
     int u0 = warp - g_mod;
     if (u0 < 0) u0 += kConsumers;
     for (int j = u0; j < my_units; j += kConsumers) {
-      const PairSrc ps = resolve_pair(P, first + j * gstride);
+      const int p0 = (first + j * gstride) * P.pps;
+      const int np = min(P.pps, P.npairs - p0);
       mbar_wait(full0 + 8 * s, phase);
-      const uint32_t r0 = ring + (uint32_t)s * R.slot_bytes;
-      const uint32_t r1 = r0 + P.pitch;
+      const uint32_t slot = ring + (uint32_t)s * R.slot_bytes;
+     for (int t = 0; t < np; ++t) {
+      const PairSrc ps = resolve_pair(P, p0 + t);
+      const uint32_t r0 = (P.mode == NS_GEMV_GATE_UP_SILU) ? slot + (uint32_t)(t * P.pitch) : slot + (uint32_t)(t * 2 * P.pitch);
+      const uint32_t r1 = (P.mode == NS_GEMV_GATE_UP_SILU) ? slot + (uint32_t)((np + t) * P.pitch) : r0 + P.pitch;
       float acc[2][M];
 #pragma unroll
       for (int r = 0; r < 2; ++r)
@@ -404,13 +443,6 @@ __global__ void __launch_bounds__(kThreads, 2)
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty0 + 8 * s);
-      s += kConsumers;
-      if (s >= stages) {
-        s -= stages;
-        phase ^= 1u;
-      }
 #pragma unroll
       for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -443,6 +475,14 @@ __global__ void __launch_bounds__(kThreads, 2)
             }
           }
         }
+      }
+     }  // pairs of this slot
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * s);  // slot may be refilled
+      s += kConsumers;
+      if (s >= stages) {
+        s -= stages;
+        phase ^= 1u;
       }
     }
     g_mod = (g_mod + my_units) % kConsumers;
@@ -578,7 +618,7 @@ extern "C" int ns_program_finalize(ns_program* p, void* queue) {
     act_region = std::max(act_region, ns_round_up((size_t)mt * o.act_row + (size_t)mt * o.meta_stride * 8, 128));
     slot = std::max(slot, 2 * o.pitch);
   }
-  const size_t budgets[2] = {110 * 1024, 200 * 1024};
+  const size_t budgets[2] = {113 * 1024, 200 * 1024};  // 2 x (113 KB + 1 KB reserved) = 228 KB = one SM
   int stages = 0;
   size_t budget = 0;
   for (int i = 0; i < 2; ++i) {
@@ -598,7 +638,11 @@ extern "C" int ns_program_finalize(ns_program* p, void* queue) {
   p->cfg.slot_bytes = slot;
   p->cfg.m = p->m;
   p->smem = act_region + (size_t)stages * slot + (size_t)stages * 16;
-  p->grid = ns_num_sms() * (budget > 110 * 1024 ? 1 : 2);
+  p->grid = ns_num_sms() * (budget > 113 * 1024 ? 1 : 2);
+  for (ProgOp& o : p->ops) {
+    o.pps = std::max(1, std::min(4, slot / (2 * o.pitch)));
+    o.nunits = (o.npairs + o.pps - 1) / o.pps;
+  }
   const size_t nops = p->ops.size();
   NS_CUDA_TRY(cudaMalloc((void**)&p->d_ops, nops * sizeof(ProgOp)));
   NS_CUDA_TRY(cudaMalloc((void**)&p->d_counters, (nops + 1) * sizeof(unsigned)));
