@@ -300,12 +300,14 @@ def run_ours(args):
 
     # persistent multi-op kernel: the same 129 matmul nodes, every node waiting (grid barrier) for the previous one
     prog = ns.Program(1)
+    bb = 0 if args.prog_nobarrier else 1
+    tmp2 = torch.zeros(1, N_FF, device="cuda")
     for lay in layers:
-        prog.add([lay["wq"], lay["wk"], lay["wv"]], ns.Program.CONCAT, x.data_ptr(), N_EMBD, qkv.data_ptr(), 3 * N_EMBD)
-        prog.add([lay["wo"]], ns.Program.PLAIN, attn.data_ptr(), N_EMBD, o.data_ptr(), N_EMBD)
-        prog.add([lay["w1"], lay["w3"]], ns.Program.GATE_UP_SILU, x.data_ptr(), N_EMBD, tmp.data_ptr(), N_FF)
-        prog.add([lay["w2"]], ns.Program.PLAIN, tmp.data_ptr(), N_FF, ffn.data_ptr(), N_EMBD)
-    prog.add([lm_head], ns.Program.PLAIN, x.data_ptr(), N_EMBD, logits.data_ptr(), N_VOCAB)
+        prog.add([lay["wq"], lay["wk"], lay["wv"]], ns.Program.CONCAT, x.data_ptr(), N_EMBD, qkv.data_ptr(), 3 * N_EMBD, barrier_before=bb)
+        prog.add([lay["wo"]], ns.Program.PLAIN, attn.data_ptr(), N_EMBD, o.data_ptr(), N_EMBD, barrier_before=bb)
+        prog.add([lay["w1"], lay["w3"]], ns.Program.GATE_UP_SILU, x.data_ptr(), N_EMBD, tmp.data_ptr(), N_FF, barrier_before=bb)
+        prog.add([lay["w2"]], ns.Program.PLAIN, (tmp if bb else tmp2).data_ptr(), N_FF, ffn.data_ptr(), N_EMBD, barrier_before=bb)
+    prog.add([lm_head], ns.Program.PLAIN, x.data_ptr(), N_EMBD, logits.data_ptr(), N_VOCAB, barrier_before=bb)
     prog.finalize(queue)
     prog.run(queue)
     L.bestla_device_sync(queue)
@@ -458,6 +460,7 @@ def main():
     ap.add_argument("--fmt", default="q4_0", choices=["q4_0", "int4g128"])
     ap.add_argument("--layers", type=int, default=N_LAYER, help="debug: fewer layers (invalid as a bench value)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--prog-nobarrier", action="store_true", help="experiment: drop the inter-op grid barriers (no dependencies)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
