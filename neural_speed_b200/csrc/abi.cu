@@ -517,13 +517,19 @@ extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* 
     return ns_launch_gemm_tc(w, ws, dst, ldo, m, bias, bcast, residual, st);
   }
   const int tile = ns_gemv_tile_rows(w);
+  const bool fused = ns_decode_op_supported(w);  // one launch: activation quantisation fused into the GEMV (program.cu)
   for (int m0 = 0; m0 < m; m0 += tile) {
     const int mt = (m - m0 < tile) ? (m - m0) : tile;
+    const float* b = bias ? (bcast ? bias : bias + (size_t)m0 * ldo) : nullptr;
+    const float* r = residual ? residual + (size_t)m0 * ldo : nullptr;
+    if (fused) {
+      if (int rc = ns_launch_decode_op(&w, 1, NS_GEMV_PLAIN, act + (size_t)m0 * lda, lda, dst + (size_t)m0 * ldo, ldo, mt, m, b,
+                                       bcast, r, nullptr, st))
+        return rc;
+      continue;
+    }
     if (int rc = ns_launch_act_prep(act + (size_t)m0 * lda, lda, mt, w, ws, st)) return rc;
-    if (int rc = ns_launch_gemv(&w, 1, NS_GEMV_PLAIN, ws, dst + (size_t)m0 * ldo, ldo, mt, m,
-                                bias ? (bcast ? bias : bias + (size_t)m0 * ldo) : nullptr, bcast,
-                                residual ? residual + (size_t)m0 * ldo : nullptr, nullptr, st))
-      return rc;
+    if (int rc = ns_launch_gemv(&w, 1, NS_GEMV_PLAIN, ws, dst + (size_t)m0 * ldo, ldo, mt, m, b, bcast, r, nullptr, st)) return rc;
   }
   return NS_OK;
 }
@@ -545,8 +551,15 @@ extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_wei
     return NS_OK;
   }
   const int tile = ns_gemv_tile_rows(wq);
+  const bool fused = ns_decode_op_supported(wq);
   for (int m0 = 0; m0 < m; m0 += tile) {
     const int mt = (m - m0 < tile) ? (m - m0) : tile;
+    if (fused) {
+      if (int rc = ns_launch_decode_op(wl, 3, NS_GEMV_CONCAT, act + (size_t)m0 * lda, lda, dst + (size_t)m0 * ldo, ldo, mt, m,
+                                       nullptr, 0, nullptr, nullptr, st))
+        return rc;
+      continue;
+    }
     if (int rc = ns_launch_act_prep(act + (size_t)m0 * lda, lda, mt, wq, ws, st)) return rc;
     if (int rc = ns_launch_gemv(wl, 3, NS_GEMV_CONCAT, ws, dst + (size_t)m0 * ldo, ldo, mt, m, nullptr, 0, nullptr,
                                 nullptr, st))
@@ -578,8 +591,15 @@ extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_we
   }
   const ns_weight* gu[2] = {w1, w3};
   int tile = ns_gemv_tile_rows(w1);
+  const bool fused = ns_decode_op_supported(w1) && ns_decode_op_supported(w2);
   for (int m0 = 0; m0 < m; m0 += tile) {
     const int mt = (m - m0 < tile) ? (m - m0) : tile;
+    if (fused) {
+      if (int rc = ns_launch_decode_op(gu, 2, NS_GEMV_GATE_UP_SILU, act + (size_t)m0 * lda, lda, tmp + (size_t)m0 * fmid, fmid, mt,
+                                       m, nullptr, 0, nullptr, nullptr, st))
+        return rc;
+      continue;
+    }
     if (int rc = ns_launch_act_prep(act + (size_t)m0 * lda, lda, mt, w1, ws, st)) return rc;
     if (int rc = ns_launch_gemv(gu, 2, NS_GEMV_GATE_UP_SILU, ws, tmp + (size_t)m0 * fmid, fmid, mt, m, nullptr, 0, nullptr,
                                 nullptr, st))
@@ -588,6 +608,12 @@ extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_we
   tile = ns_gemv_tile_rows(w2);
   for (int m0 = 0; m0 < m; m0 += tile) {
     const int mt = (m - m0 < tile) ? (m - m0) : tile;
+    if (fused) {
+      if (int rc = ns_launch_decode_op(&w2, 1, NS_GEMV_PLAIN, tmp + (size_t)m0 * fmid, fmid, dst + (size_t)m0 * ldo, ldo, mt, m,
+                                       nullptr, 0, nullptr, nullptr, st))
+        return rc;
+      continue;
+    }
     if (int rc = ns_launch_act_prep(tmp + (size_t)m0 * fmid, fmid, mt, w2, ws, st)) return rc;
     if (int rc = ns_launch_gemv(&w2, 1, NS_GEMV_PLAIN, ws, dst + (size_t)m0 * ldo, ldo, mt, m, nullptr, 0, nullptr, nullptr,
                                 st))

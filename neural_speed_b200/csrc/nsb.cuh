@@ -4,7 +4,7 @@
 //   N self-contained rows of `pitch` bytes (16-B multiple), row n at rows + n*pitch:
 //     [ q      : q_bytes = kpad/2 (4-bit) or kpad (8-bit), kpad = roundup(K, 32)           ]
 //     [ scales : ngroups x {f32|bf16|f16}, ngroups = ceil(K/group)  (at sc_off = q_bytes)  ]
-//     [ zp     : ngroups x int8, asymmetric only                    (at zp_off)            ]
+//     [ zp     : ngroups x int8, asymmetric only       (at zp_off, 16-B aligned)           ]
 //   Everything one output row needs is ONE contiguous byte range, so the decode GEMV streams whole rows with
 //   cp.async.bulk (TMA 1-D) into a shared-memory ring, and the prefill GEMM sees the q part as a 2-D tensor of pitch
 //   `pitch` for cp.async.bulk.tensor.
@@ -46,7 +46,7 @@ static inline void ns_weight_layout(ns_weight* w) {
   w->ngroups = (w->k + w->group - 1) / w->group;
   w->q_bytes = (w->wfmt == NS_W_S8) ? w->kpad : w->kpad / 2;
   w->sc_off = w->q_bytes;
-  w->zp_off = w->sc_off + w->ngroups * ns_stype_size(w->stype);
+  w->zp_off = (int)ns_round_up((size_t)w->sc_off + (size_t)w->ngroups * ns_stype_size(w->stype), 16);  // TMA-copyable
   w->pitch = (int)ns_round_up((size_t)w->zp_off + (w->asym ? w->ngroups : 0), 16);
 }
 
@@ -115,6 +115,10 @@ struct GemvParams {
   int npairs;
 };
 int ns_launch_gemv_ring(const GemvParams& P, int amode, bool asym, int mt, cudaStream_t st);  // gemv_ring.cu
+// program.cu: fused activation-quantisation + GEMV launch for m <= 4 rows (the hot decode path)
+bool ns_decode_op_supported(const ns_weight* w);
+int ns_launch_decode_op(const ns_weight* const* weights, int nw, int mode, const float* act, int lda, float* dst, int ldo, int m,
+                        int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st);
 
 template <typename... Args>
 static inline cudaError_t ns_launch_pdl(void (*kern)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
