@@ -517,19 +517,16 @@ extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* 
     return ns_launch_gemm_tc(w, ws, dst, ldo, m, bias, bcast, residual, st);
   }
   const int tile = ns_gemv_tile_rows(w);
-  const bool fused = ns_decode_op_supported(w);  // one launch: activation quantisation fused into the GEMV (program.cu)
+  const bool fused = ns_gemv_fused_quant_ok(w);  // the GEMV quantises the activations itself: one launch per tile
   for (int m0 = 0; m0 < m; m0 += tile) {
     const int mt = (m - m0 < tile) ? (m - m0) : tile;
-    const float* b = bias ? (bcast ? bias : bias + (size_t)m0 * ldo) : nullptr;
-    const float* r = residual ? residual + (size_t)m0 * ldo : nullptr;
-    if (fused) {
-      if (int rc = ns_launch_decode_op(&w, 1, NS_GEMV_PLAIN, act + (size_t)m0 * lda, lda, dst + (size_t)m0 * ldo, ldo, mt, m, b,
-                                       bcast, r, nullptr, st))
-        return rc;
-      continue;
-    }
-    if (int rc = ns_launch_act_prep(act + (size_t)m0 * lda, lda, mt, w, ws, st)) return rc;
-    if (int rc = ns_launch_gemv(&w, 1, NS_GEMV_PLAIN, ws, dst + (size_t)m0 * ldo, ldo, mt, m, b, bcast, r, nullptr, st)) return rc;
+    const float* a = act + (size_t)m0 * lda;
+    if (!fused)
+      if (int rc = ns_launch_act_prep(a, lda, mt, w, ws, st)) return rc;
+    if (int rc = ns_launch_gemv(&w, 1, NS_GEMV_PLAIN, fused ? nullptr : ws, dst + (size_t)m0 * ldo, ldo, mt, m,
+                                bias ? (bcast ? bias : bias + (size_t)m0 * ldo) : nullptr, bcast,
+                                residual ? residual + (size_t)m0 * ldo : nullptr, nullptr, st, fused ? a : nullptr, lda))
+      return rc;
   }
   return NS_OK;
 }
@@ -551,18 +548,14 @@ extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_wei
     return NS_OK;
   }
   const int tile = ns_gemv_tile_rows(wq);
-  const bool fused = ns_decode_op_supported(wq);
+  const bool fused = ns_gemv_fused_quant_ok(wq);
   for (int m0 = 0; m0 < m; m0 += tile) {
     const int mt = (m - m0 < tile) ? (m - m0) : tile;
-    if (fused) {
-      if (int rc = ns_launch_decode_op(wl, 3, NS_GEMV_CONCAT, act + (size_t)m0 * lda, lda, dst + (size_t)m0 * ldo, ldo, mt, m,
-                                       nullptr, 0, nullptr, nullptr, st))
-        return rc;
-      continue;
-    }
-    if (int rc = ns_launch_act_prep(act + (size_t)m0 * lda, lda, mt, wq, ws, st)) return rc;
-    if (int rc = ns_launch_gemv(wl, 3, NS_GEMV_CONCAT, ws, dst + (size_t)m0 * ldo, ldo, mt, m, nullptr, 0, nullptr,
-                                nullptr, st))
+    const float* a = act + (size_t)m0 * lda;
+    if (!fused)
+      if (int rc = ns_launch_act_prep(a, lda, mt, wq, ws, st)) return rc;
+    if (int rc = ns_launch_gemv(wl, 3, NS_GEMV_CONCAT, fused ? nullptr : ws, dst + (size_t)m0 * ldo, ldo, mt, m, nullptr, 0,
+                                nullptr, nullptr, st, fused ? a : nullptr, lda))
       return rc;
   }
   return NS_OK;
@@ -591,32 +584,24 @@ extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_we
   }
   const ns_weight* gu[2] = {w1, w3};
   int tile = ns_gemv_tile_rows(w1);
-  const bool fused = ns_decode_op_supported(w1) && ns_decode_op_supported(w2);
+  const bool fused1 = ns_gemv_fused_quant_ok(w1), fused2 = ns_gemv_fused_quant_ok(w2);
   for (int m0 = 0; m0 < m; m0 += tile) {
     const int mt = (m - m0 < tile) ? (m - m0) : tile;
-    if (fused) {
-      if (int rc = ns_launch_decode_op(gu, 2, NS_GEMV_GATE_UP_SILU, act + (size_t)m0 * lda, lda, tmp + (size_t)m0 * fmid, fmid, mt,
-                                       m, nullptr, 0, nullptr, nullptr, st))
-        return rc;
-      continue;
-    }
-    if (int rc = ns_launch_act_prep(act + (size_t)m0 * lda, lda, mt, w1, ws, st)) return rc;
-    if (int rc = ns_launch_gemv(gu, 2, NS_GEMV_GATE_UP_SILU, ws, tmp + (size_t)m0 * fmid, fmid, mt, m, nullptr, 0, nullptr,
-                                nullptr, st))
+    const float* a = act + (size_t)m0 * lda;
+    if (!fused1)
+      if (int rc = ns_launch_act_prep(a, lda, mt, w1, ws, st)) return rc;
+    if (int rc = ns_launch_gemv(gu, 2, NS_GEMV_GATE_UP_SILU, fused1 ? nullptr : ws, tmp + (size_t)m0 * fmid, fmid, mt, m, nullptr,
+                                0, nullptr, nullptr, st, fused1 ? a : nullptr, lda))
       return rc;
   }
   tile = ns_gemv_tile_rows(w2);
   for (int m0 = 0; m0 < m; m0 += tile) {
     const int mt = (m - m0 < tile) ? (m - m0) : tile;
-    if (fused) {
-      if (int rc = ns_launch_decode_op(&w2, 1, NS_GEMV_PLAIN, tmp + (size_t)m0 * fmid, fmid, dst + (size_t)m0 * ldo, ldo, mt, m,
-                                       nullptr, 0, nullptr, nullptr, st))
-        return rc;
-      continue;
-    }
-    if (int rc = ns_launch_act_prep(tmp + (size_t)m0 * fmid, fmid, mt, w2, ws, st)) return rc;
-    if (int rc = ns_launch_gemv(&w2, 1, NS_GEMV_PLAIN, ws, dst + (size_t)m0 * ldo, ldo, mt, m, nullptr, 0, nullptr, nullptr,
-                                st))
+    const float* a = tmp + (size_t)m0 * fmid;
+    if (!fused2)
+      if (int rc = ns_launch_act_prep(a, fmid, mt, w2, ws, st)) return rc;
+    if (int rc = ns_launch_gemv(&w2, 1, NS_GEMV_PLAIN, fused2 ? nullptr : ws, dst + (size_t)m0 * ldo, ldo, mt, m, nullptr, 0,
+                                nullptr, nullptr, st, fused2 ? a : nullptr, fmid))
       return rc;
   }
   return NS_OK;

@@ -360,8 +360,16 @@ int ns_gemv_tile_rows(const ns_weight* w) {
 
 // One tile: m <= ns_gemv_tile_rows(w).  act_ws is the image ns_launch_act_prep produced for exactly these m rows.
 // dst points at the tile's first output row; m_total is the full M (only used for the [nw][M][ldo] QKV layout).
+bool ns_gemv_fused_quant_ok(const ns_weight* w) {
+  if (w->wfmt != NS_W_S4 || w->shuffle) return false;
+  if (!(w->comp == NS_COMP_Q8_0 || w->comp == NS_COMP_INT8 || w->comp == NS_COMP_INT8_S8)) return false;
+  const int qg = w->comp == NS_COMP_Q8_0 ? 32 : w->group;  // one activation block must sit inside one warp
+  return (qg == 32 || qg == 64 || qg == 128 || qg == 256) && w->k % qg == 0;
+}
+
 int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* act_ws, float* dst, int ldo, int m,
-                   int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st) {
+                   int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st,
+                   const float* act_f32, int lda) {
   const ns_weight* w0 = ws_[0];
   for (int i = 1; i < nw; ++i) {
     const ns_weight* wi = ws_[i];
@@ -426,6 +434,13 @@ int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* ac
   P.aux = aux;
   P.npairs = (mode == NS_GEMV_GATE_UP_SILU) ? w0->n : (int)((ntot + 1) / 2);
   P.act = act_ws;
+  P.act_f32 = act_f32;
+  P.lda = lda;
+  P.comp = w0->comp;
+  if (act_f32 && !(ns_gemv_fused_quant_ok(w0))) {
+    ns_set_error("internal: fused activation quantisation not available for this weight");
+    return NS_E_INVALID;
+  }
 
   const int mt = m >= 3 ? 4 : m;  // kernel template rows (1, 2, 4)
   size_t smem;

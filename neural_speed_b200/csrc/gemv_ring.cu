@@ -15,6 +15,7 @@
 // warps per SM cannot keep up with HBM; the launch-boundary cost is removed instead by the persistent multi-op kernel.)
 // Roofline: HBM.  Algorithmic bytes per launch = sum over weights of N*K/2 + N*ceil(K/g)*(scale_bytes [+1 if asym]).
 #include "nsb.cuh"
+#include "quant_smem.cuh"
 
 namespace {
 
@@ -172,7 +173,13 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
 
   // ===================== consumers =====================
   pdl_wait();  // activations (and residual) come from earlier kernels
-  {
+  if (P.act_f32) {
+    // fused NE_TASK_INIT: quantise the fp32 rows straight into the shared-memory image (no separate kernel, no round trip)
+    const QuantIn qi{P.act_f32, P.lda, P.k, P.kpad, P.comp == NS_COMP_Q8_0 ? 32 : P.group, R.act_row, P.meta_off, P.meta_stride};
+    if (P.comp == NS_COMP_Q8_0) nsq::quantise_to_smem<NS_COMP_Q8_0, kConsumers * 32>(qi, P.m, smem_base);
+    else if (P.comp == NS_COMP_INT8) nsq::quantise_to_smem<NS_COMP_INT8, kConsumers * 32>(qi, P.m, smem_base);
+    else nsq::quantise_to_smem<NS_COMP_INT8_S8, kConsumers * 32>(qi, P.m, smem_base);
+  } else {
     const uint4* src = reinterpret_cast<const uint4*>(P.act);
     uint4* dstv = reinterpret_cast<uint4*>(smem);
     const int nvec = P.act_bytes >> 4;

@@ -74,7 +74,9 @@ static inline int ns_meta_stride(int kpad) { return (int)ns_round_up((size_t)(kp
 int ns_launch_act_prep(const float* act, int lda, int m, const ns_weight* w, void* ws, cudaStream_t st);
 int ns_gemv_tile_rows(const ns_weight* w);
 int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* act_ws, float* dst, int ldo, int m,
-                   int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st);
+                   int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st,
+                   const float* act_f32 = nullptr, int lda = 0);
+bool ns_gemv_fused_quant_ok(const ns_weight* w);  // can the GEMV quantise the activations itself (one launch)?
 int ns_launch_repack_q4_0(const void* rows_dev, size_t nb01, ns_weight* w, cudaStream_t st);
 int ns_launch_repack_canonical(const int8_t* q_kn_dev, const float* sc_dev, const int8_t* zp_dev, ns_weight* w,
                                cudaStream_t st);
@@ -102,7 +104,9 @@ struct GemvParams {
   int k, kpad, group, ngroups, stype;
   int cpg;  // 32-element chunks per scale group
   int pitch, q_bytes, sc_off, zp_off;
-  const void* act;  // prepared activation image (device)
+  const void* act;  // prepared activation image (device), or NULL when act_f32 is given
+  const float* act_f32;  // raw fp32 activations [m][lda]: quantised inside the kernel (fused NE_TASK_INIT)
+  int lda, comp;
   int act_bytes;    // bytes to stage in shared memory
   int meta_off;     // byte offset of the meta array inside the image (int8 modes)
   int meta_stride;  // int2 per activation row
@@ -115,10 +119,6 @@ struct GemvParams {
   int npairs;
 };
 int ns_launch_gemv_ring(const GemvParams& P, int amode, bool asym, int mt, cudaStream_t st);  // gemv_ring.cu
-// program.cu: fused activation-quantisation + GEMV launch for m <= 4 rows (the hot decode path)
-bool ns_decode_op_supported(const ns_weight* w);
-int ns_launch_decode_op(const ns_weight* const* weights, int nw, int mode, const float* act, int lda, float* dst, int ldo, int m,
-                        int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st);
 
 template <typename... Args>
 static inline cudaError_t ns_launch_pdl(void (*kern)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
