@@ -9,7 +9,8 @@
 // issues cp.async.bulk (UBLKCP) copies of whole weight-row PAIRS -- a row of the NSB layout is one contiguous
 // [nibbles | scales | zero-points] byte range -- into a ring of slots guarded by full/empty mbarriers.  Each consumer warp
 // owns a whole stage at a time (two rows): no cross-warp reduction, rows dealt round-robin over CTAs (balanced at any N).
-// 8 consumer warps + 1 producer warp per CTA, 2 CTAs per SM (~105 KB ring each).  The producer streams BEFORE
+// 7 consumer warps + 1 producer warp per CTA, 2 CTAs per SM (~105 KB ring each = 3 slots per consumer warp for K=4096;
+// measured r01: 8 warps x 2 slots 60.0 %, 7 x 3 66.3 %, 6 x 3 64.4 % of the HBM roofline in back-to-back launches).  The producer streams BEFORE
 // griddepcontrol.wait, so under programmatic dependent launch a CTA starts filling its ring the moment it becomes
 // resident.  (Measured alternative, r01: quarter-SM CTAs that let the next kernel co-reside were slower -- 8 consumer
 // warps per SM cannot keep up with HBM; the launch-boundary cost is removed instead by the persistent multi-op kernel.)
@@ -19,7 +20,7 @@
 
 namespace {
 
-constexpr int kConsumers = 8;
+constexpr int kConsumers = 7;
 constexpr int kThreads = (kConsumers + 1) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -328,7 +329,7 @@ int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
   const int act_row = (int)ns_round_up((size_t)P.kpad, 1024);
   const size_t act_region = ns_round_up((size_t)mt * act_row + (size_t)mt * P.meta_stride * 8, 128);
   // Shared-memory plan: half an SM (two CTAs per SM), or a whole SM for very long rows.
-  const size_t budgets[2] = {110 * 1024, 200 * 1024};
+  const size_t budgets[2] = {113 * 1024, 200 * 1024};
   int stages = 0;
   size_t budget = 0;
   for (int i = 0; i < 2; ++i) {
@@ -344,7 +345,7 @@ int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
   }
   if (stages > 32) stages = 32;
   const size_t smem = act_region + (size_t)stages * stage_bytes + (size_t)stages * 16;
-  const int ctas_per_sm = budget > 110 * 1024 ? 1 : 2;
+  const int ctas_per_sm = budget > 113 * 1024 ? 1 : 2;
   int grid = ns_num_sms() * ctas_per_sm;
   if (grid > P.npairs) grid = P.npairs;
   if (grid < 1) grid = 1;
