@@ -456,8 +456,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fmt", default="q4_0", choices=["q4_0", "int4g128"])
     ap.add_argument("--layers", type=int, default=N_LAYER, help="debug: fewer layers (invalid as a bench value)")
