@@ -363,6 +363,47 @@ def run_ours(args):
     step_gbs = alg_bytes / (ms_step * 1e-3) / 1e9
     prog_gbs = alg_bytes / (ms_prog * 1e-3) / 1e9
 
+    # ---- prefill: the same matmul nodes for a 2048-token prompt through the tcgen05 tensor-core GEMM (bf16 numerics)
+    prefill = None
+    if rank == 0 and not args.skip_prefill:
+        MP = args.prefill_tokens
+        xp = torch.randn(MP, N_EMBD, device="cuda")
+        ap_ = torch.randn(MP, N_EMBD, device="cuda")
+        qkvp = torch.zeros(3, MP, N_EMBD, device="cuda")
+        op_ = torch.zeros(MP, N_EMBD, device="cuda")
+        tmpp = torch.zeros(2, MP, N_FF, device="cuda")
+        ffnp = torch.zeros(MP, N_EMBD, device="cuda")
+        wsp_bytes = L.ns_device_workspace_bytes(MP, N_FF)
+        wsp_t = torch.zeros(wsp_bytes, dtype=torch.uint8, device="cuda")
+        wpp = C.c_void_p(wsp_t.data_ptr())
+        torch.cuda.synchronize()
+
+        def prefill_calls():
+            for lay in layers:
+                rc = L.ns_mul_qkv(lay["wq"].h, lay["wk"].h, lay["wv"].h, C.c_void_p(xp.data_ptr()), N_EMBD, C.c_void_p(qkvp.data_ptr()),
+                                  N_EMBD, MP, wpp, queue)
+                rc |= L.ns_mul_mat(lay["wo"].h, C.c_void_p(ap_.data_ptr()), N_EMBD, C.c_void_p(op_.data_ptr()), N_EMBD, MP, None, None, 0,
+                                   wpp, queue)
+                rc |= L.ns_ffn_silu(lay["w1"].h, lay["w2"].h, lay["w3"].h, C.c_void_p(xp.data_ptr()), N_EMBD, C.c_void_p(tmpp.data_ptr()),
+                                    C.c_void_p(ffnp.data_ptr()), N_EMBD, MP, wpp, queue)
+                assert rc == 0, ns.last_error()
+
+        prefill_calls()
+        L.bestla_device_sync(queue)
+        psteps = max(2, min(5, args.steps))
+        ms_pf = timed(prefill_calls, psteps, 1)
+        flops = 2.0 * MP * sum(w.n * w.k for lay in layers for w in lay.values())
+        tf = flops / (ms_pf * 1e-3) / 1e12
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        prefill = {"tokens": MP, "tokens_per_s": MP / (ms_pf * 1e-3), "ms": ms_pf, "tflops": tf,
+                   "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1400",
+                                "kernel": "gemm_w4_tc_kernel<256> (tcgen05.mma kind::f16, in-smem int4->bf16 dequant)"},
+                   "note": f"{7 * n_layers} GEMMs of the {n_layers} layers (lm_head excluded: only the last token needs logits), "
+                           "fp32 activations converted to bf16 per GEMM, outputs fp32; includes silu*mul and conversion kernels"}
+        del xp, ap_, qkvp, op_, tmpp, ffnp, wsp_t
+        torch.cuda.empty_cache()
+
     # ---- e2e: the same token through the host-buffer C-ABI (per-op, H2D activations + D2H results every call)
     e2e = None
     cpu = None
@@ -440,6 +481,7 @@ def run_ours(args):
                                               "launches": n_gemv}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step, "clocks": clocks, "setup_s": setup_s,
+            "prefill": prefill,
             "persistent_program": {"tokens_per_s": world * 1000.0 / ms_prog, "ms_per_step": ms_prog, "launches_per_step": 1,
                                    "frac": prog_gbs / hbm_peak,
                                    "note": "same matmuls as ONE cooperative launch (ns_program, grid barrier between nodes)"},
@@ -464,6 +506,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--prog-nobarrier", action="store_true", help="experiment: drop the inter-op grid barriers (no dependencies)")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-prefill", action="store_true")
+    ap.add_argument("--prefill-tokens", type=int, default=2048)
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
