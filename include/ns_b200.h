@@ -97,7 +97,23 @@ NS_API void bestla_fusion_FFN_SiLu_f32f32_forward(float* activation, void* w1ptr
                                                   float* tmp2, float* output, int seq, int fin, int fmid, int fout,
                                                   void* workspace);
 /* ne_bestla.h:75 / ne_bestla.cpp:74 -- dequantise a blob to fp32 [n][ld] (ld >= k) */
+/* GELU feed-forward nodes of the non-Llama architectures (ne_bestla.h:53-73, ip_fusion_ffn.cpp:729-779);
+ * tanh-GELU of kernel_ref.h:1570.  Gelu_Mul: tmp2 = gelu(x W1) * (x W3); GeLu: tmp1 = gelu(x W1); Add_GeLu adds b1/b2. */
+NS_API bool bestla_fusion_FFN_Gelu_Mul_f32f32_support(void* w1ptr, void* w2ptr, void* w3ptr, int seq, int fin, int fmid,
+                                                      int fout);
+NS_API void bestla_fusion_FFN_Gelu_Mul_f32f32_forward(float* activation, void* w1ptr, void* w2ptr, void* w3ptr, float* tmp1,
+                                                      float* tmp2, float* output, int seq, int fin, int fmid, int fout,
+                                                      void* workspace);
+NS_API bool bestla_fusion_FFN_GeLu_f32f32_support(void* w1ptr, void* w2ptr, int seq, int fin, int fmid, int fout);
+NS_API void bestla_fusion_FFN_GeLu_f32f32_forward(float* activation, void* w1ptr, void* w2ptr, float* tmp1, float* output,
+                                                  int seq, int fin, int fmid, int fout, void* workspace);
+NS_API bool bestla_fusion_FFN_Add_GeLu_f32f32_support(void* w1ptr, void* w2ptr, int seq, int fin, int fmid, int fout);
+NS_API void bestla_fusion_FFN_Add_GeLu_f32f32_forward(float* activation, void* w1ptr, void* w2ptr, float* b1ptr, float* b2ptr,
+                                                      float* tmp1, float* output, int seq, int fin, int fmid, int fout,
+                                                      bool boardcast_bias, void* workspace);
 NS_API void bestla_unpackweight_fp32(void* wptr, int n, int k, float* fp32data, int ld);
+/* ne_bestla.h:77: quantise f32 [n][ld] into dstptr with the attributes of the blob srcptr (host only) */
+NS_API void bestla_packweight_copyattr(const float* f32ptr, void* dstptr, int n, int k, int ld, void* srcptr);
 
 /* ------------------------------------------------------------------ 2. device-resident set (NS_SYCL analogue) */
 /* ne_bestla.h:86-95.  device = opaque context owning one CUDA stream on cuda:<current>; queue = cudaStream_t */
@@ -153,6 +169,10 @@ NS_API int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* dst,
 NS_API int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_weight* wv, const float* act, int lda, float* dst,
                       int ldo, int m, void* workspace, void* queue);
 /* ne_ffn_silu: tmp = silu(act.W1^T) * (act.W3^T) [m][fmid];  dst = tmp.W2^T [m][fout] */
+/* GELU variants on device buffers: w3 != NULL -> Gelu_Mul (b1/b2 must be NULL); w3 == NULL -> (Add_)GeLu with optional biases */
+NS_API int ns_ffn_gelu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* b1, const float* b2,
+                       int bias_bcast, const float* act, int lda, float* tmp, float* dst, int ldo, int m, void* workspace,
+                       void* queue);
 NS_API int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda, float* tmp,
                        float* dst, int ldo, int m, void* workspace, void* queue);
 

@@ -40,13 +40,16 @@ EXPORTS = [
     "bestla_fusion_QKV_f32f32_get_workspace_size", "bestla_fusion_QKV_f32f32_support", "bestla_fusion_QKV_f32f32_forward",
     "bestla_fusion_FFN_f32f32_get_workspace_size", "bestla_fusion_FFN_SiLu_f32f32_support",
     "bestla_fusion_FFN_SiLu_f32f32_forward", "bestla_unpackweight_fp32",
+    "bestla_fusion_FFN_Gelu_Mul_f32f32_support", "bestla_fusion_FFN_Gelu_Mul_f32f32_forward",
+    "bestla_fusion_FFN_GeLu_f32f32_support", "bestla_fusion_FFN_GeLu_f32f32_forward",
+    "bestla_fusion_FFN_Add_GeLu_f32f32_support", "bestla_fusion_FFN_Add_GeLu_f32f32_forward", "bestla_packweight_copyattr",
     "bestla_create_device", "bestla_get_device_queue", "bestla_release_device", "bestla_device_gmem_size",
     "bestla_device_malloc", "bestla_device_free", "bestla_device_memcpy", "bestla_device_memcpy_sync", "bestla_device_sync",
     "bestla_device_storage_size", "ns_device_storage_bytes", "bestla_device_load_storage", "ns_device_workspace_bytes",
     "bestla_device_f32f32_forward",
     "ns_weight_from_q4_0", "ns_weight_from_btla_blob", "ns_weight_from_unpacked", "ns_weight_free", "ns_weight_info",
     "ns_weight_set_comp", "ns_weight_algorithmic_bytes", "ns_weight_dequant_f32",
-    "ns_mul_mat", "ns_mul_qkv", "ns_ffn_silu", "ns_mul_mat_q4_0_f32_host",
+    "ns_mul_mat", "ns_mul_qkv", "ns_ffn_silu", "ns_ffn_gelu", "ns_mul_mat_q4_0_f32_host",
     "ns_program_create", "ns_program_add_matmul", "ns_program_finalize", "ns_program_run", "ns_program_algorithmic_bytes",
     "ns_program_free",
     "ns_prepare_activation", "ns_matmul_prepared", "ns_graph_begin", "ns_graph_end", "ns_graph_launch", "ns_graph_free",
@@ -121,6 +124,21 @@ def lib() -> C.CDLL:
     L.ns_mul_mat.argtypes = [vp, vp, i, vp, i, i, vp, vp, i, vp, vp]
     L.ns_mul_qkv.argtypes = [vp, vp, vp, vp, i, vp, i, i, vp, vp]
     L.ns_ffn_silu.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp, vp]
+    L.ns_ffn_gelu.argtypes = [vp, vp, vp, vp, vp, i, vp, i, vp, vp, i, i, vp, vp]
+    L.bestla_fusion_FFN_Gelu_Mul_f32f32_support.restype = C.c_bool
+    L.bestla_fusion_FFN_Gelu_Mul_f32f32_support.argtypes = [vp, vp, vp, i, i, i, i]
+    L.bestla_fusion_FFN_Gelu_Mul_f32f32_forward.restype = None
+    L.bestla_fusion_FFN_Gelu_Mul_f32f32_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
+    L.bestla_fusion_FFN_GeLu_f32f32_support.restype = C.c_bool
+    L.bestla_fusion_FFN_GeLu_f32f32_support.argtypes = [vp, vp, i, i, i, i]
+    L.bestla_fusion_FFN_GeLu_f32f32_forward.restype = None
+    L.bestla_fusion_FFN_GeLu_f32f32_forward.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp]
+    L.bestla_fusion_FFN_Add_GeLu_f32f32_support.restype = C.c_bool
+    L.bestla_fusion_FFN_Add_GeLu_f32f32_support.argtypes = [vp, vp, i, i, i, i]
+    L.bestla_fusion_FFN_Add_GeLu_f32f32_forward.restype = None
+    L.bestla_fusion_FFN_Add_GeLu_f32f32_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, C.c_bool, vp]
+    L.bestla_packweight_copyattr.restype = None
+    L.bestla_packweight_copyattr.argtypes = [vp, vp, i, i, i, vp]
     L.ns_mul_mat_q4_0_f32_host.argtypes = [vp, sz, vp, vp, i, i, i]
     L.ns_prepare_activation.argtypes = [vp, vp, i, i, vp, vp]
     L.ns_matmul_prepared.argtypes = [vp, i, i, vp, vp, i, i, vp, i, vp, vp, vp]
@@ -314,6 +332,14 @@ def ffn_silu(w1: Weight, w2: Weight, w3: Weight, act_ptr: int, lda: int, tmp_ptr
              queue=None):
     _check(lib().ns_ffn_silu(w1.h, w2.h, w3.h, C.c_void_p(act_ptr), lda, C.c_void_p(tmp_ptr), C.c_void_p(dst_ptr), ldo, m,
                              None, queue), "ns_ffn_silu")
+
+
+def ffn_gelu(w1: Weight, w2: Weight, w3, b1_ptr, b2_ptr, bias_bcast: int, act_ptr: int, lda: int, tmp_ptr: int, dst_ptr: int,
+             ldo: int, m: int, queue=None):
+    """GELU feed-forward (Gelu_Mul when w3 is given, else (Add_)GeLu), device pointers."""
+    _check(lib().ns_ffn_gelu(w1.h, w2.h, w3.h if w3 is not None else None, C.c_void_p(b1_ptr) if b1_ptr else None,
+                             C.c_void_p(b2_ptr) if b2_ptr else None, bias_bcast, C.c_void_p(act_ptr), lda, C.c_void_p(tmp_ptr),
+                             C.c_void_p(dst_ptr), ldo, m, None, queue), "ns_ffn_gelu")
 
 
 class Program:

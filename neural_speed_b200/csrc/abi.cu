@@ -561,26 +561,37 @@ extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_wei
   return NS_OK;
 }
 
-// tmp: [2][m][fmid] floats when m > 4 (gate and up GEMM outputs; the product lands in the first half), else [m][fmid]
-extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda,
-                           float* tmp, float* dst, int ldo, int m, void* workspace, void* queue) {
+// Fused feed-forward.  w3 != NULL: tmp = elt(x W1^T) * (x W3^T), dst = tmp W2^T (SiLu / Gelu_Mul, ip_fusion_ffn.cpp:734-753).
+// w3 == NULL: tmp = gelu(x W1^T + b1), dst = tmp W2^T + b2 (GeLu / Add_GeLu, ip_fusion_ffn.cpp:755-779).
+// tmp: [2][m][fmid] floats when m > 4 and w3 is given (gate and up GEMM outputs; the product lands in the first half), else [m][fmid]
+static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, int eltop, const float* b1, const float* b2,
+                    int bcast, const float* act, int lda, float* tmp, float* dst, int ldo, int m, void* workspace, void* queue) {
   if (int rc = ns_ensure_device()) return rc;
-  if (!w1 || !w2 || !w3 || !act || !tmp || !dst || m <= 0 || w2->k != w1->n) return NS_E_INVALID;
+  if (!w1 || !w2 || !act || !tmp || !dst || m <= 0 || w2->k != w1->n || (w3 && (w3->n != w1->n || w3->k != w1->k)) ||
+      (w3 && (b1 || b2)) || (!w3 && eltop != NS_ELT_GELU)) {
+    ns_set_error("fused FFN: invalid arguments");
+    return NS_E_INVALID;
+  }
   cudaStream_t st = stream_of(queue);
   const int fmid = w1->n;
-  const bool tc = use_tc(w1, m, 0) && ns_gemm_tc_supported(w2) && ns_gemm_tc_supported(w3) && !w1->shuffle && !w3->shuffle;
+  const bool tc = use_tc(w1, m, 0) && ns_gemm_tc_supported(w2) && (!w3 || ns_gemm_tc_supported(w3)) && !w1->shuffle &&
+                  !(w3 && w3->shuffle);
   const int kmax = w1->kpad > w2->kpad ? w1->kpad : w2->kpad;
   void* ws = pick_ws(workspace, st, tc ? ns_gemm_tc_workspace_bytes(m, kmax) : ns_act_workspace_bytes(4, kmax));
   if (!ws) return NS_E_CUDA;
   if (tc) {
     float* gate = tmp;
-    float* up = tmp + (size_t)m * fmid;
     if (int rc = ns_launch_act_bf16(w1, act, lda, m, ws, st)) return rc;
-    if (int rc = ns_launch_gemm_tc(w1, ws, gate, fmid, m, nullptr, 0, nullptr, st)) return rc;
-    if (int rc = ns_launch_gemm_tc(w3, ws, up, fmid, m, nullptr, 0, nullptr, st)) return rc;
-    if (int rc = ns_launch_silu_mul(gate, up, gate, nullptr, (size_t)m * fmid, st)) return rc;
+    if (int rc = ns_launch_gemm_tc(w1, ws, gate, fmid, m, b1, bcast, nullptr, st)) return rc;
+    if (w3) {
+      float* up = tmp + (size_t)m * fmid;
+      if (int rc = ns_launch_gemm_tc(w3, ws, up, fmid, m, nullptr, 0, nullptr, st)) return rc;
+      if (int rc = ns_launch_silu_mul(gate, up, gate, nullptr, (size_t)m * fmid, st, eltop)) return rc;
+    } else {
+      if (int rc = ns_launch_gelu(gate, (size_t)m * fmid, st)) return rc;
+    }
     if (int rc = ns_launch_act_bf16(w2, gate, fmid, m, ws, st)) return rc;
-    return ns_launch_gemm_tc(w2, ws, dst, ldo, m, nullptr, 0, nullptr, st);
+    return ns_launch_gemm_tc(w2, ws, dst, ldo, m, b2, bcast, nullptr, st);
   }
   const ns_weight* gu[2] = {w1, w3};
   int tile = ns_gemv_tile_rows(w1);
@@ -590,9 +601,16 @@ extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_we
     const float* a = act + (size_t)m0 * lda;
     if (!fused1)
       if (int rc = ns_launch_act_prep(a, lda, mt, w1, ws, st)) return rc;
-    if (int rc = ns_launch_gemv(gu, 2, NS_GEMV_GATE_UP_SILU, fused1 ? nullptr : ws, tmp + (size_t)m0 * fmid, fmid, mt, m, nullptr,
-                                0, nullptr, nullptr, st, fused1 ? a : nullptr, lda))
-      return rc;
+    if (w3) {
+      if (int rc = ns_launch_gemv(gu, 2, NS_GEMV_GATE_UP_SILU, fused1 ? nullptr : ws, tmp + (size_t)m0 * fmid, fmid, mt, m, nullptr,
+                                  0, nullptr, nullptr, st, fused1 ? a : nullptr, lda, eltop))
+        return rc;
+    } else {
+      if (int rc = ns_launch_gemv(gu, 1, NS_GEMV_PLAIN, fused1 ? nullptr : ws, tmp + (size_t)m0 * fmid, fmid, mt, m,
+                                  b1 ? (bcast ? b1 : b1 + (size_t)m0 * fmid) : nullptr, bcast, nullptr, nullptr, st,
+                                  fused1 ? a : nullptr, lda, NS_ELT_GELU))
+        return rc;
+    }
   }
   tile = ns_gemv_tile_rows(w2);
   for (int m0 = 0; m0 < m; m0 += tile) {
@@ -600,11 +618,22 @@ extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_we
     const float* a = tmp + (size_t)m0 * fmid;
     if (!fused2)
       if (int rc = ns_launch_act_prep(a, fmid, mt, w2, ws, st)) return rc;
-    if (int rc = ns_launch_gemv(&w2, 1, NS_GEMV_PLAIN, fused2 ? nullptr : ws, dst + (size_t)m0 * ldo, ldo, mt, m, nullptr, 0,
-                                nullptr, nullptr, st, fused2 ? a : nullptr, fmid))
+    if (int rc = ns_launch_gemv(&w2, 1, NS_GEMV_PLAIN, fused2 ? nullptr : ws, dst + (size_t)m0 * ldo, ldo, mt, m,
+                                b2 ? (bcast ? b2 : b2 + (size_t)m0 * ldo) : nullptr, bcast, nullptr, nullptr, st,
+                                fused2 ? a : nullptr, fmid))
       return rc;
   }
   return NS_OK;
+}
+extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda,
+                           float* tmp, float* dst, int ldo, int m, void* workspace, void* queue) {
+  if (!w3) return NS_E_INVALID;
+  return ffn_impl(w1, w2, w3, NS_ELT_DEFAULT, nullptr, nullptr, 0, act, lda, tmp, dst, ldo, m, workspace, queue);
+}
+extern "C" int ns_ffn_gelu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* b1, const float* b2,
+                           int bias_bcast, const float* act, int lda, float* tmp, float* dst, int ldo, int m, void* workspace,
+                           void* queue) {
+  return ffn_impl(w1, w2, w3, NS_ELT_GELU, b1, b2, bias_bcast, act, lda, tmp, dst, ldo, m, workspace, queue);
 }
 
 extern "C" int ns_prepare_activation(const ns_weight* w, const float* act, int lda, int m, void* workspace, void* queue) {
@@ -792,7 +821,8 @@ struct HostIO {  // device staging for host-buffer calls
   float* act = nullptr;
   float* out = nullptr;
   float* tmp = nullptr;
-  size_t act_elems = 0, out_elems = 0, tmp_elems = 0;
+  float* bias = nullptr;
+  size_t act_elems = 0, out_elems = 0, tmp_elems = 0, bias_elems = 0;
 };
 static HostIO g_io;
 static bool io_reserve(float** p, size_t* have, size_t need) {
@@ -933,6 +963,69 @@ extern "C" void bestla_fusion_FFN_SiLu_f32f32_forward(float* activation, void* w
   cudaMemcpyAsync(output, g_io.out, (size_t)seq * fout * 4, cudaMemcpyDeviceToHost, st);
   if (tmp2) cudaMemcpyAsync(tmp2, g_io.tmp, (size_t)seq * fmid * 4, cudaMemcpyDeviceToHost, st);
   if (cudaStreamSynchronize(st) != cudaSuccess) ns_fatal("kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
+
+static bool ffn2_support(void* w1ptr, void* w2ptr, int fin, int fmid, int fout) {
+  BlobView v[2];
+  ns_weight w[2];
+  void* ptrs[2] = {w1ptr, w2ptr};
+  for (int i = 0; i < 2; ++i)
+    if (!parse_blob(ptrs[i], &v[i]) || blob_to_weight_meta(v[i], &w[i]) != NS_OK || v[i].shuffle) return false;
+  if (v[0].n != fmid || v[0].k != fin || v[1].n != fout || v[1].k != fmid) return false;
+  return v[0].core_id == v[1].core_id;  // ffn_2w::bestla_fusion_ffn_f32f32_support, ip_fusion_ffn.cpp:33-77
+}
+static void ffn_host(float* activation, void* w1ptr, void* w2ptr, void* w3ptr, int eltop, float* b1, float* b2, bool bcast,
+                     float* tmp1, float* tmp2, float* output, int seq, int fin, int fmid, int fout) {
+  const ns_weight* w1 = cached_blob(w1ptr);
+  const ns_weight* w2 = cached_blob(w2ptr);
+  const ns_weight* w3 = w3ptr ? cached_blob(w3ptr) : nullptr;
+  if (!w1 || !w2 || (w3ptr && !w3) || w1->n != fmid || w1->k != fin || w2->n != fout || w2->k != fmid)
+    ns_fatal("invalid parameters (%s)", g_err);
+  cudaStream_t st = default_stream();
+  const size_t nb1 = b1 ? (bcast ? (size_t)fmid : (size_t)seq * fmid) : 0, nb2 = b2 ? (bcast ? (size_t)fout : (size_t)seq * fout) : 0;
+  if (!io_reserve(&g_io.act, &g_io.act_elems, (size_t)seq * fin) || !io_reserve(&g_io.out, &g_io.out_elems, (size_t)seq * fout) ||
+      !io_reserve(&g_io.tmp, &g_io.tmp_elems, (size_t)2 * seq * fmid) || !io_reserve(&g_io.bias, &g_io.bias_elems, nb1 + nb2 + 1))
+    ns_fatal("device staging allocation failed");
+  cudaMemcpyAsync(g_io.act, activation, (size_t)seq * fin * 4, cudaMemcpyHostToDevice, st);
+  if (b1) cudaMemcpyAsync(g_io.bias, b1, nb1 * 4, cudaMemcpyHostToDevice, st);
+  if (b2) cudaMemcpyAsync(g_io.bias + nb1, b2, nb2 * 4, cudaMemcpyHostToDevice, st);
+  if (ffn_impl(w1, w2, w3, eltop, b1 ? g_io.bias : nullptr, b2 ? g_io.bias + nb1 : nullptr, bcast ? 1 : 0, g_io.act, fin, g_io.tmp,
+               g_io.out, fout, seq, nullptr, st))
+    ns_fatal("%s", g_err);
+  cudaMemcpyAsync(output, g_io.out, (size_t)seq * fout * 4, cudaMemcpyDeviceToHost, st);
+  // the reference leaves the activated intermediate in tmp1 (2w) / the gated product in tmp2 (3w)
+  float* tmp_host = w3 ? tmp2 : tmp1;
+  if (tmp_host) cudaMemcpyAsync(tmp_host, g_io.tmp, (size_t)seq * fmid * 4, cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) ns_fatal("kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
+extern "C" bool bestla_fusion_FFN_Gelu_Mul_f32f32_support(void* w1ptr, void* w2ptr, void* w3ptr, int seq, int fin, int fmid,
+                                                          int fout) {
+  return bestla_fusion_FFN_SiLu_f32f32_support(w1ptr, w2ptr, w3ptr, seq, fin, fmid, fout);
+}
+extern "C" void bestla_fusion_FFN_Gelu_Mul_f32f32_forward(float* activation, void* w1ptr, void* w2ptr, void* w3ptr, float* tmp1,
+                                                          float* tmp2, float* output, int seq, int fin, int fmid, int fout,
+                                                          void* workspace) {
+  (void)workspace;
+  ffn_host(activation, w1ptr, w2ptr, w3ptr, NS_ELT_GELU, nullptr, nullptr, false, tmp1, tmp2, output, seq, fin, fmid, fout);
+}
+extern "C" bool bestla_fusion_FFN_GeLu_f32f32_support(void* w1ptr, void* w2ptr, int seq, int fin, int fmid, int fout) {
+  (void)seq;
+  return ffn2_support(w1ptr, w2ptr, fin, fmid, fout);
+}
+extern "C" void bestla_fusion_FFN_GeLu_f32f32_forward(float* activation, void* w1ptr, void* w2ptr, float* tmp1, float* output,
+                                                      int seq, int fin, int fmid, int fout, void* workspace) {
+  (void)workspace;
+  ffn_host(activation, w1ptr, w2ptr, nullptr, NS_ELT_GELU, nullptr, nullptr, false, tmp1, nullptr, output, seq, fin, fmid, fout);
+}
+extern "C" bool bestla_fusion_FFN_Add_GeLu_f32f32_support(void* w1ptr, void* w2ptr, int seq, int fin, int fmid, int fout) {
+  (void)seq;
+  return ffn2_support(w1ptr, w2ptr, fin, fmid, fout);
+}
+extern "C" void bestla_fusion_FFN_Add_GeLu_f32f32_forward(float* activation, void* w1ptr, void* w2ptr, float* b1ptr, float* b2ptr,
+                                                          float* tmp1, float* output, int seq, int fin, int fmid, int fout,
+                                                          bool boardcast_bias, void* workspace) {
+  (void)workspace;
+  ffn_host(activation, w1ptr, w2ptr, nullptr, NS_ELT_GELU, b1ptr, b2ptr, boardcast_bias, tmp1, nullptr, output, seq, fin, fmid, fout);
 }
 
 extern "C" void bestla_unpackweight_fp32(void* wptr, int n, int k, float* fp32data, int ld) {

@@ -377,18 +377,30 @@ int ns_launch_act_bf16(const ns_weight* w, const float* act, int lda, int m, voi
 
 // silu(gate) * up, elementwise (epilogues Swish alpha=-1 + Mul of ip_fusion_ffn.cpp:408-470, kernel_ref.h:1574)
 __global__ void __launch_bounds__(256) silu_mul_kernel(const float* __restrict__ g, const float* __restrict__ u,
-                                                       float* __restrict__ out, float* __restrict__ aux, size_t total) {
+                                                       float* __restrict__ out, float* __restrict__ aux, size_t total,
+                                                       int eltop) {
   pdl_launch_dependents();
   pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const float x = g[i];
-  const float sg = x / (1.f + expf(-x));
+  const float sg = eltop == NS_ELT_GELU ? ns_gelu(x) : ns_silu(x);
   if (aux) aux[i] = sg;
   out[i] = sg * u[i];
 }
-int ns_launch_silu_mul(const float* g, const float* u, float* out, float* aux, size_t total, cudaStream_t st) {
-  NS_CUDA_TRY(ns_launch_pdl(silu_mul_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, g, u, out, aux, total));
+int ns_launch_silu_mul(const float* g, const float* u, float* out, float* aux, size_t total, cudaStream_t st, int eltop) {
+  NS_CUDA_TRY(ns_launch_pdl(silu_mul_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, g, u, out, aux, total, eltop));
+  ns_count_launch();
+  return NS_OK;
+}
+__global__ void __launch_bounds__(256) gelu_kernel(float* __restrict__ x, size_t total) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) x[i] = ns_gelu(x[i]);
+}
+int ns_launch_gelu(float* x, size_t total, cudaStream_t st) {
+  NS_CUDA_TRY(ns_launch_pdl(gelu_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, x, total));
   ns_count_launch();
   return NS_OK;
 }

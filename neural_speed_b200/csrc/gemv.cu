@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvParams P) {
         for (int m = 0; m < M; ++m) {
           if (m < P.m) {
             const float g = acc[0][m], up = acc[1][m];
-            const float sg = g / (1.f + expf(-g));  // swish alpha=-1 (kernel_ref.h:1574)
+            const float sg = P.eltop == NS_ELT_GELU ? ns_gelu(g) : ns_silu(g);  // kernel_ref.h:1569-1576
             if (P.aux) P.aux[(size_t)m * P.ldo + rr[0].out] = sg;
             P.dst[(size_t)m * P.ldo + rr[0].out] = sg * up;
           }
@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvParams P) {
               const size_t o = (size_t)m * P.ldo + rr[r].out;
               float v = acc[r][m];
               if (P.bias) v += P.bias_bcast ? P.bias[rr[r].out] : P.bias[o];
+              if (P.eltop == NS_ELT_GELU) v = ns_gelu(v);
               if (P.residual) v += P.residual[o];
               P.dst[o] = v;
             }
@@ -369,7 +370,7 @@ bool ns_gemv_fused_quant_ok(const ns_weight* w) {
 
 int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* act_ws, float* dst, int ldo, int m,
                    int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st,
-                   const float* act_f32, int lda) {
+                   const float* act_f32, int lda, int eltop) {
   const ns_weight* w0 = ws_[0];
   for (int i = 1; i < nw; ++i) {
     const ns_weight* wi = ws_[i];
@@ -436,6 +437,7 @@ int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* ac
   P.act = act_ws;
   P.act_f32 = act_f32;
   P.lda = lda;
+  P.eltop = eltop;
   P.comp = w0->comp;
   if (act_f32 && !(ns_gemv_fused_quant_ok(w0))) {
     ns_set_error("internal: fused activation quantisation not available for this weight");

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
         for (int m = 0; m < M; ++m) {
           if (m < P.m) {
             const float g = acc[0][m], up = acc[1][m];
-            const float sg = g / (1.f + expf(-g));  // swish alpha=-1 (kernel_ref.h:1574)
+            const float sg = P.eltop == NS_ELT_GELU ? ns_gelu(g) : ns_silu(g);  // kernel_ref.h:1569-1576
             if (P.aux) P.aux[(size_t)m * P.ldo + ps.out0] = sg;
             P.dst[(size_t)m * P.ldo + ps.out0] = sg * up;
           }
@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
               const size_t o = (size_t)m * P.ldo + out;
               float v = acc[r][m];
               if (P.bias) v += P.bias_bcast ? P.bias[out] : P.bias[o];
+              if (P.eltop == NS_ELT_GELU) v = ns_gelu(v);
               if (P.residual) v += P.residual[o];
               P.dst[o] = v;
             }

@@ -75,7 +75,7 @@ int ns_launch_act_prep(const float* act, int lda, int m, const ns_weight* w, voi
 int ns_gemv_tile_rows(const ns_weight* w);
 int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* act_ws, float* dst, int ldo, int m,
                    int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st,
-                   const float* act_f32 = nullptr, int lda = 0);
+                   const float* act_f32 = nullptr, int lda = 0, int eltop = 0);
 bool ns_gemv_fused_quant_ok(const ns_weight* w);  // can the GEMV quantise the activations itself (one launch)?
 int ns_launch_repack_q4_0(const void* rows_dev, size_t nb01, ns_weight* w, cudaStream_t st);
 int ns_launch_repack_canonical(const int8_t* q_kn_dev, const float* sc_dev, const int8_t* zp_dev, ns_weight* w,
@@ -90,9 +90,12 @@ bool ns_gemm_tc_supported(const ns_weight* w);
 int ns_launch_act_bf16(const ns_weight* w, const float* act, int lda, int m, void* ws, cudaStream_t st);
 int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, int m, const float* bias, int bias_bcast,
                       const float* residual, cudaStream_t st);
-int ns_launch_silu_mul(const float* g, const float* u, float* out, float* aux, size_t total, cudaStream_t st);
+int ns_launch_silu_mul(const float* g, const float* u, float* out, float* aux, size_t total, cudaStream_t st, int eltop = 0);
+int ns_launch_gelu(float* x, size_t total, cudaStream_t st);
 
 enum { NS_GEMV_PLAIN = 0, NS_GEMV_CONCAT = 1, NS_GEMV_GATE_UP_SILU = 2 };
+// element-wise epilogue op (bestla.h:89 BTLA_ELTWISEOP): DEFAULT = Swish(alpha=-1) in gate/up mode, nothing otherwise
+enum { NS_ELT_DEFAULT = 0, NS_ELT_GELU = 1 };
 enum { A_S8 = 0, A_U8 = 1, A_F32 = 2 };
 
 // shared by both GEMV kernels
@@ -117,6 +120,7 @@ struct GemvParams {
   const float* residual;
   float* aux;
   int npairs;
+  int eltop;  // NS_ELT_*
 };
 int ns_launch_gemv_ring(const GemvParams& P, int amode, bool asym, int mt, cudaStream_t st);  // gemv_ring.cu
 
@@ -146,6 +150,11 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
                : "l"(p));
   return r;
 }
+// epilogue element-wise ops (kernel_ref.h:1569-1576: tanh-GELU and Swish alpha=-1)
+__device__ __forceinline__ float ns_gelu(float x) {
+  return 0.5f * x * (1.f + tanhf(0.7978845834732056f * (x + 0.044714998453855515f * x * x * x)));
+}
+__device__ __forceinline__ float ns_silu(float x) { return x / (1.f + expf(-x)); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -487,6 +487,41 @@ extern "C" bool BTLAGemmUnPackB(float* FpData, const void* PackedBuf, size_t N, 
   return true;
 }
 
+// Re-quantise an fp32 [n][k] matrix with the attributes (block size, dtype, scale type, asym, compute type) of an existing
+// blob `srcptr` (ne_bestla.cpp:79-112).  Nothing is written when srcptr is not a k-block blob, as in the reference.
+extern "C" void bestla_packweight_copyattr(const float* f32ptr, void* dstptr, int n, int k, int ld, void* srcptr) {
+  if (!f32ptr || !dstptr || !srcptr) return;
+  const uint8_t* b = (const uint8_t*)srcptr;
+  uint32_t prologue, qtype, stype;
+  uint64_t core;
+  int blk;
+  memcpy(&prologue, b + 8, 4);
+  memcpy(&core, b + 12, 8);
+  memcpy(&qtype, b + 36, 4);
+  memcpy(&blk, b + 40, 4);
+  if (prologue != 1 && prologue != 2) return;
+  const uint8_t* p = b + 48;
+  size_t qsz, qoff;
+  memcpy(&qsz, p, 8);
+  memcpy(&qoff, p + 8, 8);
+  p += 16 + qoff + qsz;
+  memcpy(&stype, p, 4);
+  p += 12 + 4 + 8;  // scaT zpT redT, CStep, CSize
+  size_t ssz, soff;
+  memcpy(&ssz, p, 8);
+  memcpy(&soff, p + 8, 8);
+  p += 16 + soff + ssz;
+  const bool asym = prologue == 1 && *p != 0;
+  // B operand type of the core's compute type -> ne_comp_type (gemm::CompTypeHelper::get_B, bestla_gemm.h:40-83)
+  const uint32_t comp = (uint32_t)((core >> 16) & 0xffff);
+  const uint32_t btype = (comp >> 4) & 0xf;  // tFP32=0 tBF16=1 tFP16=2 tS8=3 tU8=4
+  int ne_comp = NS_NE_COMP_UNDEF;
+  if (btype == 1) ne_comp = NS_NE_COMP_BF16;
+  if (btype == 3) ne_comp = NS_NE_COMP_INT8;
+  if (btype == 0) ne_comp = NS_NE_COMP_F32;
+  BTLAGemmQuantPackB(dstptr, f32ptr, (size_t)n, (size_t)k, (size_t)ld, (size_t)blk, qtype, stype, asym, ne_comp, false, nullptr);
+}
+
 // quantize_row_q4_0_reference (vectors/cpu/quantize.h:243-279); x*id + 8.5f as one fma, as the reference's default
 // x86 build contracts it (see oracle/oracle_ggml.c).
 extern "C" void ns_quantize_row_q4_0(const float* x, void* vy, int k) {

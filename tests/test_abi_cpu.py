@@ -138,3 +138,20 @@ def test_oracle_blob_layout_against_reference_kernels():
         packed = np.zeros(dst.size // 2, np.uint8)
         R.ref_btla_compress_s8_s4(dst.ctypes.data_as(C.c_void_p), packed.ctypes.data_as(C.c_void_p), C.c_size_t(dst.size))
         assert np.array_equal(packed, btla_blob.compress_s4(mine))
+
+
+def test_packweight_copyattr_matches_direct_quantisation():
+    """bestla_packweight_copyattr (ne_bestla.cpp:79-112): re-quantising with the attributes read from a blob gives the same
+    bytes as quantising with those attributes directly."""
+    rng = np.random.default_rng(77)
+    n, k = 96, 512
+    w_kn = rng.uniform(-0.5, 0.5, (k, n)).astype(np.float32)      # copyattr passes isTrans=false: [K][N]
+    for alg, sdt, cdt, g in (("sym", "fp32", "int8", 128), ("asym", "bf16", "int8", 32), ("sym", "fp32", "fp32", 64),
+                             ("asym", "fp32", "bf16", 128)):
+        src = ns.np_bestla_quantize(rng.uniform(-1, 1, (n, k)).astype(np.float32), "int4", g, alg, sdt, cdt)
+        want = ns.np_bestla_quantize(np.ascontiguousarray(w_kn.T), "int4", g, alg, sdt, cdt)
+        raw = np.zeros(src.size + 64, np.uint8)          # the blob's internal padding depends on the address: align like the packer
+        dst = raw[(-raw.ctypes.data) % 64:][:src.size]
+        ns.lib().bestla_packweight_copyattr(w_kn.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), n, k, n,
+                                            src.ctypes.data_as(C.c_void_p))
+        assert dst.size == want.size and np.array_equal(dst, want), (alg, sdt, cdt, g)

@@ -348,6 +348,56 @@ def test_fused_qkv_and_ffn_drop_ins():
     close(ffn, want, 1e-6)
 
 
+def _gelu(x):
+    x = x.astype(np.float32)
+    return (np.float32(0.5) * x * (np.float32(1) + np.tanh(np.float32(0.7978845834732056) *
+                                                           (x + np.float32(0.044714998453855515) * x * x * x)))).astype(np.float32)
+
+
+@pytest.mark.parametrize("m", [2, 8])
+def test_gelu_ffn_drop_ins(m):
+    """bestla_fusion_FFN_{Gelu_Mul,GeLu,Add_GeLu}_f32f32_forward (ip_fusion_ffn.cpp:745-779): the fused node must equal the
+    same matmuls issued one by one with the tanh-GELU of kernel_ref.h:1570 between them."""
+    rng = np.random.default_rng(31 + m)
+    k, n, fmid, g = 512, 384, 1408, 128
+    a = rng.uniform(-0.5, 0.5, (m, k)).astype(np.float32)
+    mk = lambda r, c: ns.np_bestla_quantize(rng.uniform(-0.5, 0.5, (r, c)).astype(np.float32), "int4", g, "sym", "fp32", "int8")
+    b1, b3, b2 = mk(fmid, k), mk(fmid, k), mk(n, fmid)
+    L = ns.lib()
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    tol = 1e-5 if m <= 4 else 2e-2  # m > 4 runs the bf16 tensor-core GEMM
+
+    def mm(x, b, rows, cols):
+        o = np.zeros((m, rows), np.float32)
+        L.bestla_f32f32_forward(p(np.ascontiguousarray(x)), p(b), p(o), m, rows, cols, cols, rows, None)
+        return o
+
+    # Gelu_Mul
+    assert L.bestla_fusion_FFN_Gelu_Mul_f32f32_support(p(b1), p(b2), p(b3), m, k, fmid, n)
+    tmp1, tmp2, out = np.zeros((m, fmid), np.float32), np.zeros((m, fmid), np.float32), np.zeros((m, n), np.float32)
+    L.bestla_fusion_FFN_Gelu_Mul_f32f32_forward(p(a), p(b1), p(b2), p(b3), p(tmp1), p(tmp2), p(out), m, k, fmid, n, None)
+    want_mid = _gelu(mm(a, b1, fmid, k)) * mm(a, b3, fmid, k)
+    close(tmp2, want_mid, tol)
+    close(out, mm(tmp2, b2, n, fmid), tol)
+    # GeLu
+    assert L.bestla_fusion_FFN_GeLu_f32f32_support(p(b1), p(b2), m, k, fmid, n)
+    assert not L.bestla_fusion_FFN_GeLu_f32f32_support(p(b1), p(b2), m, k, fmid + 1, n)
+    tmp1[:] = 0
+    out[:] = 0
+    L.bestla_fusion_FFN_GeLu_f32f32_forward(p(a), p(b1), p(b2), p(tmp1), p(out), m, k, fmid, n, None)
+    close(tmp1, _gelu(mm(a, b1, fmid, k)), tol)
+    close(out, mm(tmp1, b2, n, fmid), tol)
+    # Add_GeLu, broadcast and per-row biases
+    for bcast in (True, False):
+        bias1 = rng.normal(0, 0.5, (1 if bcast else m, fmid)).astype(np.float32)
+        bias2 = rng.normal(0, 0.5, (1 if bcast else m, n)).astype(np.float32)
+        assert L.bestla_fusion_FFN_Add_GeLu_f32f32_support(p(b1), p(b2), m, k, fmid, n)
+        L.bestla_fusion_FFN_Add_GeLu_f32f32_forward(p(a), p(b1), p(b2), p(bias1), p(bias2), p(tmp1), p(out), m, k, fmid, n, bcast,
+                                                    None)
+        close(tmp1, _gelu(mm(a, b1, fmid, k) + bias1), tol)
+        close(out, mm(tmp1, b2, n, fmid) + bias2, tol)
+
+
 def test_device_set_load_storage_and_forward():
     """the NS_SYCL-style device API: create_device / malloc / load_storage / device forward / memcpy / sync"""
     rng = np.random.default_rng(37)
