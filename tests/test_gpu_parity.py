@@ -273,6 +273,31 @@ def test_gptq_act_order_shuffle():
     close(got, oracle.btla_gemv_u8s8(a8, asc, azp, q, sc, zp, g))
 
 
+@pytest.mark.parametrize("name", ["gptq4_asym", "gptq4_sym", "gptq4_desc", "gptq8_asym", "awq4"])
+def test_gptq_awq_checkpoint_tensors_to_device_weight(name):
+    """Config 3: HF qweight/qzeros/scales/g_idx -> device weight -> matmul equals the checkpoint's own dequantised weights
+    (fp32 compute: sycl_gemm.cpp:404-442 tolerance 1e-3), and the int8 path equals the CPU oracle on the canonical tensors."""
+    import os
+    from neural_speed_b200 import convert
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "gptq_awq.npz"))
+    bits, g, sym, desc = (int(v) for v in gold[f"{name}.cfg"])
+    cfg = dict(quant_method=str(gold[f"{name}.method"]), bits=bits, group_size=g, sym=bool(sym), desc_act=bool(desc))
+    args = (gold[f"{name}.qweight"], gold[f"{name}.scales"], gold[f"{name}.qzeros"], gold[f"{name}.g_idx"])
+    c = convert.to_canonical(*args, **cfg)
+    k, n = c["q"].shape
+    rng = np.random.default_rng(41)
+    a = rng.uniform(-0.5, 0.5, (3, k)).astype(np.float32)
+    order = np.argsort(gold[f"{name}.g_idx"], kind="stable") if desc else np.arange(k)
+    wdq = oracle.btla_dequant(c["q"], c["scales"], c["zp"], g)               # [K, N] in regrouped row order
+    got = run_mul_mat(convert.to_weight(*args, comp=ns.COMP_F32, **cfg), a)
+    assert np.abs(got - oracle.gemm_f64acc(np.ascontiguousarray(a[:, order]), wdq)).max() <= 1e-3
+    if bits == 4:
+        got8 = run_mul_mat(convert.to_weight(*args, **cfg), a)
+        a8, asc, azp = oracle.btla_quantize_act_u8(np.ascontiguousarray(a[:, order]), g)
+        zp = c["zp"] if c["zp"] is not None else None
+        close(got8, oracle.btla_gemv_u8s8(a8, asc, azp, c["q"], c["scales"], zp, g))
+
+
 # ------------------------------------------------------------------------------------------------------- blobs + drop-ins
 @pytest.mark.parametrize("cdt,sdt,alg", [("int8", "fp32", "sym"), ("int8", "bf16", "asym"), ("fp32", "fp32", "sym"),
                                          ("bf16", "fp32", "asym")])
