@@ -33,7 +33,7 @@ extern "C" {
 
 /* ------------------------------------------------------------------------------------------------ enums */
 /* weight element formats in the device ("NSB") layout */
-enum ns_wfmt { NS_W_S4 = 0, NS_W_S8 = 1, NS_W_NF4 = 2 };
+enum ns_wfmt { NS_W_S4 = 0, NS_W_S8 = 1, NS_W_NF4 = 2, NS_W_Q6K = 3 /* ggml block_q6_K, only via ns_weight_from_q6_K */ };
 /* scale storage */
 enum ns_stype { NS_S_F32 = 0, NS_S_BF16 = 1, NS_S_F16 = 2 };
 /* activation numerics ("compute type"): which reference arithmetic the kernel reproduces
@@ -145,6 +145,10 @@ typedef struct ns_weight ns_weight; /* opaque: repacked weight in HBM + metadata
  * (data_types.h:79-83), row stride nb01 bytes.  `rows` may be a host or a device pointer (rows_on_device). */
 NS_API ns_weight* ns_weight_from_q4_0(const void* rows, int n, int k, size_t nb01, int rows_on_device, void* queue);
 /* serialized BesTLA blob (host memory), StorageWeightKBlockNInteger / NFloat */
+/* N rows of K/256 block_q6_K (core/data_types.h:133-138, 210 bytes each), row stride nb01: the type of output.weight in
+ * llama.cpp "Q4_0" GGUF files.  ns_mul_mat on it reproduces quantize_row_q8_K + ggml_vec_dot_q6_K_q8_K
+ * (vectors/cpu/quantize.h:1020, core/layers/vec_dot.h:907) bit for bit; plain matmul only (no fused QKV/FFN). */
+NS_API ns_weight* ns_weight_from_q6_K(const void* rows, int n, int k, size_t nb01, int rows_on_device, void* queue);
 NS_API ns_weight* ns_weight_from_btla_blob(const void* blob, void* queue);
 /* canonical unpacked container as BTLAGemmPackB takes it (bestla_gemm.h:46-50): q int8 [k][n] (values, e.g.
  * nibble-8), scales f32 [k/g][n], zp int8 [k/g][n] or NULL, shuffle int[k] or NULL.  Host pointers. */
@@ -218,6 +222,9 @@ NS_API int ns_mul_mat_q4_0_f32_host(const void* src0_rows, size_t nb01, const fl
 
 /* ------------------------------------------------------------------ 3c. quantisers / packing API */
 /* device RTN->Q4_0 (quantize_row_q4_0_reference, quantize.h:243): src f32 [n][k] device -> dst block_q4_0 rows device */
+/* same for NE_TYPE_Q6_K weights (ne_layers.c:320-327) */
+NS_API int ns_mul_mat_q6_K_f32_host(const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01,
+                                    int ne11);
 NS_API int ns_device_quantize_q4_0(const float* src_dev, void* dst_dev, int n, int k, void* queue);
 /* device activation quantiser exposed for parity tests: one of ns_comp; outputs are device buffers
  * q: [m][k] (int8/uint8), scale: [m][k/g] f32, zp: [m][k/g] int32 (u8 mode, else untouched) */

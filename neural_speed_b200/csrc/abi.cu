@@ -173,6 +173,7 @@ extern "C" int ns_weight_set_comp(ns_weight* w, int comp) {
   return NS_OK;
 }
 extern "C" size_t ns_weight_algorithmic_bytes(const ns_weight* w) {
+  if (w->wfmt == NS_W_Q6K) return (size_t)w->n * (w->k / 256) * 210;  // block_q6_K bytes
   // N*K*bits/8 + N*ceil(K/g)*(scale_bytes [+1 if asym])
   const size_t bits = (w->wfmt == NS_W_S8) ? 8 : 4;
   return (size_t)w->n * w->k * bits / 8 + (size_t)w->n * w->ngroups * (stype_size(w->stype) + (w->asym ? 1 : 0));
@@ -212,6 +213,50 @@ extern "C" ns_weight* ns_weight_from_q4_0(const void* rows, int n, int k, size_t
     src = tmp;
   }
   int rc = ns_launch_repack_q4_0(src, nb01, w, st);
+  if (tmp) {
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+  }
+  if (rc) {
+    ns_weight_free(w);
+    return nullptr;
+  }
+  return w;
+}
+
+extern "C" ns_weight* ns_weight_from_q6_K(const void* rows, int n, int k, size_t nb01, int rows_on_device, void* queue) {
+  if (ns_ensure_device()) return nullptr;
+  if (!rows || n <= 0 || k <= 0 || k % 256 != 0 || nb01 < (size_t)k / 256 * 210) {
+    ns_set_error("ns_weight_from_q6_K: invalid arguments (n=%d k=%d nb01=%zu)", n, k, nb01);
+    return nullptr;
+  }
+  cudaStream_t st = stream_of(queue);
+  ns_weight* w = new ns_weight();
+  memset(w, 0, sizeof(*w));
+  w->n = n;
+  w->k = k;
+  w->wfmt = NS_W_Q6K;
+  w->stype = NS_S_F32;
+  w->comp = NS_COMP_Q8_0;  // ggml integer path (Q8_K activations)
+  w->asym = 0;
+  ns_q6k_layout(w);
+  if (weight_alloc(w, false)) {
+    delete w;
+    return nullptr;
+  }
+  const void* src = rows;
+  void* tmp = nullptr;
+  if (!rows_on_device) {
+    const size_t bytes = (size_t)n * nb01;
+    if (!ns_cuda_ok(cudaMalloc(&tmp, bytes), "cudaMalloc(q6_K staging)") ||
+        !ns_cuda_ok(cudaMemcpyAsync(tmp, rows, bytes, cudaMemcpyHostToDevice, st), "H2D q6_K rows")) {
+      if (tmp) cudaFree(tmp);
+      ns_weight_free(w);
+      return nullptr;
+    }
+    src = tmp;
+  }
+  int rc = ns_launch_repack_q6k(src, nb01, w, st);
   if (tmp) {
     cudaStreamSynchronize(st);
     cudaFree(tmp);
@@ -477,6 +522,7 @@ extern "C" ns_weight* ns_weight_from_btla_blob(const void* blob, void* queue) {
 extern "C" int ns_weight_dequant_f32(const ns_weight* w, float* dst_dev, int ld, void* queue) {
   if (int rc = ns_ensure_device()) return rc;
   if (!w || !dst_dev || ld < w->k) return NS_E_INVALID;
+  if (w->wfmt == NS_W_Q6K) return ns_launch_dequant_q6k(w, dst_dev, ld, stream_of(queue));
   return ns_launch_dequant(w, dst_dev, ld, stream_of(queue));
 }
 
@@ -507,10 +553,22 @@ extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* 
     return NS_E_INVALID;
   }
   cudaStream_t st = stream_of(queue);
+  const int bcast = (flags & NS_MM_BIAS_BCAST) ? 1 : 0;
+  if (w->wfmt == NS_W_Q6K) {  // ggml Q6_K x Q8_K, tiles of <= 4 activation rows
+    void* ws6 = pick_ws(workspace, st, ns_q6k_workspace_bytes(4, w->k));
+    if (!ws6) return NS_E_CUDA;
+    for (int m0 = 0; m0 < m; m0 += 4) {
+      const int mt = m - m0 < 4 ? m - m0 : 4;
+      if (int rc = ns_launch_mul_mat_q6k(w, act + (size_t)m0 * lda, lda, dst + (size_t)m0 * ldo, ldo, mt,
+                                         bias ? (bcast ? bias : bias + (size_t)m0 * ldo) : nullptr, bcast,
+                                         residual ? residual + (size_t)m0 * ldo : nullptr, ws6, st))
+        return rc;
+    }
+    return NS_OK;
+  }
   const bool tc = use_tc(w, m, flags);
   void* ws = pick_ws(workspace, st, ws_need(w, m, tc));
   if (!ws) return NS_E_CUDA;
-  const int bcast = (flags & NS_MM_BIAS_BCAST) ? 1 : 0;
   if (tc) {
     // M > 4: tcgen05 tensor-core GEMM, bf16 numerics (the reference switches from GEMV to GEMM at M > 4 as well)
     if (int rc = ns_launch_act_bf16(w, act, lda, m, ws, st)) return rc;
@@ -1041,23 +1099,23 @@ extern "C" void bestla_unpackweight_fp32(void* wptr, int n, int k, float* fp32da
 }
 
 // ggml host drop-in
-extern "C" int ns_mul_mat_q4_0_f32_host(const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01,
-                                        int ne11) {
+static int ggml_mul_mat_host(int q6k, const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01, int ne11) {
   if (int rc = ns_ensure_device()) return rc;
-  if (!src0_rows || !src1 || !dst || ne00 % 32 != 0 || ne01 <= 0 || ne11 <= 0) {
-    ns_set_error("ns_mul_mat_q4_0_f32_host: invalid arguments");
+  if (!src0_rows || !src1 || !dst || ne00 % (q6k ? 256 : 32) != 0 || ne01 <= 0 || ne11 <= 0) {
+    ns_set_error("ggml host matmul: invalid arguments");
     return NS_E_INVALID;
   }
   const ns_weight* w = nullptr;
   {
-    const size_t tag = blob_tag(src0_rows) ^ ((size_t)ne00 << 32) ^ (size_t)ne01;
+    const size_t tag = blob_tag(src0_rows) ^ ((size_t)ne00 << 32) ^ (size_t)ne01 ^ ((size_t)q6k << 63);
     std::unique_lock<std::mutex> lk(g_mu);
     auto it = g_cache.find(src0_rows);
     if (it != g_cache.end() && it->second.tag == tag) {
       w = it->second.w;
     } else {
       lk.unlock();
-      ns_weight* nw = ns_weight_from_q4_0(src0_rows, ne01, ne00, nb01, 0, nullptr);
+      ns_weight* nw = q6k ? ns_weight_from_q6_K(src0_rows, ne01, ne00, nb01, 0, nullptr)
+                          : ns_weight_from_q4_0(src0_rows, ne01, ne00, nb01, 0, nullptr);
       if (!nw) return NS_E_CUDA;
       lk.lock();
       auto it2 = g_cache.find(src0_rows);
@@ -1076,4 +1134,12 @@ extern "C" int ns_mul_mat_q4_0_f32_host(const void* src0_rows, size_t nb01, cons
   NS_CUDA_TRY(cudaMemcpyAsync(dst, g_io.out, (size_t)ne11 * ne01 * 4, cudaMemcpyDeviceToHost, st));
   NS_CUDA_TRY(cudaStreamSynchronize(st));
   return NS_OK;
+}
+extern "C" int ns_mul_mat_q4_0_f32_host(const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01,
+                                        int ne11) {
+  return ggml_mul_mat_host(0, src0_rows, nb01, src1, dst, ne00, ne01, ne11);
+}
+extern "C" int ns_mul_mat_q6_K_f32_host(const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01,
+                                        int ne11) {
+  return ggml_mul_mat_host(1, src0_rows, nb01, src1, dst, ne00, ne01, ne11);
 }

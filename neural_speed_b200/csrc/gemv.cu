@@ -380,6 +380,10 @@ int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* ac
       return NS_E_UNSUPPORTED;
     }
   }
+  if (w0->wfmt == NS_W_Q6K) {
+    ns_set_error("Q6_K weights support the plain matmul only");
+    return NS_E_UNSUPPORTED;
+  }
   if (mode == NS_GEMV_GATE_UP_SILU && (nw != 2 || ws_[0]->n != ws_[1]->n)) {
     ns_set_error("gate/up fusion needs two weights with equal n");
     return NS_E_INVALID;

@@ -84,6 +84,14 @@ int ns_launch_repack_btla(const void* qbuf_dev, const void* sc_dev, int src_styp
                           int kpad_src, int ntile, int packrow, int is_float, ns_weight* w, cudaStream_t st);
 int ns_launch_dequant(const ns_weight* w, float* dst, int ld, cudaStream_t st);
 
+// ggml Q6_K x Q8_K (q6k.cu)
+void ns_q6k_layout(ns_weight* w);
+int ns_launch_repack_q6k(const void* rows_dev, size_t nb01, ns_weight* w, cudaStream_t st);
+size_t ns_q6k_workspace_bytes(int m, int k);
+int ns_launch_dequant_q6k(const ns_weight* w, float* dst, int ld, cudaStream_t st);
+int ns_launch_mul_mat_q6k(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* bias,
+                          int bias_bcast, const float* residual, void* ws, cudaStream_t st);
+
 // tensor-core path (gemm_tc.cu)
 size_t ns_gemm_tc_workspace_bytes(int m, int kpad);
 bool ns_gemm_tc_supported(const ns_weight* w);

@@ -210,6 +210,65 @@ def mul_mat_q4_0_f32(wq, a, impl="oracle", nth=0):
     return dst
 
 
+# ----------------------------------------------------------------------------- ggml Q6_K / Q8_K
+Q6_K_BLOCK_BYTES = 210   # block_q6_K, data_types.h:133-138
+Q8_K_BLOCK_BYTES = 292   # block_q8_K, data_types.h:140-144
+
+
+def _rowwise_k(fn, x, out_bytes_per_block):
+    x = _c(x, np.float32)
+    rows, k = x.reshape(-1, x.shape[-1]).shape
+    assert k % 256 == 0
+    out = np.zeros((rows, k // 256 * out_bytes_per_block), np.uint8)
+    x2 = x.reshape(rows, k)
+    for r in range(rows):
+        fn(_p(x2[r]), _p(out[r]), C.c_int(k))
+    return out
+
+
+def quantize_q6_K(w, impl="oracle"):
+    """w [N,K] f32 -> uint8 [N, K/256*210] (block_q6_K rows)."""
+    fn = lib().orc_quantize_row_q6_K if impl == "oracle" else ref_ggml().ref_quantize_row_q6_K
+    return _rowwise_k(fn, w, Q6_K_BLOCK_BYTES)
+
+
+def quantize_q8_K(x, impl="oracle"):
+    """x [M,K] f32 -> uint8 [M, K/256*292] (block_q8_K rows)."""
+    fn = lib().orc_quantize_row_q8_K if impl == "oracle" else ref_ggml().ref_quantize_row_q8_K
+    return _rowwise_k(fn, x, Q8_K_BLOCK_BYTES)
+
+
+def dequantize_q6_K(wq, k, impl="oracle"):
+    wq = _c(wq, np.uint8)
+    out = np.empty((wq.shape[0], k), np.float32)
+    fn = lib().orc_dequantize_row_q6_K if impl == "oracle" else ref_ggml().ref_dequantize_row_q6_K
+    for r in range(wq.shape[0]):
+        fn(_p(wq[r]), _p(out[r]), C.c_int(k))
+    return out
+
+
+def vec_dot_q6_K_q8_K(wrow, arow, k, impl="oracle"):
+    s = C.c_float()
+    fn = lib().orc_vec_dot_q6_K_q8_K if impl == "oracle" else ref_ggml().ref_vec_dot_q6_K_q8_K
+    fn(C.c_int(k), C.byref(s), _p(_c(wrow, np.uint8)), _p(_c(arow, np.uint8)))
+    return np.float32(s.value)
+
+
+def mul_mat_q6_K_f32(wq, a, impl="oracle", nth=0):
+    """wq uint8 [N, K/256*210], a f32 [M,K] -> f32 [M,N]."""
+    wq = _c(wq, np.uint8)
+    a = _c(a, np.float32)
+    m, k = a.shape
+    n = wq.shape[0]
+    assert wq.shape[1] == k // 256 * Q6_K_BLOCK_BYTES
+    dst = np.empty((m, n), np.float32)
+    wdata = np.zeros(m * (k // 256) * Q8_K_BLOCK_BYTES + 64, np.uint8)
+    fn = lib().orc_mul_mat_q6_K_f32 if impl == "oracle" else ref_ggml().ref_mul_mat_q6_K_f32
+    fn.restype = C.c_int
+    fn(_p(wq), _p(a), _p(dst), C.c_int(n), C.c_int(k), C.c_int(m), _p(wdata), C.c_int(nth))
+    return dst
+
+
 def argmax(x):
     x = _c(x, np.float32).ravel()
     lib().orc_argmax_f32.restype = C.c_int

@@ -234,3 +234,197 @@ ORC_API int orc_argmax_f32(const float* x, int n) {
     if (x[i] > x[best]) best = i;
   return best;
 }
+
+/* ================================================================================================================
+ * Q6_K weights x Q8_K activations (llama.cpp "Q4_0" GGUF files keep output.weight in Q6_K).
+ *   block_q6_K / block_q8_K          core/data_types.h:133-145
+ *   nearest_int, make_qx_quants      vectors/cpu/quantize.h:801-875
+ *   quantize_row_q6_K_reference      :877-954      dequantize_row_q6_K :956-999
+ *   quantize_row_q8_K_reference      :1020-1055
+ *   ggml_vec_dot_q6_K_q8_K (AVX2)    core/layers/vec_dot.h:907-983
+ * ================================================================================================================ */
+#define QKK 256
+#pragma pack(push, 1)
+typedef struct { uint8_t ql[QKK / 2]; uint8_t qh[QKK / 4]; int8_t scales[QKK / 16]; uint16_t d; } orc_q6_K; /* 210 bytes */
+#pragma pack(pop)
+typedef struct { float d; int8_t qs[QKK]; int16_t bsums[QKK / 16]; } orc_q8_K;                            /* 292 bytes */
+
+static int orc_nearest_int(float fval) { /* quantize.h:801-807: round half to even through the 1.5*2^23 trick */
+  float val = fval + 12582912.f;
+  int i;
+  memcpy(&i, &val, sizeof(int));
+  return (i & 0x007fffff) - 0x00400000;
+}
+#define ORC_MAX(a, b) ((a) > (b) ? (a) : (b))
+#define ORC_MIN(a, b) ((a) < (b) ? (a) : (b))
+
+/* make_qx_quants with rmse_type 1 (the only mode Q6_K uses, quantize.h:889).  The reference's default x86 build contracts
+ * a*b+c into fma (-ffp-contract=fast); the explicit fmaf calls below reproduce what gcc emits for these expressions. */
+static float orc_make_qx_quants_rmse1(int n, int nmax, const float* x, int8_t* L) {
+  float max = 0, amax = 0;
+  for (int i = 0; i < n; ++i) {
+    float ax = fabsf(x[i]);
+    if (ax > amax) { amax = ax; max = x[i]; }
+  }
+  if (amax < 1e-30f) {
+    for (int i = 0; i < n; ++i) L[i] = 0;
+    return 0.f;
+  }
+  float iscale = -nmax / max;
+  float sumlx = 0, suml2 = 0;
+  for (int i = 0; i < n; ++i) {
+    int l = orc_nearest_int(iscale * x[i]);
+    l = ORC_MAX(-nmax, ORC_MIN(nmax - 1, l));
+    L[i] = (int8_t)(l + nmax);
+    float w = x[i] * x[i];
+    sumlx = fmaf(w * x[i], (float)l, sumlx);
+    suml2 = fmaf(w * (float)l, (float)l, suml2);
+  }
+  float scale = sumlx / suml2;
+  float best = scale * sumlx;
+  for (int is = -9; is <= 9; ++is) {
+    if (is == 0) continue;
+    iscale = -(nmax + 0.1f * is) / max;
+    sumlx = suml2 = 0;
+    for (int i = 0; i < n; ++i) {
+      int l = orc_nearest_int(iscale * x[i]);
+      l = ORC_MAX(-nmax, ORC_MIN(nmax - 1, l));
+      float w = x[i] * x[i];
+      sumlx = fmaf(w * x[i], (float)l, sumlx);
+      suml2 = fmaf(w * (float)l, (float)l, suml2);
+    }
+    if (suml2 > 0 && sumlx * sumlx > best * suml2) {
+      for (int i = 0; i < n; ++i) {
+        int l = orc_nearest_int(iscale * x[i]);
+        L[i] = (int8_t)(nmax + ORC_MAX(-nmax, ORC_MIN(nmax - 1, l)));
+      }
+      scale = sumlx / suml2;
+      best = scale * sumlx;
+    }
+  }
+  return scale;
+}
+
+ORC_API void orc_quantize_row_q6_K(const float* x, void* vy, int k) {
+  orc_q6_K* y = (orc_q6_K*)vy;
+  int8_t L[QKK];
+  float scales[QKK / 16];
+  for (int i = 0; i < k / QKK; ++i, x += QKK) {
+    float max_scale = 0, max_abs_scale = 0;
+    for (int ib = 0; ib < QKK / 16; ++ib) {
+      const float scale = orc_make_qx_quants_rmse1(16, 32, x + 16 * ib, L + 16 * ib);
+      scales[ib] = scale;
+      const float a = fabsf(scale);
+      if (a > max_abs_scale) { max_abs_scale = a; max_scale = scale; }
+    }
+    if (!max_abs_scale) {
+      memset(&y[i], 0, sizeof(orc_q6_K));
+      continue;
+    }
+    float iscale = -128.f / max_scale;
+    y[i].d = orc_fp32_to_fp16(1 / iscale);
+    for (int ib = 0; ib < QKK / 16; ++ib) y[i].scales[ib] = (int8_t)ORC_MIN(127, orc_nearest_int(iscale * scales[ib]));
+    for (int j = 0; j < QKK / 16; ++j) {
+      float d = orc_fp16_to_fp32(y[i].d) * y[i].scales[j];
+      if (!d) continue;
+      for (int ii = 0; ii < 16; ++ii) {
+        int l = orc_nearest_int(x[16 * j + ii] / d);
+        l = ORC_MAX(-32, ORC_MIN(31, l));
+        L[16 * j + ii] = (int8_t)(l + 32);
+      }
+    }
+    uint8_t* ql = y[i].ql;
+    uint8_t* qh = y[i].qh;
+    for (int j = 0; j < QKK; j += 128, ql += 64, qh += 32)
+      for (int l = 0; l < 32; ++l) {
+        ql[l] = (uint8_t)((L[j + l] & 0xF) | ((L[j + l + 64] & 0xF) << 4));
+        ql[l + 32] = (uint8_t)((L[j + l + 32] & 0xF) | ((L[j + l + 96] & 0xF) << 4));
+        qh[l] = (uint8_t)((L[j + l] >> 4) | ((L[j + l + 32] >> 4) << 2) | ((L[j + l + 64] >> 4) << 4) | ((L[j + l + 96] >> 4) << 6));
+      }
+  }
+}
+
+/* element e (0..255) of a block as the signed 6-bit value minus 32, and its scale index (dequantize_row_q6_K :956-999) */
+static int orc_q6_K_elem(const orc_q6_K* b, int e, int* sc_idx) {
+  const int half = e >> 7, r = e & 127, c = r >> 5, l = r & 31;
+  const uint8_t lo = b->ql[64 * half + 32 * (c & 1) + l];
+  const int nib = (c >> 1) ? (lo >> 4) : (lo & 0xF);
+  const int hi = (b->qh[32 * half + l] >> (2 * c)) & 3;
+  *sc_idx = 8 * half + 2 * c + (l >> 4);
+  return (nib | (hi << 4)) - 32;
+}
+
+ORC_API void orc_dequantize_row_q6_K(const void* vx, float* y, int k) {
+  const orc_q6_K* x = (const orc_q6_K*)vx;
+  for (int i = 0; i < k / QKK; ++i) {
+    const float d = orc_fp16_to_fp32(x[i].d);
+    for (int e = 0; e < QKK; ++e) {
+      int si;
+      const int q = orc_q6_K_elem(&x[i], e, &si);
+      y[i * QKK + e] = d * x[i].scales[si] * q; /* (d * sc) * q, left to right as the reference */
+    }
+  }
+}
+
+ORC_API void orc_quantize_row_q8_K(const float* x, void* vy, int k) {
+  orc_q8_K* y = (orc_q8_K*)vy;
+  for (int i = 0; i < k / QKK; ++i, x += QKK) {
+    float max = 0, amax = 0;
+    for (int j = 0; j < QKK; ++j) {
+      float ax = fabsf(x[j]);
+      if (ax > amax) { amax = ax; max = x[j]; }
+    }
+    if (!amax) {
+      y[i].d = 0;
+      memset(y[i].qs, 0, QKK);
+      continue; /* bsums are left untouched by the reference too */
+    }
+    const float iscale = -128.f / max;
+    for (int j = 0; j < QKK; ++j) y[i].qs[j] = (int8_t)ORC_MIN(127, orc_nearest_int(iscale * x[j]));
+    for (int j = 0; j < QKK / 16; ++j) {
+      int sum = 0;
+      for (int ii = 0; ii < 16; ++ii) sum += y[i].qs[j * 16 + ii];
+      y[i].bsums[j] = (int16_t)sum;
+    }
+    y[i].d = 1 / iscale;
+  }
+}
+
+/* AVX2 structure (vec_dot.h:907-983): per super-block an int32x8 `sumi`; lane L gathers, from each of the eight
+ * 32-element chunks, elements 4L..4L+3 times their 16-group scale; then acc[L] = fma(d, (float)sumi[L], acc[L]) and the
+ * final hsum_float_8.  (maddubs never saturates here: 2*63*127 < 32767.) */
+ORC_API void orc_vec_dot_q6_K_q8_K(int n, float* s, const void* vx, const void* vy) {
+  const orc_q6_K* x = (const orc_q6_K*)vx;
+  const orc_q8_K* y = (const orc_q8_K*)vy;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < n / QKK; ++i) {
+    const float d = y[i].d * orc_fp16_to_fp32(x[i].d);
+    int32_t sumi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int chunk = 0; chunk < 8; ++chunk)
+      for (int L = 0; L < 8; ++L)
+        for (int j = 0; j < 4; ++j) {
+          const int e = 32 * chunk + 4 * L + j;
+          int si;
+          const int q = orc_q6_K_elem(&x[i], e, &si);
+          sumi[L] += (int32_t)x[i].scales[si] * q * y[i].qs[e];
+        }
+    for (int L = 0; L < 8; ++L) acc[L] = fmaf(d, (float)sumi[L], acc[L]);
+  }
+  *s = lanes8_hsum(acc);
+}
+
+ORC_API int orc_mul_mat_q6_K_f32(const void* w, const float* a, float* dst, int N, int K, int M, void* wdata, int nth) {
+  const size_t arow = (size_t)K / QKK * sizeof(orc_q8_K);
+  const size_t wrow = (size_t)K / QKK * sizeof(orc_q6_K);
+  for (int m = 0; m < M; ++m) orc_quantize_row_q8_K(a + (size_t)m * K, (char*)wdata + m * arow, K);
+#ifdef _OPENMP
+  if (nth <= 0) nth = omp_get_max_threads();
+#else
+  nth = 1;
+#endif
+#pragma omp parallel for num_threads(nth) schedule(static)
+  for (int n = 0; n < N; ++n)
+    for (int m = 0; m < M; ++m)
+      orc_vec_dot_q6_K_q8_K(K, &dst[(size_t)m * N + n], (const char*)w + n * wrow, (const char*)wdata + m * arow);
+  return nth;
+}

@@ -110,3 +110,41 @@ REF_API int ref_mul_mat_q4_0_f32(const void* w, const float* a, float* dst, int 
   }
   return nth;
 }
+
+/* ---- Q6_K weights x Q8_K activations (quantize.h:877-1060, vec_dot.h:744-990): the type llama.cpp "Q4_0" GGUF files use
+ * for output.weight.  Same driver shape as above (ne_layers.c:7085-7203 is type-generic through quantize_fns). */
+REF_API void ref_quantize_row_q6_K(const float* x, void* y, int k) { quantize_row_q6_K(x, y, k); }
+REF_API void ref_dequantize_row_q6_K(const void* x, float* y, int k) { dequantize_row_q6_K((const block_q6_K*)x, y, k); }
+REF_API void ref_quantize_row_q8_K(const float* x, void* y, int k) { quantize_row_q8_K(x, y, k); }
+REF_API void ref_vec_dot_q6_K_q8_K(int n, float* s, const void* vx, const void* vy) { ggml_vec_dot_q6_K_q8_K(n, s, vx, vy); }
+REF_API int ref_sizeof_block_q6_K(void) { return (int)sizeof(block_q6_K); }
+REF_API int ref_sizeof_block_q8_K(void) { return (int)sizeof(block_q8_K); }
+REF_API int ref_mul_mat_q6_K_f32(const void* w, const float* a, float* dst, int N, int K, int M, void* wdata, int nth) {
+  ref_ggml_init();
+  const size_t row_size = (size_t)K / QK_K * sizeof(block_q8_K);
+  const size_t nb01 = (size_t)K / QK_K * sizeof(block_q6_K);
+  for (int m = 0; m < M; ++m) quantize_row_q8_K(a + (size_t)m * K, (char*)wdata + m * row_size, K);
+#ifdef _OPENMP
+  if (nth <= 0) nth = omp_get_max_threads();
+#else
+  nth = 1;
+#endif
+#pragma omp parallel num_threads(nth)
+  {
+#ifdef _OPENMP
+    const int ith = omp_get_thread_num();
+    const int nthr = omp_get_num_threads();
+#else
+    const int ith = 0, nthr = 1;
+#endif
+    const int64_t dr = (N + nthr - 1) / nthr;
+    const int64_t ir10 = dr * ith;
+    const int64_t ir11 = MIN(ir10 + dr, N);
+    for (int m = 0; m < M; ++m) {
+      const char* src1_col = (const char*)wdata + m * row_size;
+      float* dst_col = dst + (size_t)m * N;
+      for (int64_t ir = ir10; ir < ir11; ++ir) ggml_vec_dot_q6_K_q8_K(K, &dst_col[ir], (const char*)w + ir * nb01, src1_col);
+    }
+  }
+  return nth;
+}

@@ -30,6 +30,18 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ggml_q4_0.npz"), w=w, a=a, wq=wq, aq=aq, out=out,
                         wdq=oracle.dequantize_q4_0(wq, K, "ref"))
 
+    # ---- ggml Q6_K x Q8_K (output.weight of llama.cpp "Q4_0" GGUF files): quantisers, dequantiser, mul_mat
+    rng6 = np.random.default_rng(4321)
+    N6, K6, M6 = 40, 1024, 3
+    w6 = rng6.normal(0, 0.02, (N6, K6)).astype(np.float32)
+    w6[2, :256] = 0.0
+    w6[3, 32:48] = 0.0
+    a6 = rng6.normal(0, 1.0, (M6, K6)).astype(np.float32)
+    a6[1, 256:512] = 0.0
+    wq6 = oracle.quantize_q6_K(w6, "ref")
+    np.savez_compressed(os.path.join(HERE, "ggml_q6_K.npz"), w=w6, a=a6, wq=wq6, aq=oracle.quantize_q8_K(a6, "ref"),
+                        wdq=oracle.dequantize_q6_K(wq6, K6, "ref"), out=oracle.mul_mat_q6_K_f32(wq6, a6, "ref", nth=1))
+
     # ---- BesTLA: RTN quantiser, activation quantisers, NF4 (kernel_ref.h)
     K2, N2, M2 = 256, 48, 4
     w2 = rng.uniform(-0.5, 0.5, (K2, N2)).astype(np.float32)

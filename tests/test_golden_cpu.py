@@ -18,6 +18,15 @@ def test_ggml_q4_0_golden():
     assert np.array_equal(oracle.mul_mat_q4_0_f32(z["wq"], z["a"]), z["out"])
 
 
+def test_ggml_q6_K_golden():
+    z = np.load(os.path.join(G, "ggml_q6_K.npz"))
+    k = z["w"].shape[1]
+    assert np.array_equal(oracle.quantize_q6_K(z["w"]), z["wq"])
+    assert np.array_equal(oracle.quantize_q8_K(z["a"]), z["aq"])
+    assert np.array_equal(oracle.dequantize_q6_K(z["wq"], k), z["wdq"])
+    assert np.array_equal(oracle.mul_mat_q6_K_f32(z["wq"], z["a"]), z["out"])
+
+
 @pytest.mark.parametrize("g", [32, 128])
 def test_btla_quant_golden(g):
     z = np.load(os.path.join(G, "btla_quant.npz"))

@@ -131,6 +131,47 @@ def test_q4_0_mul_mat_vs_oracle(n, k, m):
     assert oracle.argmax(got[0]) == oracle.argmax(want[0])
 
 
+@pytest.mark.parametrize("n,k,m", [(40, 1024, 1), (32000, 4096, 1), (1001, 2048, 3), (64, 4096, 4), (24, 512, 6)])
+def test_q6_K_mul_mat_bit_exact(n, k, m):
+    """NE_TYPE_Q6_K x Q8_K (lm_head of llama.cpp "Q4_0" GGUF files): the kernel keeps the AVX2 body's lane structure and
+    fma order (vec_dot.h:907-983), so the result is bit-identical to the CPU path, not merely close."""
+    rng = np.random.default_rng(300 + n + m)
+    w = rng.normal(0, 0.02, (n, k)).astype(np.float32)
+    a = rng.normal(0, 1.0, (m, k)).astype(np.float32)
+    if m > 1:
+        a[1, :256] = 0.0
+    rows = oracle.quantize_q6_K(w)
+    wd = ns.Weight.from_q6_K_host(rows, n, k)
+    assert wd.wfmt == ns.W_Q6K
+    assert np.array_equal(_dequant_dev(wd), oracle.dequantize_q6_K(rows, k))
+    want = oracle.mul_mat_q6_K_f32(rows, a)
+    got = run_mul_mat(wd, a)
+    assert np.array_equal(got, want)
+    assert oracle.argmax(got[0]) == oracle.argmax(want[0])
+    bias = rng.normal(0, 1, (1, n)).astype(np.float32)
+    assert np.array_equal(run_mul_mat(wd, a, bias=bias, flags=ns.MM_BIAS_BCAST), want + bias)
+
+
+def test_q6_K_golden_fixture_through_host_abi():
+    z = np.load(os.path.join(G, "ggml_q6_K.npz"))
+    wq, a, want = np.ascontiguousarray(z["wq"]), np.ascontiguousarray(z["a"]), z["out"]
+    n, k = z["w"].shape
+    out = np.zeros((a.shape[0], n), np.float32)
+    rc = ns.lib().ns_mul_mat_q6_K_f32_host(wq.ctypes.data_as(C.c_void_p), wq.shape[1], a.ctypes.data_as(C.c_void_p),
+                                           out.ctypes.data_as(C.c_void_p), k, n, a.shape[0])
+    assert rc == 0, ns.last_error()
+    assert np.array_equal(out, want)
+
+
+def test_q6_K_is_rejected_by_the_fused_nodes():
+    rows = oracle.quantize_q6_K(np.random.default_rng(1).normal(0, 0.02, (64, 256)).astype(np.float32))
+    w = ns.Weight.from_q6_K_host(rows, 64, 256)
+    import torch
+    x = torch.zeros(1, 256, device="cuda")
+    out = torch.zeros(3, 1, 64, device="cuda")
+    assert ns.lib().ns_mul_qkv(w.h, w.h, w.h, C.c_void_p(x.data_ptr()), 256, C.c_void_p(out.data_ptr()), 64, 1, None, None) != 0
+
+
 def test_q4_0_golden_fixture_through_host_abi():
     z = np.load(os.path.join(G, "ggml_q4_0.npz"))
     wq, a, want = np.ascontiguousarray(z["wq"]), np.ascontiguousarray(z["a"]), z["out"]

@@ -130,3 +130,44 @@ def test_btla_activation_quant(g, K):
     f = oracle.btla_quantize_act_s8(a, g, "ref")
     for x, y in zip(o, f):
         assert np.array_equal(x, y)
+
+
+# ----------------------------------------------------------------------------------------------- ggml Q6_K x Q8_K
+@need_ref_g
+def test_q6_K_block_sizes():
+    assert ref_g.ref_sizeof_block_q6_K() == oracle.Q6_K_BLOCK_BYTES and ref_g.ref_sizeof_block_q8_K() == oracle.Q8_K_BLOCK_BYTES
+
+
+@need_ref_g
+@pytest.mark.parametrize("seed,scale", [(11, 0.02), (12, 1.0), (13, 40.0)])
+def test_q6_K_quantisers_dequantiser_and_dot(seed, scale):
+    r = _rng(seed)
+    w = (r.normal(0, scale, (48, 1024))).astype(np.float32)
+    w[3, :256] = 0.0          # all-zero super-block
+    w[5, 16:32] = 0.0         # all-zero 16-group inside a live super-block (make_qx_quants early return)
+    w[7, 300] = 1000 * scale  # outlier: exercises the clamp to [-32, 31]
+    a = r.normal(0, 1.0, (3, 1024)).astype(np.float32)
+    a[1, 256:512] = 0.0       # all-zero activation block: d == 0
+    a[2, 7] = -a[2, 9]        # equal magnitudes, opposite signs: the first one decides the sign of `max`
+    wq = oracle.quantize_q6_K(w, "oracle")
+    assert np.array_equal(wq, oracle.quantize_q6_K(w, "ref"))
+    assert np.array_equal(oracle.quantize_q8_K(a, "oracle"), oracle.quantize_q8_K(a, "ref"))
+    assert np.array_equal(oracle.dequantize_q6_K(wq, 1024, "oracle"), oracle.dequantize_q6_K(wq, 1024, "ref"))
+    aq = oracle.quantize_q8_K(a, "ref")
+    for n in range(0, 48, 5):
+        for m in range(3):
+            assert oracle.vec_dot_q6_K_q8_K(wq[n], aq[m], 1024, "oracle") == oracle.vec_dot_q6_K_q8_K(wq[n], aq[m], 1024, "ref")
+    assert np.array_equal(oracle.mul_mat_q6_K_f32(wq, a, "oracle"), oracle.mul_mat_q6_K_f32(wq, a, "ref", nth=2))
+
+
+@need_ref_g
+def test_q6_K_random_bytes_dot():
+    """Any byte pattern is a valid block_q6_K: the dot must agree on adversarial bit patterns too (fp16 d kept finite)."""
+    r = _rng(21)
+    k = 512
+    wq = r.integers(0, 256, (16, k // 256 * 210), dtype=np.uint8)
+    for b in range(k // 256):
+        wq[:, b * 210 + 208:b * 210 + 210] = np.frombuffer(np.float16(r.uniform(-0.01, 0.01, 16)).tobytes(), np.uint8).reshape(16, 2)
+    a = r.normal(0, 2.0, (2, k)).astype(np.float32)
+    assert np.array_equal(oracle.mul_mat_q6_K_f32(wq, a, "oracle"), oracle.mul_mat_q6_K_f32(wq, a, "ref", nth=1))
+    assert np.array_equal(oracle.dequantize_q6_K(wq, k, "oracle"), oracle.dequantize_q6_K(wq, k, "ref"))
