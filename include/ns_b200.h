@@ -242,6 +242,12 @@ NS_API bool BTLAGemmPackB(void* PackedBuf, const int8_t* QData, const float* Sca
                           size_t ldb, size_t BlkSize, uint32_t QuantType, uint32_t ScaleDtype, bool isAsym, int CompType,
                           int* shuffle_indice, void* ThreadPool);
 NS_API bool BTLAGemmUnPackB(float* FpData, const void* PackedBuf, size_t N, size_t K, size_t ldb, void* ThreadPool);
+/* Tensor-parallel shard of a blob: bestla_split_weight (models/model_utils/model_files.h:1538-1562) -- unpack, slice the
+ * [dst_k][dst_n] block at (k_rank, n_rank) (or the rank's third of each fused Q/K/V projection), re-quantise with the source
+ * blob's attributes.  ns_split_weight_size gives the bytes `dst` must hold (0 = unsupported). Host only. */
+NS_API size_t ns_split_weight_size(const void* src, size_t dst_n, size_t dst_k);
+NS_API bool ns_split_weight(const void* src, void* dst, size_t src_n, size_t src_k, size_t dst_n, size_t dst_k, size_t n_rank,
+                            size_t k_rank, bool qkv_fusion);
 /* host Q4_0 row quantiser (ne_quantize_q4_0 path; quantize.h:243) for the weight-packing API */
 NS_API void ns_quantize_row_q4_0(const float* x, void* y, int k);
 

@@ -54,7 +54,7 @@ EXPORTS = [
     "ns_program_free",
     "ns_prepare_activation", "ns_matmul_prepared", "ns_graph_begin", "ns_graph_end", "ns_graph_launch", "ns_graph_free",
     "ns_device_quantize_q4_0", "ns_device_quantize_act",
-    "BTLAGemmPackBSize", "BTLAGemmQuantPackB", "BTLAGemmPackB", "BTLAGemmUnPackB", "ns_quantize_row_q4_0",
+    "BTLAGemmPackBSize", "BTLAGemmQuantPackB", "BTLAGemmPackB", "BTLAGemmUnPackB", "ns_quantize_row_q4_0", "ns_split_weight_size", "ns_split_weight",
 ]
 
 _lib = None
@@ -160,6 +160,10 @@ def lib() -> C.CDLL:
     L.ns_graph_free.argtypes = [vp]
     L.ns_device_quantize_q4_0.argtypes = [vp, vp, i, i, vp]
     L.ns_device_quantize_act.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp]
+    L.ns_split_weight_size.restype = sz
+    L.ns_split_weight_size.argtypes = [vp, sz, sz]
+    L.ns_split_weight.restype = C.c_bool
+    L.ns_split_weight.argtypes = [vp, vp, sz, sz, sz, sz, sz, sz, C.c_bool]
     L.BTLAGemmPackBSize.restype = sz
     L.BTLAGemmPackBSize.argtypes = [sz, sz, sz, C.c_uint32, C.c_uint32, C.c_bool, i, vp]
     L.BTLAGemmQuantPackB.restype = C.c_bool

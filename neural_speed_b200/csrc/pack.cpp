@@ -487,39 +487,83 @@ extern "C" bool BTLAGemmUnPackB(float* FpData, const void* PackedBuf, size_t N, 
   return true;
 }
 
-// Re-quantise an fp32 [n][k] matrix with the attributes (block size, dtype, scale type, asym, compute type) of an existing
-// blob `srcptr` (ne_bestla.cpp:79-112).  Nothing is written when srcptr is not a k-block blob, as in the reference.
-extern "C" void bestla_packweight_copyattr(const float* f32ptr, void* dstptr, int n, int k, int ld, void* srcptr) {
-  if (!f32ptr || !dstptr || !srcptr) return;
-  const uint8_t* b = (const uint8_t*)srcptr;
-  uint32_t prologue, qtype, stype;
+// the attributes bestla_packweight_copyattr reads back from a k-block blob (ne_bestla.cpp:79-112)
+struct BlobAttr {
+  int n, k, blk;
+  uint32_t qtype, stype;
+  bool asym;
+  int ne_comp;
+};
+static bool read_blob_attr(const void* blob, BlobAttr* a) {
+  const uint8_t* b = (const uint8_t*)blob;
+  uint32_t prologue;
   uint64_t core;
-  int blk;
   memcpy(&prologue, b + 8, 4);
   memcpy(&core, b + 12, 8);
-  memcpy(&qtype, b + 36, 4);
-  memcpy(&blk, b + 40, 4);
-  if (prologue != 1 && prologue != 2) return;
+  memcpy(&a->n, b + 28, 4);
+  memcpy(&a->k, b + 32, 4);
+  memcpy(&a->qtype, b + 36, 4);
+  memcpy(&a->blk, b + 40, 4);
+  if (prologue != 1 && prologue != 2) return false;
   const uint8_t* p = b + 48;
   size_t qsz, qoff;
   memcpy(&qsz, p, 8);
   memcpy(&qoff, p + 8, 8);
   p += 16 + qoff + qsz;
-  memcpy(&stype, p, 4);
+  memcpy(&a->stype, p, 4);
   p += 12 + 4 + 8;  // scaT zpT redT, CStep, CSize
   size_t ssz, soff;
   memcpy(&ssz, p, 8);
   memcpy(&soff, p + 8, 8);
   p += 16 + soff + ssz;
-  const bool asym = prologue == 1 && *p != 0;
-  // B operand type of the core's compute type -> ne_comp_type (gemm::CompTypeHelper::get_B, bestla_gemm.h:40-83)
-  const uint32_t comp = (uint32_t)((core >> 16) & 0xffff);
-  const uint32_t btype = (comp >> 4) & 0xf;  // tFP32=0 tBF16=1 tFP16=2 tS8=3 tU8=4
-  int ne_comp = NS_NE_COMP_UNDEF;
-  if (btype == 1) ne_comp = NS_NE_COMP_BF16;
-  if (btype == 3) ne_comp = NS_NE_COMP_INT8;
-  if (btype == 0) ne_comp = NS_NE_COMP_F32;
-  BTLAGemmQuantPackB(dstptr, f32ptr, (size_t)n, (size_t)k, (size_t)ld, (size_t)blk, qtype, stype, asym, ne_comp, false, nullptr);
+  a->asym = prologue == 1 && *p != 0;
+  // B operand type of the core's compute type -> ne_comp_type (gemm::CompTypeHelper::get_B, bestla_gemm.h:22-83)
+  const uint32_t btype = (uint32_t)((core >> 20) & 0xf);  // tFP32=0 tBF16=1 tFP16=2 tS8=3 tU8=4
+  a->ne_comp = NS_NE_COMP_UNDEF;
+  if (btype == 1) a->ne_comp = NS_NE_COMP_BF16;
+  if (btype == 3) a->ne_comp = NS_NE_COMP_INT8;
+  if (btype == 0) a->ne_comp = NS_NE_COMP_F32;
+  return true;
+}
+
+// Re-quantise an fp32 [k][ld] matrix (n columns used) with the attributes (block size, dtype, scale type, asym, compute
+// type) of an existing blob `srcptr` (ne_bestla.cpp:79-112).  Nothing is written when srcptr is not a k-block blob, as in
+// the reference.
+extern "C" void bestla_packweight_copyattr(const float* f32ptr, void* dstptr, int n, int k, int ld, void* srcptr) {
+  if (!f32ptr || !dstptr || !srcptr) return;
+  BlobAttr a;
+  if (!read_blob_attr(srcptr, &a)) return;
+  BTLAGemmQuantPackB(dstptr, f32ptr, (size_t)n, (size_t)k, (size_t)ld, (size_t)a.blk, a.qtype, a.stype, a.asym, a.ne_comp, false,
+                     nullptr);
+}
+
+// Tensor-parallel shard of a blob (bestla_split_weight, models/model_utils/model_files.h:1538-1562): unpack to fp32
+// [src_k][src_n], take the [dst_k][dst_n] block at (k_rank, n_rank) -- or, with qkv_fusion, the rank's third of each of the
+// three N-concatenated projections -- and re-quantise it with the source blob's attributes.
+extern "C" size_t ns_split_weight_size(const void* src, size_t dst_n, size_t dst_k) {
+  BlobAttr a;
+  if (!src || !read_blob_attr(src, &a)) return 0;
+  return BTLAGemmPackBSize(dst_n, dst_k, (size_t)a.blk, a.qtype, a.stype, a.asym, a.ne_comp, nullptr);
+}
+extern "C" bool ns_split_weight(const void* src, void* dst, size_t src_n, size_t src_k, size_t dst_n, size_t dst_k, size_t n_rank,
+                                size_t k_rank, bool qkv_fusion) {
+  BlobAttr a;
+  if (!src || !dst || !read_blob_attr(src, &a) || (size_t)a.n != src_n || (size_t)a.k != src_k) return false;
+  if ((n_rank + 1) * dst_n > src_n || (k_rank + 1) * dst_k > src_k || (qkv_fusion && (dst_n % 3 || src_n % 3))) return false;
+  std::vector<float> fp(src_n * src_k);
+  if (!BTLAGemmUnPackB(fp.data(), src, src_n, src_k, src_n, nullptr)) return false;
+  if (qkv_fusion) {
+    std::vector<float> part(dst_n * dst_k);
+    for (size_t i = 0; i < dst_k; ++i)
+      for (int j = 0; j < 3; ++j)
+        memcpy(part.data() + dst_n * i + j * dst_n / 3, fp.data() + src_n * (k_rank * dst_k + i) + j * src_n / 3 + n_rank * dst_n / 3,
+               dst_n / 3 * sizeof(float));
+    bestla_packweight_copyattr(part.data(), dst, (int)dst_n, (int)dst_k, (int)dst_n, const_cast<void*>(src));
+  } else {
+    bestla_packweight_copyattr(fp.data() + k_rank * dst_k * src_n + n_rank * dst_n, dst, (int)dst_n, (int)dst_k, (int)src_n,
+                               const_cast<void*>(src));
+  }
+  return true;
 }
 
 // quantize_row_q4_0_reference (vectors/cpu/quantize.h:243-279); x*id + 8.5f as one fma, as the reference's default

@@ -1,0 +1,85 @@
+"""Two-GPU tensor-parallel layer: shards from ns_split_weight, matmuls in libns_b200, NCCL sum all-reduce after o-proj and
+down-proj (llama.cpp:592,693).  Needs 2 GPUs (run with `gpurun --gpus 2`); skipped on a single-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import traceback
+    try:
+        import torch.distributed as dist
+        import neural_speed_b200 as ns
+        import oracle
+        from neural_speed_b200 import tp
+        torch.cuda.set_device(rank)
+        ns.lib().bestla_init()
+        ctx = tp.TPContext(backend="nccl")
+        n_embd, n_ff, n_head, g, m = 1024, 2048, 8, 128, 1
+        plan = tp.LlamaShardPlan(world, n_embd, n_ff, n_head, n_head, g)
+        dims = {"wq": (n_embd, n_embd), "wk": (n_embd, n_embd), "wv": (n_embd, n_embd), "wo": (n_embd, n_embd),
+                "w1": (n_ff, n_embd), "w3": (n_ff, n_embd), "w2": (n_embd, n_ff)}
+        full = {}
+        for i, (name, (nn, kk)) in enumerate(dims.items()):
+            w = np.random.default_rng(50 + i).uniform(-0.05, 0.05, (nn, kk)).astype(np.float32)
+            full[name] = ns.np_bestla_quantize(w, "int4", g, "sym", "fp32", "fp32")
+        sh = plan.shapes()
+        shards = {r: {name: tp.split_blob(full[name], *dims[name], world, r, sh[name][0]) for name in dims} for r in range(world)}
+        layer = {name: ns.Weight.from_blob(shards[rank][name]) for name in dims}
+        x = torch.from_numpy(np.random.default_rng(9).uniform(-0.5, 0.5, (m, n_embd)).astype(np.float32)).cuda()
+        eng = tp.TPLlamaMatmuls(plan, [layer], ctx)
+        out = eng.layer(0, x)
+        torch.cuda.synchronize()
+        ns.lib().bestla_device_sync(None)
+        # expectation from the dequantised shards (fp32 compute, tolerance 1e-3 as sycl_gemm.cpp:404-442)
+        xs = x.cpu().numpy()
+        dq = {r: {name: ns.unpack_blob(shards[r][name], sh[name][1], sh[name][2]) for name in dims} for r in range(world)}
+        o = sum(oracle.gemm_f64acc(oracle.gemm_f64acc(xs, dq[r]["wq"]), dq[r]["wo"]).astype(np.float64) for r in range(world))
+        h = (xs + o).astype(np.float32)
+
+        def mid(r):
+            gt = oracle.gemm_f64acc(h, dq[r]["w1"])
+            return (gt / (1 + np.exp(-gt)) * oracle.gemm_f64acc(h, dq[r]["w3"])).astype(np.float32)
+
+        dn = sum(oracle.gemm_f64acc(mid(r), dq[r]["w2"]).astype(np.float64) for r in range(world))
+        want = h + dn
+        err = float(np.abs(out.cpu().numpy() - want).max())
+        assert err <= 2e-3, err
+        gathered = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(gathered, out)
+        assert all(torch.equal(gathered[0], t) for t in gathered)   # every rank holds the same activation after the all-reduce
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+
+
+def test_two_gpu_tensor_parallel_layer():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
