@@ -231,6 +231,37 @@ NS_API int ns_device_quantize_q4_0(const float* src_dev, void* dst_dev, int n, i
 NS_API int ns_device_quantize_act(const float* act_dev, int lda, int m, int k, int group, int comp, void* q_dev,
                                   float* scale_dev, int* zp_dev, void* queue);
 
+/* ---- device-resident Llama-family eval step ----------------------------------------------------------
+ * Mirrors model_eval for the llama architecture (models/llama/llama.cpp:190-720): embedding lookup, RMSNorm, fused
+ * QKV / three matmuls (GQA), RoPE mode 0, fp16 KV cache, softmax attention, o-proj + residual, RMSNorm, SiLU FFN + residual,
+ * final RMSNorm, lm_head, greedy argmax (lowest index on ties, model_utils.cpp:2963-2985).  Weights are ns_weight handles
+ * (borrowed: they must outlive the context); norms and the embedding table are fp32 host arrays copied to the device.
+ * One-token evals replay one CUDA graph; ns_llama_generate feeds each argmax to the next step on the device. */
+typedef struct ns_llama ns_llama;
+typedef struct ns_llama_hparams {
+  int n_vocab, n_embd, n_head, n_head_kv, n_layer, n_ff, n_ctx;
+  float norm_eps;   /* hparams.norm_eps   (<= 0: 1e-6)  */
+  float rope_theta; /* hparams.freq_base  (<= 0: 10000) */
+  float rope_scale; /* hparams.freq_scale (<= 0: 1)     */
+} ns_llama_hparams;
+enum ns_llama_tensor {
+  NS_LT_TOK_EMBD = 0, /* others[0]  [n_vocab][n_embd] f32 */
+  NS_LT_OUT_NORM = 1, /* others[1]  [n_embd] f32          */
+  NS_LT_OUTPUT = 2,   /* others[2]  n_vocab x n_embd weight (any ns_weight format, incl. Q6_K) */
+  NS_LT_ATTN_NORM = 3, NS_LT_WQ = 4, NS_LT_WK = 5, NS_LT_WV = 6, NS_LT_WO = 7, /* layers[il].norm[0], attn[0..3] */
+  NS_LT_FFN_NORM = 8, NS_LT_W1 = 9, NS_LT_W2 = 10, NS_LT_W3 = 11               /* layers[il].norm[1], ffn[0..2]  */
+};
+NS_API ns_llama* ns_llama_create(const ns_llama_hparams* hp, void* queue);
+NS_API void ns_llama_free(ns_llama* ctx);
+NS_API int ns_llama_set_f32(ns_llama* ctx, int tensor, int layer, const float* host, size_t count);
+NS_API int ns_llama_set_weight(ns_llama* ctx, int tensor, int layer, const ns_weight* w);
+/* evaluate n_tokens new tokens after n_past cached ones; logits_host (nullable) gets the n_vocab logits of the LAST token,
+ * next_token (nullable) its greedy pick.  Synchronous (host buffers). */
+NS_API int ns_llama_eval(ns_llama* ctx, const int32_t* tokens, int n_tokens, int n_past, float* logits_host, int32_t* next_token);
+/* greedy generation of n_new tokens starting with first_token at position n_past; out_tokens[i] = pick after step i */
+NS_API int ns_llama_generate(ns_llama* ctx, int32_t first_token, int n_past, int n_new, int32_t* out_tokens);
+NS_API unsigned long long ns_llama_kv_bytes(const ns_llama* ctx);
+
 /* core/layers/bestla_gemm.h:37-56 (C++ in the reference; same names/argument meaning, extern "C" here).
  * QuantType/ScaleDtype are raw BTLA_DTYPE values, CompType an ne_comp_type.  ThreadPool is ignored. */
 NS_API size_t BTLAGemmPackBSize(size_t N, size_t K, size_t BlkSize, uint32_t QuantType, uint32_t ScaleDtype, bool isAsym,

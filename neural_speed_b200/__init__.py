@@ -55,6 +55,8 @@ EXPORTS = [
     "ns_prepare_activation", "ns_matmul_prepared", "ns_graph_begin", "ns_graph_end", "ns_graph_launch", "ns_graph_free",
     "ns_device_quantize_q4_0", "ns_device_quantize_act",
     "BTLAGemmPackBSize", "BTLAGemmQuantPackB", "BTLAGemmPackB", "BTLAGemmUnPackB", "ns_quantize_row_q4_0", "ns_split_weight_size", "ns_split_weight",
+    "ns_llama_create", "ns_llama_free", "ns_llama_set_f32", "ns_llama_set_weight", "ns_llama_eval", "ns_llama_generate",
+    "ns_llama_kv_bytes",
 ]
 
 _lib = None
@@ -160,6 +162,16 @@ def lib() -> C.CDLL:
     L.ns_graph_free.argtypes = [vp]
     L.ns_device_quantize_q4_0.argtypes = [vp, vp, i, i, vp]
     L.ns_device_quantize_act.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp]
+    L.ns_llama_create.restype = vp
+    L.ns_llama_create.argtypes = [vp, vp]
+    L.ns_llama_free.restype = None
+    L.ns_llama_free.argtypes = [vp]
+    L.ns_llama_set_f32.argtypes = [vp, i, i, vp, sz]
+    L.ns_llama_set_weight.argtypes = [vp, i, i, vp]
+    L.ns_llama_eval.argtypes = [vp, vp, i, i, vp, vp]
+    L.ns_llama_generate.argtypes = [vp, C.c_int32, i, i, vp]
+    L.ns_llama_kv_bytes.restype = C.c_ulonglong
+    L.ns_llama_kv_bytes.argtypes = [vp]
     L.ns_split_weight_size.restype = sz
     L.ns_split_weight_size.argtypes = [vp, sz, sz]
     L.ns_split_weight.restype = C.c_bool
@@ -353,6 +365,60 @@ def ffn_gelu(w1: Weight, w2: Weight, w3, b1_ptr, b2_ptr, bias_bcast: int, act_pt
     _check(lib().ns_ffn_gelu(w1.h, w2.h, w3.h if w3 is not None else None, C.c_void_p(b1_ptr) if b1_ptr else None,
                              C.c_void_p(b2_ptr) if b2_ptr else None, bias_bcast, C.c_void_p(act_ptr), lda, C.c_void_p(tmp_ptr),
                              C.c_void_p(dst_ptr), ldo, m, None, queue), "ns_ffn_gelu")
+
+
+class LlamaHParams(C.Structure):
+    _fields_ = [("n_vocab", C.c_int), ("n_embd", C.c_int), ("n_head", C.c_int), ("n_head_kv", C.c_int), ("n_layer", C.c_int),
+                ("n_ff", C.c_int), ("n_ctx", C.c_int), ("norm_eps", C.c_float), ("rope_theta", C.c_float), ("rope_scale", C.c_float)]
+
+
+class Llama:
+    """Device-resident Llama-family eval step (ns_llama_*): model_eval + greedy sampling of the reference, on the GPU."""
+
+    TOK_EMBD, OUT_NORM, OUTPUT, ATTN_NORM, WQ, WK, WV, WO, FFN_NORM, W1, W2, W3 = range(12)
+
+    def __init__(self, n_vocab, n_embd, n_head, n_head_kv, n_layer, n_ff, n_ctx, norm_eps=1e-6, rope_theta=10000.0, rope_scale=1.0,
+                 queue=None):
+        self.hp = LlamaHParams(n_vocab, n_embd, n_head, n_head_kv, n_layer, n_ff, n_ctx, norm_eps, rope_theta, rope_scale)
+        self.h = C.c_void_p(lib().ns_llama_create(C.byref(self.hp), queue))
+        if not self.h:
+            raise RuntimeError("ns_llama_create failed: " + last_error())
+        self._keep = []
+
+    def set_f32(self, tensor: int, layer: int, arr: np.ndarray):
+        a = np.ascontiguousarray(arr, np.float32)
+        _check(lib().ns_llama_set_f32(self.h, tensor, layer, _np_ptr(a), a.size), "ns_llama_set_f32")
+
+    def set_weight(self, tensor: int, layer: int, w: "Weight"):
+        self._keep.append(w)  # borrowed by the context
+        _check(lib().ns_llama_set_weight(self.h, tensor, layer, w.h), "ns_llama_set_weight")
+
+    def eval(self, tokens, n_past: int, want_logits=True):
+        t = np.ascontiguousarray(tokens, np.int32)
+        logits = np.empty(self.hp.n_vocab, np.float32) if want_logits else None
+        nxt = C.c_int32(0)
+        _check(lib().ns_llama_eval(self.h, _np_ptr(t), t.size, n_past, _np_ptr(logits) if want_logits else None, C.byref(nxt)),
+               "ns_llama_eval")
+        return logits, int(nxt.value)
+
+    def generate(self, first_token: int, n_past: int, n_new: int) -> np.ndarray:
+        out = np.empty(n_new, np.int32)
+        _check(lib().ns_llama_generate(self.h, first_token, n_past, n_new, _np_ptr(out)), "ns_llama_generate")
+        return out
+
+    def kv_bytes(self) -> int:
+        return int(lib().ns_llama_kv_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            lib().ns_llama_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Program:

@@ -623,7 +623,8 @@ extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_wei
 // w3 == NULL: tmp = gelu(x W1^T + b1), dst = tmp W2^T + b2 (GeLu / Add_GeLu, ip_fusion_ffn.cpp:755-779).
 // tmp: [2][m][fmid] floats when m > 4 and w3 is given (gate and up GEMM outputs; the product lands in the first half), else [m][fmid]
 static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, int eltop, const float* b1, const float* b2,
-                    int bcast, const float* act, int lda, float* tmp, float* dst, int ldo, int m, void* workspace, void* queue) {
+                    int bcast, const float* act, int lda, float* tmp, float* dst, int ldo, int m, void* workspace, void* queue,
+                    const float* residual = nullptr) {
   if (int rc = ns_ensure_device()) return rc;
   if (!w1 || !w2 || !act || !tmp || !dst || m <= 0 || w2->k != w1->n || (w3 && (w3->n != w1->n || w3->k != w1->k)) ||
       (w3 && (b1 || b2)) || (!w3 && eltop != NS_ELT_GELU)) {
@@ -649,7 +650,7 @@ static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w
       if (int rc = ns_launch_gelu(gate, (size_t)m * fmid, st)) return rc;
     }
     if (int rc = ns_launch_act_bf16(w2, gate, fmid, m, ws, st)) return rc;
-    return ns_launch_gemm_tc(w2, ws, dst, ldo, m, b2, bcast, nullptr, st);
+    return ns_launch_gemm_tc(w2, ws, dst, ldo, m, b2, bcast, residual, st);
   }
   const ns_weight* gu[2] = {w1, w3};
   int tile = ns_gemv_tile_rows(w1);
@@ -677,11 +678,17 @@ static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w
     if (!fused2)
       if (int rc = ns_launch_act_prep(a, fmid, mt, w2, ws, st)) return rc;
     if (int rc = ns_launch_gemv(&w2, 1, NS_GEMV_PLAIN, fused2 ? nullptr : ws, dst + (size_t)m0 * ldo, ldo, mt, m,
-                                b2 ? (bcast ? b2 : b2 + (size_t)m0 * ldo) : nullptr, bcast, nullptr, nullptr, st,
-                                fused2 ? a : nullptr, fmid))
+                                b2 ? (bcast ? b2 : b2 + (size_t)m0 * ldo) : nullptr, bcast,
+                                residual ? residual + (size_t)m0 * ldo : nullptr, nullptr, st, fused2 ? a : nullptr, fmid))
       return rc;
   }
   return NS_OK;
+}
+// dst = residual + FFN_SiLU(act): the decode engine's "cur = ne_add(ffn, inpFF)" (llama.cpp:698) folded into the down GEMV
+int ns_ffn_silu_residual(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda, float* tmp,
+                         float* dst, int ldo, int m, const float* residual, void* workspace, cudaStream_t st) {
+  if (!w3) return NS_E_INVALID;
+  return ffn_impl(w1, w2, w3, NS_ELT_DEFAULT, nullptr, nullptr, 0, act, lda, tmp, dst, ldo, m, workspace, (void*)st, residual);
 }
 extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda,
                            float* tmp, float* dst, int ldo, int m, void* workspace, void* queue) {

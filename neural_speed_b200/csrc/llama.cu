@@ -1,0 +1,551 @@
+// llama.cu -- device-resident decode/prefill step around the weight-only matmuls.
+//
+// Mirrors the Llama-family eval graph of the reference, models/llama/llama.cpp:190-720 (model_eval_internal):
+//   inpL = get_rows(tok_embeddings, tokens)                                    :190
+//   per layer: cur = rms_norm(inpL) * attn_norm                                :205-210
+//              Q,K,V = mul_qkv / mul_mat                                       :212-240
+//              rope(Q), rope(K) at position n_past + t (mode 0, pairs (2i,2i+1)) :351-355, ne_layers.c:9380-9396
+//              K,V -> fp16 KV cache; attention = softmax(K Q / sqrt(hd)) V      :362-420 / :286-302 (ggml path)
+//              inpFF = wo * attn + inpSA                                       :585-598
+//              cur = rms_norm(inpFF) * ffn_norm ; cur = ffn_silu(cur) + inpFF  :601-698
+//   logits = output * (rms_norm(inpL) * out_norm)                              :707-719
+// Greedy sampling = argmax with the lowest index on ties (model_utils.cpp:2963-2985).
+//
+// One token (n_tokens == 1) is ONE CUDA graph: the token id and n_past live in device memory (`state`), so the same graph
+// replays for every position; ns_llama_generate chains graph launches with the argmax feeding the next embedding
+// lookup on the device -- no host round trip per token.
+//
+// Element-wise numerics follow the reference's ggml path: fp16 KV cache, Q and the softmax probabilities rounded to fp16
+// before the K.Q and V.P dot products (ne_compute_forward_mul_mat_f16_f32), exp taken on the fp16-rounded argument and
+// rounded to fp16 (table_exp_f16, ne_layers.c:8933-8937); rms_norm as kernel_ref.h:2199-2225.
+#include <cuda_fp16.h>
+
+#include <vector>
+
+#include "nsb.cuh"
+
+namespace {
+
+struct Layer {
+  const float* attn_norm = nullptr;
+  const float* ffn_norm = nullptr;
+  const ns_weight *wq = nullptr, *wk = nullptr, *wv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr, *w3 = nullptr;
+};
+
+constexpr int kAttnThreads = 128;
+
+// x[t][:] = table[token[t]][:]
+__global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ table, const int* __restrict__ tokens, int n_embd,
+                                                    int n_vocab, float* __restrict__ x) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = blockIdx.y;
+  int tok = tokens[t];
+  tok = tok < 0 ? 0 : (tok >= n_vocab ? n_vocab - 1 : tok);
+  const float4* src = (const float4*)(table + (size_t)tok * n_embd);
+  float4* dst = (float4*)(x + (size_t)t * n_embd);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_embd / 4; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// y = x / sqrt(mean(x^2) + eps) * w      (ne_rms_norm + ne_mul; kernel_ref.h:2199-2225 "simplified")
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+                                                      int n, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float* xr = x + (size_t)blockIdx.x * n;
+  float* yr = y + (size_t)blockIdx.x * n;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) ss = fmaf(xr[i], xr[i], ss);
+  __shared__ float red[8];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float inv = 1.f / sqrtf(tot / (float)n + eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) yr[i] = xr[i] * inv * w[i];
+}
+
+// rope (mode 0) on q and k of every new token + append k,v to the fp16 cache.
+// grid (n_head + n_head_kv, n_tokens), hd/2 threads.  pos = state[1] + t.
+__global__ void rope_kv_kernel(float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
+                               __half* __restrict__ kc, __half* __restrict__ vc, const int* __restrict__ state, int n_head, int n_head_kv,
+                               int hd, int n_ctx, float theta_scale, float freq_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int h = blockIdx.x, t = blockIdx.y, i = threadIdx.x;  // pair index
+  const int pos = state[1] + t;
+  // theta_base = p; repeated `theta_base *= theta_scale` (ne_layers.c:9321,9385): keep the same sequence of roundings
+  float theta = (float)pos;
+  for (int j = 0; j < i; ++j) theta *= theta_scale;
+  theta *= freq_scale;
+  float sn, cs;
+  sincosf(theta, &sn, &cs);
+  if (h < n_head) {
+    float* p = q + (size_t)t * ldq + (size_t)h * hd + 2 * i;
+    const float x0 = p[0], x1 = p[1];
+    p[0] = x0 * cs - x1 * sn;
+    p[1] = x0 * sn + x1 * cs;
+  } else {
+    const int hk = h - n_head;
+    const float* p = k + (size_t)t * ldk + (size_t)hk * hd + 2 * i;
+    const float x0 = p[0], x1 = p[1];
+    if (pos < n_ctx) {
+      __half* kd = kc + ((size_t)hk * n_ctx + pos) * hd + 2 * i;
+      kd[0] = __float2half_rn(x0 * cs - x1 * sn);
+      kd[1] = __float2half_rn(x0 * sn + x1 * cs);
+      const float* pv = v + (size_t)t * ldv + (size_t)hk * hd + 2 * i;
+      __half* vd = vc + ((size_t)hk * n_ctx + pos) * hd + 2 * i;
+      vd[0] = __float2half_rn(pv[0]);
+      vd[1] = __float2half_rn(pv[1]);
+    }
+  }
+}
+
+// one CTA per (head, new token): two-pass softmax over positions 0 .. state[1] + t, scores in shared memory.
+// out[t][h*hd + d] = sum_i fp16(p_i) * V[i][d]
+__global__ void __launch_bounds__(kAttnThreads) attn_kernel(const float* __restrict__ q, int ldq, const __half* __restrict__ kc,
+                                                            const __half* __restrict__ vc, const int* __restrict__ state, float* __restrict__ out,
+                                                            int ldo, int n_head, int n_head_kv, int hd, int n_ctx, float scale) {
+  extern __shared__ float sm[];  // [hd] q (fp16-rounded) | [n_ctx] scores
+  pdl_launch_dependents();
+  pdl_wait();
+  const int h = blockIdx.x, t = blockIdx.y;
+  const int hk = h / (n_head / n_head_kv);
+  int len = state[1] + t + 1;
+  len = len > n_ctx ? n_ctx : len;
+  float* sq = sm;
+  float* sc = sm + hd;
+  const float* qr = q + (size_t)t * ldq + (size_t)h * hd;
+  for (int d = threadIdx.x; d < hd; d += blockDim.x) sq[d] = __half2float(__float2half_rn(qr[d]));
+  __syncthreads();
+  const __half* kh = kc + (size_t)hk * n_ctx * hd;
+  const __half* vh = vc + (size_t)hk * n_ctx * hd;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // pass 1: scores (one warp per position)
+  float lmax = -INFINITY;
+  for (int i = warp; i < len; i += nw) {
+    const __half2* kr = (const __half2*)(kh + (size_t)i * hd);
+    float acc = 0.f;
+    for (int d2 = lane; d2 < hd / 2; d2 += 32) {
+      const float2 kv = __half22float2(kr[d2]);
+      acc = fmaf(sq[2 * d2], kv.x, acc);
+      acc = fmaf(sq[2 * d2 + 1], kv.y, acc);
+    }
+    acc = warp_sum(acc) * scale;
+    if (lane == 0) sc[i] = acc;
+    lmax = fmaxf(lmax, acc);
+  }
+  __shared__ float red[kAttnThreads / 32];
+  __shared__ float bcast;
+  if (lane == 0) red[warp] = lmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+    bcast = m;
+  }
+  __syncthreads();
+  const float mx = bcast;
+  // exp on the fp16-rounded argument, result rounded to fp16 (table_exp_f16), sum in fp32
+  float lsum = 0.f;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const float a = __half2float(__float2half_rn(sc[i] - mx));
+    const float e = __half2float(__float2half_rn(expf(a)));
+    sc[i] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  __syncthreads();
+  if (lane == 0) red[warp] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < nw; ++i) s += red[i];
+    bcast = 1.f / s;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  // pass 2: thread d accumulates sum_i fp16(p_i) * V[i][d]
+  for (int d = threadIdx.x; d < hd; d += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < len; ++i) {
+      const float p = __half2float(__float2half_rn(sc[i] * inv));
+      acc = fmaf(p, __half2float(vh[(size_t)i * hd + d]), acc);
+    }
+    out[(size_t)t * ldo + (size_t)h * hd + d] = acc;
+  }
+}
+
+// greedy pick: index of the maximum, lowest index on ties; also advances the device-side position.
+// state[0] = next token, state[1] += n_tokens (only when `advance`), out_tokens[state[2]++] = next token when recording
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int n, int* __restrict__ state, int n_tokens,
+                                                      int advance, int* __restrict__ record) {
+  pdl_launch_dependents();
+  pdl_wait();
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = logits[i];
+    if (v > best || (v == best && i < bi)) {
+      best = v;
+      bi = i;
+    }
+  }
+  __shared__ float sv[32];
+  __shared__ int si[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sv[threadIdx.x >> 5] = best;
+    si[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) {
+        best = sv[w];
+        bi = si[w];
+      }
+    if (bi == 0x7fffffff) bi = 0;  // all NaN / -inf: the reference's loop keeps index 0
+    state[3] = bi;
+    if (advance) {
+      state[0] = bi;
+      state[1] += n_tokens;
+      if (record) record[state[2]++] = bi;
+    }
+  }
+}
+
+}  // namespace
+
+struct ns_llama {
+  ns_llama_hparams hp;
+  cudaStream_t st;
+  std::vector<Layer> layers;
+  float* tok_embd = nullptr;
+  float* out_norm = nullptr;
+  const ns_weight* output = nullptr;
+  std::vector<void*> owned;  // device allocations freed with the context
+  __half *kc = nullptr, *vc = nullptr;
+  int* state = nullptr;   // device: {token, n_past, n_recorded, last_pick}
+  int* tokens = nullptr;  // device: prompt tokens of the current eval
+  int* record = nullptr;  // device: generated tokens
+  int m_cap = 0;
+  float *x = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *tmp = nullptr, *logits = nullptr;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  cudaGraphExec_t decode_exec = nullptr;
+  cudaGraph_t decode_graph = nullptr;
+  int* h_state = nullptr;  // pinned host staging
+  float* h_logits = nullptr;
+};
+
+static void* dev_alloc(ns_llama* c, size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    ns_set_error("ns_llama: cudaMalloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  c->owned.push_back(p);
+  return p;
+}
+
+extern "C" ns_llama* ns_llama_create(const ns_llama_hparams* hp, void* queue) {
+  if (ns_ensure_device()) return nullptr;
+  if (!hp || hp->n_vocab <= 0 || hp->n_embd <= 0 || hp->n_head <= 0 || hp->n_head_kv <= 0 || hp->n_layer <= 0 || hp->n_ff <= 0 ||
+      hp->n_ctx <= 0 || hp->n_embd % hp->n_head || hp->n_head % hp->n_head_kv || (hp->n_embd / hp->n_head) % 2 || hp->n_embd % 4) {
+    ns_set_error("ns_llama_create: invalid hyper-parameters");
+    return nullptr;
+  }
+  ns_llama* c = new ns_llama();
+  c->hp = *hp;
+  if (c->hp.rope_theta <= 0.f) c->hp.rope_theta = 10000.f;
+  if (c->hp.rope_scale <= 0.f) c->hp.rope_scale = 1.f;
+  if (c->hp.norm_eps <= 0.f) c->hp.norm_eps = 1e-6f;
+  c->st = ns_stream_of(queue);
+  c->layers.resize(hp->n_layer);
+  const int hd = hp->n_embd / hp->n_head;
+  const size_t kv_elems = (size_t)hp->n_layer * hp->n_head_kv * hp->n_ctx * hd;
+  c->kc = (__half*)dev_alloc(c, kv_elems * 2);
+  c->vc = (__half*)dev_alloc(c, kv_elems * 2);
+  c->state = (int*)dev_alloc(c, 4 * sizeof(int));
+  c->tokens = (int*)dev_alloc(c, (size_t)hp->n_ctx * sizeof(int));
+  c->record = (int*)dev_alloc(c, (size_t)hp->n_ctx * sizeof(int));
+  c->logits = (float*)dev_alloc(c, (size_t)hp->n_vocab * 4);
+  if (!c->kc || !c->vc || !c->state || !c->tokens || !c->record || !c->logits ||
+      cudaMallocHost((void**)&c->h_state, 4 * sizeof(int)) != cudaSuccess ||
+      cudaMallocHost((void**)&c->h_logits, (size_t)hp->n_vocab * 4) != cudaSuccess) {
+    ns_llama_free(c);
+    return nullptr;
+  }
+  cudaMemsetAsync(c->kc, 0, kv_elems * 2, c->st);
+  cudaMemsetAsync(c->vc, 0, kv_elems * 2, c->st);
+  cudaMemsetAsync(c->state, 0, 4 * sizeof(int), c->st);
+  return c;
+}
+
+extern "C" void ns_llama_free(ns_llama* c) {
+  if (!c) return;
+  cudaStreamSynchronize(c->st);
+  if (c->decode_exec) cudaGraphExecDestroy(c->decode_exec);
+  if (c->decode_graph) cudaGraphDestroy(c->decode_graph);
+  for (void* p : c->owned) cudaFree(p);
+  if (c->h_state) cudaFreeHost(c->h_state);
+  if (c->h_logits) cudaFreeHost(c->h_logits);
+  delete c;
+}
+
+extern "C" int ns_llama_set_f32(ns_llama* c, int tensor, int layer, const float* host, size_t count) {
+  if (!c || !host) return NS_E_INVALID;
+  const ns_llama_hparams& hp = c->hp;
+  size_t want = 0;
+  if (tensor == NS_LT_TOK_EMBD) want = (size_t)hp.n_vocab * hp.n_embd;
+  else if (tensor == NS_LT_OUT_NORM || tensor == NS_LT_ATTN_NORM || tensor == NS_LT_FFN_NORM) want = hp.n_embd;
+  if (!want || count != want || ((tensor == NS_LT_ATTN_NORM || tensor == NS_LT_FFN_NORM) && (layer < 0 || layer >= hp.n_layer))) {
+    ns_set_error("ns_llama_set_f32: tensor %d layer %d count %zu", tensor, layer, count);
+    return NS_E_INVALID;
+  }
+  float* d = (float*)dev_alloc(c, want * 4);
+  if (!d) return NS_E_CUDA;
+  NS_CUDA_TRY(cudaMemcpyAsync(d, host, want * 4, cudaMemcpyHostToDevice, c->st));
+  NS_CUDA_TRY(cudaStreamSynchronize(c->st));
+  if (tensor == NS_LT_TOK_EMBD) c->tok_embd = d;
+  else if (tensor == NS_LT_OUT_NORM) c->out_norm = d;
+  else if (tensor == NS_LT_ATTN_NORM) c->layers[layer].attn_norm = d;
+  else c->layers[layer].ffn_norm = d;
+  return NS_OK;
+}
+
+extern "C" int ns_llama_set_weight(ns_llama* c, int tensor, int layer, const ns_weight* w) {
+  if (!c || !w) return NS_E_INVALID;
+  const ns_llama_hparams& hp = c->hp;
+  const int hd = hp.n_embd / hp.n_head, kvd = hd * hp.n_head_kv;
+  int n = 0, k = hp.n_embd;
+  switch (tensor) {
+    case NS_LT_OUTPUT: n = hp.n_vocab; break;
+    case NS_LT_WQ: n = hp.n_embd; break;
+    case NS_LT_WK: case NS_LT_WV: n = kvd; break;
+    case NS_LT_WO: n = hp.n_embd; break;
+    case NS_LT_W1: case NS_LT_W3: n = hp.n_ff; break;
+    case NS_LT_W2: n = hp.n_embd; k = hp.n_ff; break;
+    default: n = 0;
+  }
+  if (!n || w->n != n || w->k != k || (tensor != NS_LT_OUTPUT && (layer < 0 || layer >= hp.n_layer))) {
+    ns_set_error("ns_llama_set_weight: tensor %d layer %d wants %dx%d, got %dx%d", tensor, layer, n, k, w->n, w->k);
+    return NS_E_INVALID;
+  }
+  if (tensor == NS_LT_OUTPUT) {
+    c->output = w;
+  } else {
+    Layer& l = c->layers[layer];
+    const ns_weight** slot = tensor == NS_LT_WQ ? &l.wq : tensor == NS_LT_WK ? &l.wk : tensor == NS_LT_WV ? &l.wv
+                           : tensor == NS_LT_WO ? &l.wo : tensor == NS_LT_W1 ? &l.w1 : tensor == NS_LT_W2 ? &l.w2 : &l.w3;
+    *slot = w;
+  }
+  if (c->decode_exec) {  // weights changed: the captured graph holds stale pointers
+    cudaGraphExecDestroy(c->decode_exec);
+    cudaGraphDestroy(c->decode_graph);
+    c->decode_exec = nullptr;
+    c->decode_graph = nullptr;
+  }
+  return NS_OK;
+}
+
+static int ensure_buffers(ns_llama* c, int m) {
+  if (m <= c->m_cap) return NS_OK;
+  const ns_llama_hparams& hp = c->hp;
+  const int hd = hp.n_embd / hp.n_head, kvd = hd * hp.n_head_kv;
+  c->x = (float*)dev_alloc(c, (size_t)m * hp.n_embd * 4);
+  c->xn = (float*)dev_alloc(c, (size_t)m * hp.n_embd * 4);
+  c->qkv = (float*)dev_alloc(c, (size_t)m * (hp.n_embd + 2 * kvd) * 4);
+  c->attn = (float*)dev_alloc(c, (size_t)m * hp.n_embd * 4);
+  c->tmp = (float*)dev_alloc(c, (size_t)2 * m * hp.n_ff * 4);
+  const int kmax = hp.n_ff > hp.n_embd ? hp.n_ff : hp.n_embd;
+  size_t wsb = ns_act_workspace_bytes(4, (int)ns_round_up((size_t)kmax, 32));
+  const size_t tcb = ns_gemm_tc_workspace_bytes(m, (int)ns_round_up((size_t)kmax, 32));
+  const size_t q6 = ns_q6k_workspace_bytes(4, kmax);
+  wsb = wsb > tcb ? wsb : tcb;
+  wsb = wsb > q6 ? wsb : q6;
+  c->ws = dev_alloc(c, wsb);
+  c->ws_bytes = wsb;
+  if (!c->x || !c->xn || !c->qkv || !c->attn || !c->tmp || !c->ws) return NS_E_CUDA;
+  c->m_cap = m;
+  if (c->decode_exec) {
+    cudaGraphExecDestroy(c->decode_exec);
+    cudaGraphDestroy(c->decode_graph);
+    c->decode_exec = nullptr;
+    c->decode_graph = nullptr;
+  }
+  return NS_OK;
+}
+
+static int check_complete(const ns_llama* c) {
+  if (!c->tok_embd || !c->out_norm || !c->output) {
+    ns_set_error("ns_llama: tok_embeddings / output norm / output weight not set");
+    return NS_E_INVALID;
+  }
+  for (size_t i = 0; i < c->layers.size(); ++i) {
+    const Layer& l = c->layers[i];
+    if (!l.attn_norm || !l.ffn_norm || !l.wq || !l.wk || !l.wv || !l.wo || !l.w1 || !l.w2 || !l.w3) {
+      ns_set_error("ns_llama: layer %zu is missing tensors", i);
+      return NS_E_INVALID;
+    }
+  }
+  return NS_OK;
+}
+
+// enqueue the whole forward pass for m new tokens (ids in c->tokens[0..m) or, when from_state, the single id in
+// state[0]); position base = state[1].  Leaves logits of the LAST token in c->logits and the greedy pick in state[3].
+static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int* record) {
+  const ns_llama_hparams& hp = c->hp;
+  cudaStream_t st = c->st;
+  const int E = hp.n_embd, hd = E / hp.n_head, kvd = hd * hp.n_head_kv, FF = hp.n_ff;
+  const float theta_scale = powf(hp.rope_theta, -2.0f / (float)hd);  // n_rot == head_size (llama.cpp:131)
+  const float freq_scale = 1.f / hp.rope_scale;
+  const float attn_scale = 1.0f / sqrtf((float)hd);
+  float* q = c->qkv;
+  float* k = q + (size_t)m * E;
+  float* v = k + (size_t)m * kvd;
+  NS_CUDA_TRY(ns_launch_pdl(embed_kernel, dim3((unsigned)((E / 4 + 255) / 256), (unsigned)m), dim3(256), 0, st, (const float*)c->tok_embd,
+                            (const int*)(from_state ? c->state : c->tokens), E, hp.n_vocab, c->x));
+  ns_count_launch();
+  const size_t attn_smem = (size_t)(hd + hp.n_ctx) * sizeof(float);
+  static size_t attn_attr = 0;
+  if (attn_smem > 48 * 1024 && attn_smem > attn_attr) {
+    if (attn_smem > 220 * 1024) {
+      ns_set_error("ns_llama: n_ctx %d too large for the single-pass attention kernel", hp.n_ctx);
+      return NS_E_UNSUPPORTED;
+    }
+    NS_CUDA_TRY(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
+    attn_attr = attn_smem;
+  }
+  for (int il = 0; il < hp.n_layer; ++il) {
+    const Layer& L = c->layers[il];
+    __half* kc = c->kc + (size_t)il * hp.n_head_kv * hp.n_ctx * hd;
+    __half* vc = c->vc + (size_t)il * hp.n_head_kv * hp.n_ctx * hd;
+    NS_CUDA_TRY(ns_launch_pdl(rmsnorm_kernel, dim3((unsigned)m), dim3(256), 0, st, (const float*)c->x, L.attn_norm, c->xn, E, hp.norm_eps));
+    ns_count_launch();
+    bool fused = false;
+    if (hp.n_head == hp.n_head_kv) {  // fused QKV node (llama.cpp:212-215); dst = [3][m][E] = q | k | v
+      fused = ns_mul_qkv(L.wq, L.wk, L.wv, c->xn, E, q, E, m, c->ws, (void*)st) == NS_OK;
+    }
+    if (!fused) {
+      if (int rc = ns_mul_mat(L.wq, c->xn, E, q, E, m, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
+      if (int rc = ns_mul_mat(L.wk, c->xn, E, k, kvd, m, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
+      if (int rc = ns_mul_mat(L.wv, c->xn, E, v, kvd, m, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
+    }
+    NS_CUDA_TRY(ns_launch_pdl(rope_kv_kernel, dim3((unsigned)(hp.n_head + hp.n_head_kv), (unsigned)m), dim3((unsigned)(hd / 2)), 0, st, q, E,
+                              (const float*)k, kvd, (const float*)v, kvd, kc, vc, (const int*)c->state, hp.n_head, hp.n_head_kv, hd,
+                              hp.n_ctx, theta_scale, freq_scale));
+    ns_count_launch();
+    NS_CUDA_TRY(ns_launch_pdl(attn_kernel, dim3((unsigned)hp.n_head, (unsigned)m), dim3(kAttnThreads), attn_smem, st, (const float*)q, E,
+                              (const __half*)kc, (const __half*)vc, (const int*)c->state, c->attn, E, hp.n_head, hp.n_head_kv, hd,
+                              hp.n_ctx, attn_scale));
+    ns_count_launch();
+    // inpFF = wo * attn + inpSA, written over x (every row is read by its own output only after the matmul finished)
+    if (int rc = ns_mul_mat(L.wo, c->attn, E, c->xn, E, m, nullptr, c->x, 0, c->ws, (void*)st)) return rc;
+    // xn now holds inpFF; normalise it into attn (free again), FFN + residual back into x
+    NS_CUDA_TRY(ns_launch_pdl(rmsnorm_kernel, dim3((unsigned)m), dim3(256), 0, st, (const float*)c->xn, L.ffn_norm, c->attn, E, hp.norm_eps));
+    ns_count_launch();
+    if (int rc = ns_ffn_silu_residual(L.w1, L.w2, L.w3, c->attn, E, c->tmp, c->x, E, m, c->xn, c->ws, st)) return rc;
+  }
+  // logits of the last token only (model_eval keeps the last row unless logits_all)
+  NS_CUDA_TRY(ns_launch_pdl(rmsnorm_kernel, dim3(1u), dim3(256), 0, st, (const float*)(c->x + (size_t)(m - 1) * E), (const float*)c->out_norm,
+                            c->xn, E, hp.norm_eps));
+  ns_count_launch();
+  if (int rc = ns_mul_mat(c->output, c->xn, E, c->logits, hp.n_vocab, 1, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
+  NS_CUDA_TRY(ns_launch_pdl(argmax_kernel, dim3(1u), dim3(1024), 0, st, (const float*)c->logits, hp.n_vocab, c->state, m, advance, record));
+  ns_count_launch();
+  return NS_OK;
+}
+
+static int ensure_decode_graph(ns_llama* c) {
+  if (c->decode_exec) return NS_OK;
+  // one eager pass (no state advance; it writes the same K/V the real pass will) sets kernel attributes and sizes every
+  // lazily-grown buffer outside the capture, then capture
+  if (int rc = enqueue_forward(c, 1, true, 0, nullptr)) return rc;
+  NS_CUDA_TRY(cudaStreamSynchronize(c->st));
+  NS_CUDA_TRY(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_forward(c, 1, true, 1, c->record);
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(c->st, &g);
+  if (rc) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  if (!ns_cuda_ok(e, "cudaStreamEndCapture") || !g) return NS_E_CUDA;
+  if (!ns_cuda_ok(cudaGraphInstantiate(&c->decode_exec, g, 0), "cudaGraphInstantiate")) {
+    cudaGraphDestroy(g);
+    return NS_E_CUDA;
+  }
+  c->decode_graph = g;
+  return NS_OK;
+}
+
+// model_eval (models/model_utils/model_utils.h): evaluate n_tokens new tokens after n_past cached ones.
+// logits_host (nullable): n_vocab floats of the LAST token; next_token (nullable): its greedy pick.
+extern "C" int ns_llama_eval(ns_llama* c, const int32_t* tokens, int n_tokens, int n_past, float* logits_host, int32_t* next_token) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!c || !tokens || n_tokens <= 0 || n_past < 0 || n_past + n_tokens > c->hp.n_ctx) {
+    ns_set_error("ns_llama_eval: invalid arguments (n_tokens=%d n_past=%d n_ctx=%d)", n_tokens, n_past, c ? c->hp.n_ctx : 0);
+    return NS_E_INVALID;
+  }
+  if (int rc = check_complete(c)) return rc;
+  if (int rc = ensure_buffers(c, n_tokens)) return rc;
+  cudaStream_t st = c->st;
+  c->h_state[0] = tokens[0];
+  c->h_state[1] = n_past;
+  c->h_state[2] = 0;
+  c->h_state[3] = 0;
+  NS_CUDA_TRY(cudaMemcpyAsync(c->state, c->h_state, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (n_tokens == 1) {
+    if (int rc = ensure_decode_graph(c)) return rc;
+    NS_CUDA_TRY(cudaGraphLaunch(c->decode_exec, st));
+  } else {
+    NS_CUDA_TRY(cudaMemcpyAsync(c->tokens, tokens, (size_t)n_tokens * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (int rc = enqueue_forward(c, n_tokens, false, 1, nullptr)) return rc;
+  }
+  if (logits_host) NS_CUDA_TRY(cudaMemcpyAsync(c->h_logits, c->logits, (size_t)c->hp.n_vocab * 4, cudaMemcpyDeviceToHost, st));
+  NS_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->state, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  NS_CUDA_TRY(cudaStreamSynchronize(st));
+  if (logits_host) memcpy(logits_host, c->h_logits, (size_t)c->hp.n_vocab * 4);
+  if (next_token) *next_token = c->h_state[3];
+  return NS_OK;
+}
+
+// greedy generation: token `first` at position n_past, then n_new - 1 more, each fed from the previous argmax on the
+// device (one graph launch per token, no host synchronisation in between).  out_tokens[i] = pick after step i.
+extern "C" int ns_llama_generate(ns_llama* c, int32_t first_token, int n_past, int n_new, int32_t* out_tokens) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!c || !out_tokens || n_new <= 0 || n_past < 0 || n_past + n_new > c->hp.n_ctx) {
+    ns_set_error("ns_llama_generate: invalid arguments (n_past=%d n_new=%d n_ctx=%d)", n_past, n_new, c ? c->hp.n_ctx : 0);
+    return NS_E_INVALID;
+  }
+  if (int rc = check_complete(c)) return rc;
+  if (int rc = ensure_buffers(c, 1)) return rc;
+  if (int rc = ensure_decode_graph(c)) return rc;
+  cudaStream_t st = c->st;
+  c->h_state[0] = first_token;
+  c->h_state[1] = n_past;
+  c->h_state[2] = 0;
+  c->h_state[3] = 0;
+  NS_CUDA_TRY(cudaMemcpyAsync(c->state, c->h_state, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < n_new; ++i) NS_CUDA_TRY(cudaGraphLaunch(c->decode_exec, st));
+  NS_CUDA_TRY(cudaMemcpyAsync(out_tokens, c->record, (size_t)n_new * sizeof(int), cudaMemcpyDeviceToHost, st));
+  NS_CUDA_TRY(cudaStreamSynchronize(st));
+  return NS_OK;
+}
+
+extern "C" unsigned long long ns_llama_kv_bytes(const ns_llama* c) {
+  if (!c) return 0;
+  return (unsigned long long)2 * c->hp.n_layer * c->hp.n_head_kv * c->hp.n_ctx * (c->hp.n_embd / c->hp.n_head) * 2;
+}

@@ -92,6 +92,10 @@ int ns_launch_dequant_q6k(const ns_weight* w, float* dst, int ld, cudaStream_t s
 int ns_launch_mul_mat_q6k(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* bias,
                           int bias_bcast, const float* residual, void* ws, cudaStream_t st);
 
+// abi.cu: fused FFN with the residual add folded into the down projection (used by the decode engine, llama.cu)
+int ns_ffn_silu_residual(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda, float* tmp,
+                         float* dst, int ldo, int m, const float* residual, void* workspace, cudaStream_t st);
+
 // tensor-core path (gemm_tc.cu)
 size_t ns_gemm_tc_workspace_bytes(int m, int kpad);
 bool ns_gemm_tc_supported(const ns_weight* w);
