@@ -404,6 +404,56 @@ def run_ours(args):
         del xp, ap_, qkvp, op_, tmpp, ffnp, wsp_t
         torch.cuda.empty_cache()
 
+    # ---- whole decode step: ns_llama_* (embedding, RMSNorm, RoPE, fp16 KV cache, attention, residuals, argmax around the
+    # same matmuls), greedy generation with the argmax fed back on the device; one host call for the whole run
+    engine = None
+    if not args.skip_engine and n_layers == N_LAYER:
+        n_ctx, n_prompt, n_new = 1024, 32, args.gen_tokens
+        eng = ns.Llama(N_VOCAB, N_EMBD, 32, 32, n_layers, N_FF, n_ctx, 1e-5, 10000.0, 1.0, queue)
+        emb = (torch.randn(N_VOCAB, N_EMBD) * 1.0).numpy()
+        eng.set_f32(ns.Llama.TOK_EMBD, 0, emb)
+        del emb
+        ones = np.ones(N_EMBD, np.float32)
+        eng.set_f32(ns.Llama.OUT_NORM, 0, ones)
+        eng.set_weight(ns.Llama.OUTPUT, 0, lm_head)
+        ids = dict(wq=ns.Llama.WQ, wk=ns.Llama.WK, wv=ns.Llama.WV, wo=ns.Llama.WO, w1=ns.Llama.W1, w2=ns.Llama.W2, w3=ns.Llama.W3)
+        for il, lay in enumerate(layers):
+            eng.set_f32(ns.Llama.ATTN_NORM, il, ones)
+            eng.set_f32(ns.Llama.FFN_NORM, il, ones)
+            for name, w in lay.items():
+                eng.set_weight(ids[name], il, w)
+        prompt = np.random.default_rng(3).integers(3, N_VOCAB, n_prompt).astype(np.int32)
+        prompt[0] = 1  # BOS
+        t0 = time.perf_counter()
+        _, nxt = eng.eval(prompt, 0, want_logits=False)
+        t_prompt = time.perf_counter() - t0
+        eng.generate(int(nxt), n_prompt, 8)  # warm-up: builds the decode graph
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        lcg = L.ns_launch_count()
+        t0 = time.perf_counter()
+        toks = eng.generate(int(nxt), n_prompt, n_new)
+        dt_gen = time.perf_counter() - t0
+        launches_tok = (L.ns_launch_count() - lcg)  # graph replays do not count; kept for reference
+        t0 = time.perf_counter()
+        eng.eval(prompt, 0, want_logits=False)
+        t_prompt2 = time.perf_counter() - t0
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([dt_gen], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_gen = float(t.item())
+        engine = {"tokens_per_s": world * n_new / dt_gen, "ms_per_token": dt_gen / n_new * 1e3, "new_tokens": n_new,
+                  "prompt_tokens": n_prompt, "n_ctx": n_ctx, "prompt_eval_ms": t_prompt2 * 1e3, "first_prompt_eval_ms": t_prompt * 1e3,
+                  "kv_cache_bytes": eng.kv_bytes(), "distinct_tokens": int(len(set(int(v) for v in toks))),
+                  "timer": "host wall clock around ns_llama_generate (H2D first token, one CUDA graph per token, D2H token ids)",
+                  "roofline_frac": (alg_bytes * n_new / dt_gen / 1e9) / hbm_peak,
+                  "path": "ns_llama_generate: greedy, argmax fed back on device"}
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+
     # ---- e2e (headline): the token through the device-backend C-ABI of INTEGRATION.md B -- what ne_device_sync does in the
     # reference's NS_SYCL slot: the token's fp32 hidden state comes from pinned HOST memory (bestla_device_memcpy H2D), the
     # matmul nodes run device-resident (one ns_graph_launch), the fp32 logits go back to pinned HOST memory (D2H), then
@@ -517,7 +567,7 @@ def run_ours(args):
                                               "launches": n_gemv}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step, "clocks": clocks, "setup_s": setup_s,
-            "prefill": prefill,
+            "prefill": prefill, "decode_engine": engine,
             "persistent_program": {"tokens_per_s": world * 1000.0 / ms_prog, "ms_per_step": ms_prog, "launches_per_step": 1,
                                    "frac": prog_gbs / hbm_peak,
                                    "note": "same matmuls as ONE cooperative launch (ns_program, grid barrier between nodes)"},
@@ -543,6 +593,8 @@ def main():
     ap.add_argument("--prog-nobarrier", action="store_true", help="experiment: drop the inter-op grid barriers (no dependencies)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-prefill", action="store_true")
+    ap.add_argument("--skip-engine", action="store_true")
+    ap.add_argument("--gen-tokens", type=int, default=128)
     ap.add_argument("--prefill-tokens", type=int, default=2048)
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

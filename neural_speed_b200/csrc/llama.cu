@@ -48,23 +48,50 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ ta
 }
 
 // y = x / sqrt(mean(x^2) + eps) * w      (ne_rms_norm + ne_mul; kernel_ref.h:2199-2225 "simplified")
+// One CTA per row; every thread issues ALL its loads (x and w, float4) before the first use, so the row costs one memory
+// latency instead of one per loop trip (a single CTA is latency-bound, not bandwidth-bound).
+template <int V4>  // float4 per thread: n <= 256 * 4 * V4
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
                                                       int n, float eps) {
   pdl_launch_dependents();
+  const int n4 = n >> 2;
+  float4 wv[V4];
+#pragma unroll
+  for (int j = 0; j < V4; ++j) {  // the norm weights do not depend on the previous kernel: fetch them before the wait
+    const int i = threadIdx.x + j * 256;
+    wv[j] = i < n4 ? ((const float4*)w)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   pdl_wait();
-  const float* xr = x + (size_t)blockIdx.x * n;
-  float* yr = y + (size_t)blockIdx.x * n;
+  const float4* xr = (const float4*)(x + (size_t)blockIdx.x * n);
+  float4* yr = (float4*)(y + (size_t)blockIdx.x * n);
+  float4 xv[V4];
+#pragma unroll
+  for (int j = 0; j < V4; ++j) {
+    const int i = threadIdx.x + j * 256;
+    xv[j] = i < n4 ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float ss = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) ss = fmaf(xr[i], xr[i], ss);
+#pragma unroll
+  for (int j = 0; j < V4; ++j) {
+    ss = fmaf(xv[j].x, xv[j].x, ss);
+    ss = fmaf(xv[j].y, xv[j].y, ss);
+    ss = fmaf(xv[j].z, xv[j].z, ss);
+    ss = fmaf(xv[j].w, xv[j].w, ss);
+  }
   __shared__ float red[8];
-  ss = warp_sum(ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
   float tot = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) tot += red[i];
   const float inv = 1.f / sqrtf(tot / (float)n + eps);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) yr[i] = xr[i] * inv * w[i];
+#pragma unroll
+  for (int j = 0; j < V4; ++j) {
+    const int i = threadIdx.x + j * 256;
+    if (i < n4) yr[i] = make_float4(xv[j].x * inv * wv[j].x, xv[j].y * inv * wv[j].y, xv[j].z * inv * wv[j].z, xv[j].w * inv * wv[j].w);
+  }
 }
 
 // rope (mode 0) on q and k of every new token + append k,v to the fp16 cache.
@@ -178,50 +205,227 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const float* __restr
   }
 }
 
-// greedy pick: index of the maximum, lowest index on ties; also advances the device-side position.
-// state[0] = next token, state[1] += n_tokens (only when `advance`), out_tokens[state[2]++] = next token when recording
-__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int n, int* __restrict__ state, int n_tokens,
-                                                      int advance, int* __restrict__ record) {
+// Decode-shaped attention for head sizes 64 / 128: 8 warps per (head, token); a warp streams whole K/V rows (one 4- or 8-byte
+// load per lane), four rows in flight; with FUSE (single new token) the kernel also applies RoPE to its q head and to the
+// new k row and appends k,v to the cache, so rope_kv_kernel is not launched.
+template <int HD, bool FUSE>
+__global__ void __launch_bounds__(256) attn_fast_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ knew, int ldk,
+                                                        const float* __restrict__ vnew, int ldv, __half* __restrict__ kc,
+                                                        __half* __restrict__ vc, const int* __restrict__ state, float* __restrict__ out, int ldo,
+                                                        int n_head, int n_head_kv, int n_ctx, float scale, float theta_scale,
+                                                        float freq_scale) {
+  constexpr int EPL = HD / 32;  // elements per lane
+  extern __shared__ float sm[];  // [HD] q | [HD] new k | [HD] new v | [8][HD] partial out | [n_ctx] scores
+  float* sq = sm;
+  float* sk = sm + HD;
+  float* sv = sm + 2 * HD;
+  float* part = sm + 3 * HD;
+  float* sc = sm + 3 * HD + 8 * HD;
   pdl_launch_dependents();
   pdl_wait();
+  const int h = blockIdx.x, t = blockIdx.y;
+  const int group = n_head / n_head_kv, hk = h / group;
+  const int pos = state[1] + t;
+  int len = pos + 1;
+  len = len > n_ctx ? n_ctx : len;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __half* kh = kc + (size_t)hk * n_ctx * HD;
+  __half* vh = vc + (size_t)hk * n_ctx * HD;
+  const float* qr = q + (size_t)t * ldq + (size_t)h * HD;
+  if (FUSE) {
+    if (threadIdx.x < HD / 2) {
+      const int i = threadIdx.x;
+      float theta = (float)pos;
+      for (int j = 0; j < i; ++j) theta *= theta_scale;  // ne_layers.c:9385: same sequence of roundings
+      theta *= freq_scale;
+      float sn, cs;
+      sincosf(theta, &sn, &cs);
+      const float q0 = qr[2 * i], q1 = qr[2 * i + 1];
+      sq[2 * i] = __half2float(__float2half_rn(q0 * cs - q1 * sn));
+      sq[2 * i + 1] = __half2float(__float2half_rn(q0 * sn + q1 * cs));
+      const float* kr = knew + (size_t)t * ldk + (size_t)hk * HD;
+      const float k0 = kr[2 * i], k1 = kr[2 * i + 1];
+      const __half r0 = __float2half_rn(k0 * cs - k1 * sn), r1 = __float2half_rn(k0 * sn + k1 * cs);
+      sk[2 * i] = __half2float(r0);
+      sk[2 * i + 1] = __half2float(r1);
+      const float* vr = vnew + (size_t)t * ldv + (size_t)hk * HD;
+      const __half w0 = __float2half_rn(vr[2 * i]), w1 = __float2half_rn(vr[2 * i + 1]);
+      sv[2 * i] = __half2float(w0);
+      sv[2 * i + 1] = __half2float(w1);
+      if (h % group == 0 && pos < n_ctx) {  // one CTA per kv head appends to the cache
+        *(__half2*)(kh + (size_t)pos * HD + 2 * i) = __halves2half2(r0, r1);
+        *(__half2*)(vh + (size_t)pos * HD + 2 * i) = __halves2half2(w0, w1);
+      }
+    }
+  } else {
+    for (int d = threadIdx.x; d < HD; d += blockDim.x) sq[d] = __half2float(__float2half_rn(qr[d]));
+  }
+  __syncthreads();
+  float ql[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) ql[e] = sq[lane * EPL + e];
+  const int ncache = FUSE ? len - 1 : len;  // rows read from the cache; the new row comes from shared memory when fused
+
+  auto load_row = [&](const __half* base, int i, float* dst) {
+    if (EPL == 4) {
+      const uint2 u = *(const uint2*)(base + (size_t)i * HD + lane * 4);
+      const float2 a = __half22float2(*(const __half2*)&u.x), b = __half22float2(*(const __half2*)&u.y);
+      dst[0] = a.x, dst[1] = a.y, dst[2] = b.x, dst[3] = b.y;
+    } else {
+      const __half2 u = *(const __half2*)(base + (size_t)i * HD + lane * 2);
+      const float2 a = __half22float2(u);
+      dst[0] = a.x, dst[1] = a.y;
+    }
+  };
+  // pass 1: scores
+  for (int i0 = warp * 4; i0 < ncache; i0 += 32) {
+    float kr[4][EPL];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u < ncache) load_row(kh, i0 + u, kr[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u < ncache) {  // warp-uniform
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc = fmaf(ql[e], kr[u][e], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) sc[i0 + u] = acc * scale;
+      }
+    }
+  }
+  if (FUSE && warp == 0 && len - 1 == ncache) {
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc = fmaf(ql[e], sk[lane * EPL + e], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) sc[len - 1] = acc * scale;
+  }
+  __syncthreads();
+  __shared__ float red[8];
+  __shared__ float bcast;
+  float lmax = -INFINITY;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) lmax = fmaxf(lmax, sc[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if (lane == 0) red[warp] = lmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    bcast = m;
+  }
+  __syncthreads();
+  const float mx = bcast;
+  float lsum = 0.f;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const float a = __half2float(__float2half_rn(sc[i] - mx));
+    const float e = __half2float(__float2half_rn(expf(a)));  // table_exp_f16 (ne_layers.c:8933-8937)
+    sc[i] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  __syncthreads();
+  if (lane == 0) red[warp] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s2 = 0.f;
+    for (int i = 0; i < 8; ++i) s2 += red[i];
+    bcast = 1.f / s2;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  // pass 2: each warp accumulates its rows, lanes own EPL output elements; then the 8 partials are summed
+  float acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  for (int i0 = warp * 4; i0 < ncache; i0 += 32) {
+    float vr[4][EPL];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u < ncache) load_row(vh, i0 + u, vr[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u < ncache) {
+        const float p = __half2float(__float2half_rn(sc[i0 + u] * inv));
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, vr[u][e], acc[e]);
+      }
+  }
+  if (FUSE && warp == 0 && len - 1 == ncache) {
+    const float p = __half2float(__float2half_rn(sc[len - 1] * inv));
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, sv[lane * EPL + e], acc[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) part[warp * HD + lane * EPL + e] = acc[e];
+  __syncthreads();
+  for (int d = threadIdx.x; d < HD; d += blockDim.x) {
+    float s2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s2 += part[w * HD + d];
+    out[(size_t)t * ldo + (size_t)h * HD + d] = s2;
+  }
+}
+
+// greedy pick: index of the maximum, lowest index on ties (model_utils.cpp:2963-2985); also advances the device-side
+// position.  kArgmaxBlocks CTAs scan slices (all loads in flight at once); the last CTA to finish (ticket) merges the
+// partial results.  state[3] = pick; when `advance`: state[0] = pick, state[1] += n_tokens, record[state[2]++] = pick.
+constexpr int kArgmaxBlocks = 32;
+__device__ __forceinline__ void argmax_merge(float& best, int& bi, float ov, int oi) {
+  if (ov > best || (ov == best && oi < bi)) {
+    best = ov;
+    bi = oi;
+  }
+}
+__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ logits, int n, int* __restrict__ state, int n_tokens,
+                                                     int advance, int* __restrict__ record, float* __restrict__ pval, int* __restrict__ pidx,
+                                                     unsigned* __restrict__ ticket) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int per = (n + kArgmaxBlocks - 1) / kArgmaxBlocks;
+  const int lo = blockIdx.x * per, hi = min(n, lo + per);
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = logits[i];
-    if (v > best || (v == best && i < bi)) {
-      best = v;
-      bi = i;
-    }
-  }
-  __shared__ float sv[32];
-  __shared__ int si[32];
+  constexpr int U = 4;
+  for (int i0 = lo + threadIdx.x; i0 < hi; i0 += 256 * U) {
+    float v[U];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > best || (ov == best && oi < bi)) {
-      best = ov;
-      bi = oi;
-    }
+    for (int u = 0; u < U; ++u) v[u] = (i0 + u * 256 < hi) ? logits[i0 + u * 256] : -INFINITY;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * 256 < hi) argmax_merge(best, bi, v[u], i0 + u * 256);
   }
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  __shared__ bool last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) argmax_merge(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
   if ((threadIdx.x & 31) == 0) {
     sv[threadIdx.x >> 5] = best;
     si[threadIdx.x >> 5] = bi;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-      if (sv[w] > best || (sv[w] == best && si[w] < bi)) {
-        best = sv[w];
-        bi = si[w];
-      }
-    if (bi == 0x7fffffff) bi = 0;  // all NaN / -inf: the reference's loop keeps index 0
-    state[3] = bi;
-    if (advance) {
-      state[0] = bi;
-      state[1] += n_tokens;
-      if (record) record[state[2]++] = bi;
-    }
+    for (int w = 1; w < 8; ++w) argmax_merge(best, bi, sv[w], si[w]);
+    pval[blockIdx.x] = best;
+    pidx[blockIdx.x] = bi;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == kArgmaxBlocks - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  best = -INFINITY;
+  bi = 0x7fffffff;
+  for (int b2 = 0; b2 < kArgmaxBlocks; ++b2) argmax_merge(best, bi, ((volatile float*)pval)[b2], ((volatile int*)pidx)[b2]);
+  if (bi == 0x7fffffff) bi = 0;  // all NaN / -inf: the reference's loop keeps index 0
+  *ticket = 0u;                  // ready for the next launch
+  state[3] = bi;
+  if (advance) {
+    state[0] = bi;
+    state[1] += n_tokens;
+    if (record) record[state[2]++] = bi;
   }
 }
 
@@ -239,6 +443,9 @@ struct ns_llama {
   int* state = nullptr;   // device: {token, n_past, n_recorded, last_pick}
   int* tokens = nullptr;  // device: prompt tokens of the current eval
   int* record = nullptr;  // device: generated tokens
+  float* am_val = nullptr;  // argmax partials
+  int* am_idx = nullptr;
+  unsigned* am_ticket = nullptr;
   int m_cap = 0;
   float *x = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *tmp = nullptr, *logits = nullptr;
   void* ws = nullptr;
@@ -281,7 +488,11 @@ extern "C" ns_llama* ns_llama_create(const ns_llama_hparams* hp, void* queue) {
   c->tokens = (int*)dev_alloc(c, (size_t)hp->n_ctx * sizeof(int));
   c->record = (int*)dev_alloc(c, (size_t)hp->n_ctx * sizeof(int));
   c->logits = (float*)dev_alloc(c, (size_t)hp->n_vocab * 4);
-  if (!c->kc || !c->vc || !c->state || !c->tokens || !c->record || !c->logits ||
+  c->am_val = (float*)dev_alloc(c, 64 * sizeof(float));
+  c->am_idx = (int*)dev_alloc(c, 64 * sizeof(int));
+  c->am_ticket = (unsigned*)dev_alloc(c, sizeof(unsigned));
+  if (c->am_ticket) cudaMemsetAsync(c->am_ticket, 0, sizeof(unsigned), c->st);
+  if (!c->kc || !c->vc || !c->state || !c->tokens || !c->record || !c->logits || !c->am_val || !c->am_idx || !c->am_ticket ||
       cudaMallocHost((void**)&c->h_state, 4 * sizeof(int)) != cudaSuccess ||
       cudaMallocHost((void**)&c->h_logits, (size_t)hp->n_vocab * 4) != cudaSuccess) {
     ns_llama_free(c);
@@ -360,6 +571,18 @@ extern "C" int ns_llama_set_weight(ns_llama* c, int tensor, int layer, const ns_
   return NS_OK;
 }
 
+static int launch_rmsnorm(const float* x, const float* w, float* y, int rows, int n, float eps, cudaStream_t st) {
+  if (n % 4 || n > 256 * 4 * 8) {
+    ns_set_error("ns_llama: n_embd %d unsupported by the RMSNorm kernel (needs n %% 4 == 0, n <= 8192)", n);
+    return NS_E_UNSUPPORTED;
+  }
+  const int v4 = (n / 4 + 255) / 256;
+  auto kern = v4 <= 1 ? rmsnorm_kernel<1> : v4 <= 2 ? rmsnorm_kernel<2> : v4 <= 4 ? rmsnorm_kernel<4> : rmsnorm_kernel<8>;
+  NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)rows), dim3(256), 0, st, x, w, y, n, eps));
+  ns_count_launch();
+  return NS_OK;
+}
+
 static int ensure_buffers(ns_llama* c, int m) {
   if (m <= c->m_cap) return NS_OK;
   const ns_llama_hparams& hp = c->hp;
@@ -428,12 +651,26 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
     NS_CUDA_TRY(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
     attn_attr = attn_smem;
   }
+  const size_t fast_smem = (size_t)(11 * hd + hp.n_ctx) * sizeof(float);
+  if (fast_smem > 48 * 1024) {
+    static size_t fast_attr = 0;
+    if (fast_smem > 220 * 1024) {
+      ns_set_error("ns_llama: n_ctx %d too large for the single-pass attention kernel", hp.n_ctx);
+      return NS_E_UNSUPPORTED;
+    }
+    if (fast_smem > fast_attr) {
+      NS_CUDA_TRY(cudaFuncSetAttribute(attn_fast_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+      NS_CUDA_TRY(cudaFuncSetAttribute(attn_fast_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+      NS_CUDA_TRY(cudaFuncSetAttribute(attn_fast_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+      NS_CUDA_TRY(cudaFuncSetAttribute(attn_fast_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+      fast_attr = fast_smem;
+    }
+  }
   for (int il = 0; il < hp.n_layer; ++il) {
     const Layer& L = c->layers[il];
     __half* kc = c->kc + (size_t)il * hp.n_head_kv * hp.n_ctx * hd;
     __half* vc = c->vc + (size_t)il * hp.n_head_kv * hp.n_ctx * hd;
-    NS_CUDA_TRY(ns_launch_pdl(rmsnorm_kernel, dim3((unsigned)m), dim3(256), 0, st, (const float*)c->x, L.attn_norm, c->xn, E, hp.norm_eps));
-    ns_count_launch();
+    if (int rc = launch_rmsnorm(c->x, L.attn_norm, c->xn, m, E, hp.norm_eps, st)) return rc;
     bool fused = false;
     if (hp.n_head == hp.n_head_kv) {  // fused QKV node (llama.cpp:212-215); dst = [3][m][E] = q | k | v
       fused = ns_mul_qkv(L.wq, L.wk, L.wv, c->xn, E, q, E, m, c->ws, (void*)st) == NS_OK;
@@ -443,27 +680,41 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
       if (int rc = ns_mul_mat(L.wk, c->xn, E, k, kvd, m, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
       if (int rc = ns_mul_mat(L.wv, c->xn, E, v, kvd, m, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
     }
-    NS_CUDA_TRY(ns_launch_pdl(rope_kv_kernel, dim3((unsigned)(hp.n_head + hp.n_head_kv), (unsigned)m), dim3((unsigned)(hd / 2)), 0, st, q, E,
-                              (const float*)k, kvd, (const float*)v, kvd, kc, vc, (const int*)c->state, hp.n_head, hp.n_head_kv, hd,
-                              hp.n_ctx, theta_scale, freq_scale));
-    ns_count_launch();
-    NS_CUDA_TRY(ns_launch_pdl(attn_kernel, dim3((unsigned)hp.n_head, (unsigned)m), dim3(kAttnThreads), attn_smem, st, (const float*)q, E,
-                              (const __half*)kc, (const __half*)vc, (const int*)c->state, c->attn, E, hp.n_head, hp.n_head_kv, hd,
-                              hp.n_ctx, attn_scale));
-    ns_count_launch();
+    const bool fast = (hd == 128 || hd == 64);
+    if (fast && m == 1) {  // rope + KV append + attention in one launch
+      auto kern = hd == 128 ? attn_fast_kernel<128, true> : attn_fast_kernel<64, true>;
+      NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)hp.n_head, 1u), dim3(256), fast_smem, st, (const float*)q, E, (const float*)k, kvd,
+                                (const float*)v, kvd, kc, vc, (const int*)c->state, c->attn, E, hp.n_head, hp.n_head_kv, hp.n_ctx,
+                                attn_scale, theta_scale, freq_scale));
+      ns_count_launch();
+    } else {
+      NS_CUDA_TRY(ns_launch_pdl(rope_kv_kernel, dim3((unsigned)(hp.n_head + hp.n_head_kv), (unsigned)m), dim3((unsigned)(hd / 2)), 0, st, q,
+                                E, (const float*)k, kvd, (const float*)v, kvd, kc, vc, (const int*)c->state, hp.n_head, hp.n_head_kv, hd,
+                                hp.n_ctx, theta_scale, freq_scale));
+      ns_count_launch();
+      if (fast) {
+        auto kern = hd == 128 ? attn_fast_kernel<128, false> : attn_fast_kernel<64, false>;
+        NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)hp.n_head, (unsigned)m), dim3(256), fast_smem, st, (const float*)q, E,
+                                  (const float*)k, kvd, (const float*)v, kvd, kc, vc, (const int*)c->state, c->attn, E, hp.n_head,
+                                  hp.n_head_kv, hp.n_ctx, attn_scale, theta_scale, freq_scale));
+      } else {
+        NS_CUDA_TRY(ns_launch_pdl(attn_kernel, dim3((unsigned)hp.n_head, (unsigned)m), dim3(kAttnThreads), attn_smem, st, (const float*)q,
+                                  E, (const __half*)kc, (const __half*)vc, (const int*)c->state, c->attn, E, hp.n_head, hp.n_head_kv, hd,
+                                  hp.n_ctx, attn_scale));
+      }
+      ns_count_launch();
+    }
     // inpFF = wo * attn + inpSA, written over x (every row is read by its own output only after the matmul finished)
     if (int rc = ns_mul_mat(L.wo, c->attn, E, c->xn, E, m, nullptr, c->x, 0, c->ws, (void*)st)) return rc;
     // xn now holds inpFF; normalise it into attn (free again), FFN + residual back into x
-    NS_CUDA_TRY(ns_launch_pdl(rmsnorm_kernel, dim3((unsigned)m), dim3(256), 0, st, (const float*)c->xn, L.ffn_norm, c->attn, E, hp.norm_eps));
-    ns_count_launch();
+    if (int rc = launch_rmsnorm(c->xn, L.ffn_norm, c->attn, m, E, hp.norm_eps, st)) return rc;
     if (int rc = ns_ffn_silu_residual(L.w1, L.w2, L.w3, c->attn, E, c->tmp, c->x, E, m, c->xn, c->ws, st)) return rc;
   }
   // logits of the last token only (model_eval keeps the last row unless logits_all)
-  NS_CUDA_TRY(ns_launch_pdl(rmsnorm_kernel, dim3(1u), dim3(256), 0, st, (const float*)(c->x + (size_t)(m - 1) * E), (const float*)c->out_norm,
-                            c->xn, E, hp.norm_eps));
-  ns_count_launch();
+  if (int rc = launch_rmsnorm(c->x + (size_t)(m - 1) * E, c->out_norm, c->xn, 1, E, hp.norm_eps, st)) return rc;
   if (int rc = ns_mul_mat(c->output, c->xn, E, c->logits, hp.n_vocab, 1, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
-  NS_CUDA_TRY(ns_launch_pdl(argmax_kernel, dim3(1u), dim3(1024), 0, st, (const float*)c->logits, hp.n_vocab, c->state, m, advance, record));
+  NS_CUDA_TRY(ns_launch_pdl(argmax_kernel, dim3((unsigned)kArgmaxBlocks), dim3(256), 0, st, (const float*)c->logits, hp.n_vocab, c->state, m,
+                            advance, record, c->am_val, c->am_idx, c->am_ticket));
   ns_count_launch();
   return NS_OK;
 }

@@ -19,9 +19,9 @@ def _need_gpu():
     yield
 
 
-def _build(n_head_kv=4, out_fmt="q4_0", seed=0, n_layer=2, n_ctx=48):
+def _build(n_head_kv=4, out_fmt="q4_0", seed=0, n_layer=2, n_ctx=48, n_head=4):
     rng = np.random.default_rng(seed)
-    hp = dict(n_vocab=320, n_embd=256, n_head=4, n_head_kv=n_head_kv, n_layer=n_layer, n_ff=512, n_ctx=n_ctx, norm_eps=1e-5,
+    hp = dict(n_vocab=320, n_embd=256, n_head=n_head, n_head_kv=n_head_kv, n_layer=n_layer, n_ff=512, n_ctx=n_ctx, norm_eps=1e-5,
               rope_theta=10000.0, rope_scale=1.0)
     E, FF, V = hp["n_embd"], hp["n_ff"], hp["n_vocab"]
     kvd = E // hp["n_head"] * n_head_kv
@@ -64,9 +64,11 @@ def _check_logits(got, want, tol=1e-2):
         assert int(np.argmax(got)) == greedy(want)
 
 
-@pytest.mark.parametrize("n_head_kv,out_fmt", [(4, "q4_0"), (2, "q4_0"), (4, "q6_K")])
-def test_token_by_token_decode_matches_the_cpu_graph(n_head_kv, out_fmt):
-    hp, orc, eng = _build(n_head_kv, out_fmt, seed=n_head_kv)
+@pytest.mark.parametrize("n_head,n_head_kv,out_fmt", [(4, 4, "q4_0"), (4, 2, "q4_0"), (4, 4, "q6_K"), (2, 2, "q4_0"), (2, 1, "q4_0"),
+                                                       (8, 8, "q4_0")])
+def test_token_by_token_decode_matches_the_cpu_graph(n_head, n_head_kv, out_fmt):
+    """head sizes 64 and 128 take the fused rope + KV-append + attention kernel, 32 the generic one"""
+    hp, orc, eng = _build(n_head_kv, out_fmt, seed=n_head_kv, n_head=n_head)
     toks = [1, 17, 300, 5, 123, 77, 9]
     for pos, t in enumerate(toks):
         want = orc.eval([t], pos)
@@ -87,9 +89,10 @@ def test_small_prompt_eval_then_decode():
     eng.close()
 
 
-def test_long_prompt_goes_through_the_tensor_core_gemm():
+@pytest.mark.parametrize("n_head", [4, 2])
+def test_long_prompt_goes_through_the_tensor_core_gemm(n_head):
     """M > 4 rows take the bf16 tcgen05 GEMM: same graph, bf16 matmul numerics (looser bar), KV cache usable afterwards"""
-    hp, orc, eng = _build(seed=6)
+    hp, orc, eng = _build(n_head, seed=6, n_head=n_head)
     prompt = list(np.random.default_rng(1).integers(3, hp["n_vocab"], 12))
     _check_logits(eng.eval(prompt, 0)[0], orc.eval(prompt, 0), tol=4e-2)
     _check_logits(eng.eval([42], 12)[0], orc.eval([42], 12), tol=4e-2)
