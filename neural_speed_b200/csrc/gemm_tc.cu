@@ -30,11 +30,8 @@ namespace {
 constexpr int BLOCK_N = 128;  // weight rows per CTA (UMMA M)
 constexpr int BLOCK_K = 64;   // bf16 elements per k block (one 128-byte swizzle atom)
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 384;
-constexpr int SP = 6;  // packed-weight stages (4 KB)
-constexpr int SD = 3;  // dequantised-weight stages (16 KB)
-constexpr int PACKED_STAGE = BLOCK_N * (BLOCK_K / 2);  // 4096
-constexpr int DEQ_STAGE = BLOCK_N * BLOCK_K * 2;       // 16384
+constexpr int PACKED_TILE = BLOCK_N * (BLOCK_K / 2);  // 4096: nibbles of one 128-row sub-tile and k block
+constexpr int DEQ_TILE = BLOCK_N * BLOCK_K * 2;       // 16384: the same as bf16
 
 struct GemmParams {
   const uint8_t* rows;
@@ -116,9 +113,17 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
       : "r"(taddr)                                                                                                          \
       : "memory")
 
-template <int T>
+// NB = number of 128-row weight sub-tiles a CTA owns (each with its own TMEM accumulator).  The bf16 activation tile is the
+// expensive operand to re-read (2 B/element against 0.5 B for the weights): at T = 256, NB = 1 a CTA pulls 36 KB per 4.2 MFLOP
+// and the GEMM is bound by L2 -> SM bandwidth (measured 36 % of the tensor peak); NB = 2 halves the activation traffic per flop.
+template <int T, int NB>
 struct Smem {
-  static constexpr int SA = (T >= 256) ? 4 : 6;  // activation stages
+  static constexpr int SP = NB == 2 ? 4 : 6;                 // packed-weight stages
+  static constexpr int SD = NB == 2 ? 2 : 3;                 // dequantised-weight stages
+  static constexpr int SA = NB == 2 ? (T >= 256 ? 3 : 4) : ((T >= 256) ? 4 : 6);  // activation stages
+  static constexpr int PACKED_STAGE = NB * PACKED_TILE;
+  static constexpr int DEQ_STAGE = NB * DEQ_TILE;
+  static constexpr int kThreads = 256 + 128 * NB;
   static constexpr int ACT_STAGE = T * BLOCK_K * 2;
   static constexpr int off_deq = 0;
   static constexpr int off_act = off_deq + SD * DEQ_STAGE;
@@ -129,11 +134,11 @@ struct Smem {
   static constexpr int total = off_tmem_ptr + 16 + 1024;  // + slack for manual 1024-B alignment
 };
 
-template <int T>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int T, int NB>
+__global__ void __launch_bounds__(256 + 128 * NB, 1)
     gemm_w4_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const GemmParams P) {
-  using L = Smem<T>;
-  constexpr int SA = L::SA;
+  using L = Smem<T, NB>;
+  constexpr int SA = L::SA, SP = L::SP, SD = L::SD, PACKED_STAGE = L::PACKED_STAGE, DEQ_STAGE = L::DEQ_STAGE;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   unsigned char* deq = smem + L::off_deq;
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::off_tmem_ptr);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BLOCK_N;
+  const int n0 = blockIdx.x * (BLOCK_N * NB);
   const int t0 = blockIdx.y * T;
   const int num_kb = (P.kpad + BLOCK_K - 1) / BLOCK_K;
 
@@ -158,14 +163,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < SP; ++i) {
       mbar_init(&p_full[i], 1);
-      mbar_init(&p_empty[i], 4);
+      mbar_init(&p_empty[i], 4 * NB);
     }
     for (int i = 0; i < SA; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < SD; ++i) {
-      mbar_init(&d_full[i], 4);
+      mbar_init(&d_full[i], 4 * NB);
       mbar_init(&d_empty[i], 1);
     }
     mbar_init(tmem_full, 1);
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)T)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)(T * NB))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -221,10 +226,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t a_addr = smem_u32(deq + sd * DEQ_STAGE);
         const uint32_t b_addr = smem_u32(act + sa * L::ACT_STAGE);
 #pragma unroll
-        for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4) {
-          umma_bf16(tmem_base, make_desc_sw128(a_addr + k4 * UMMA_K * 2), make_desc_sw128(b_addr + k4 * UMMA_K * 2), idesc,
-                    (uint32_t)((kb | k4) != 0));
-        }
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4) {
+            umma_bf16(tmem_base + (uint32_t)(nb * T), make_desc_sw128(a_addr + nb * DEQ_TILE + k4 * UMMA_K * 2),
+                      make_desc_sw128(b_addr + k4 * UMMA_K * 2), idesc, (uint32_t)((kb | k4) != 0));
+          }
         umma_commit(&d_empty[sd]);  // fires when the MMAs above have finished reading shared memory
         umma_commit(&a_empty[sa]);
         if (kb == num_kb - 1) umma_commit(tmem_full);
@@ -232,8 +239,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
     }
   } else if (warp >= 8) {
-    // ============================ dequant: one thread per weight row ============================
-    const int r = threadIdx.x - 256;
+    // ============================ dequant: one thread per weight row (128 * NB rows) ============================
+    const int r = threadIdx.x - 256;  // row inside the CTA's 128*NB rows; packed rows are 32 B apart, bf16 sub-tiles DEQ_TILE apart
     int grow = n0 + r;
     if (grow >= P.n) grow = P.n - 1;  // rows past N are zero-filled by TMA; keep the scale loads in bounds
     const uint8_t* rowp = P.rows + (size_t)grow * P.pitch;
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_empty[sp]);  // nibbles are in registers
       if (kb >= SD) mbar_wait(&d_empty[sd], ((kb / SD) - 1) & 1);
-      drow_base = deq + sd * DEQ_STAGE + (r >> 3) * 1024 + swz * 128;
+      drow_base = deq + sd * DEQ_STAGE + (r >> 7) * DEQ_TILE + ((r & 127) >> 3) * 1024 + swz * 128;
       const uint32_t words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
       for (int c = 0; c < 8; ++c) {  // packed word c = k 8c..8c+7 = 16-byte chunk c of the bf16 row
@@ -283,16 +290,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp >= 4) {
     // ============================ epilogue: TMEM -> registers -> global ============================
     const int q = warp - 4;  // TMEM lane quarter == warp % 4
-    const int nrow = n0 + q * 32 + lane;
-    const bool nvalid = nrow < P.n;
     pdl_wait();  // dst / residual may still be in use by the preceding kernel
     mbar_wait(tmem_full, 0);
     tcgen05_fence_after();
-    const float bcast_bias = (P.bias && P.bias_bcast && nvalid) ? P.bias[nrow] : 0.f;
 #pragma unroll 1
-    for (int c0 = 0; c0 < T; c0 += 32) {
+    for (int cc = 0; cc < NB * T; cc += 32) {
+      const int nb = cc / T, c0 = cc % T;
+      const int nrow = n0 + nb * BLOCK_N + q * 32 + lane;
+      const bool nvalid = nrow < P.n;
+      const float bcast_bias = (P.bias && P.bias_bcast && nvalid) ? P.bias[nrow] : 0.f;
       uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
       TMEM_LD_32X32B_X32(taddr, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)T) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(T * NB)) : "memory");
   }
 }
 
@@ -346,16 +354,16 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <int T>
+template <int T, int NB>
 int launch_t(const CUtensorMap& mw, const CUtensorMap& ma, const GemmParams& P, cudaStream_t st) {
-  auto kern = gemm_w4_tc_kernel<T>;
+  auto kern = gemm_w4_tc_kernel<T, NB>;
   static bool attr_set = false;
   if (!attr_set) {
-    NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<T>::total));
+    NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<T, NB>::total));
     attr_set = true;
   }
-  dim3 grid((P.n + BLOCK_N - 1) / BLOCK_N, (P.m + T - 1) / T);
-  NS_CUDA_TRY(ns_launch_pdl(kern, grid, dim3(kThreads), (size_t)Smem<T>::total, st, mw, ma, P));
+  dim3 grid((P.n + BLOCK_N * NB - 1) / (BLOCK_N * NB), (P.m + T - 1) / T);
+  NS_CUDA_TRY(ns_launch_pdl(kern, grid, dim3(Smem<T, NB>::kThreads), (size_t)Smem<T, NB>::total, st, mw, ma, P));
   ns_count_launch();
   return NS_OK;
 }
@@ -419,12 +427,14 @@ int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, i
   }
   const __nv_bfloat16* abf = (const __nv_bfloat16*)ws;
   int T = m <= 32 ? 32 : (m <= 64 ? 64 : (m <= 128 ? 128 : 256));
+  static const int force_nb = getenv("NS_TC_NB") ? atoi(getenv("NS_TC_NB")) : 0;  // tuning aid
+  const int NBsel = force_nb ? force_nb : ((T >= 128 && w->n >= 2 * BLOCK_N) ? 2 : 1);
   CUtensorMap mw, ma;
   {
     // packed nibbles: uint8 [n][q_bytes] with row pitch `pitch`; box = 32 bytes (64 k) x 128 rows, no swizzle
     cuuint64_t dims[2] = {(cuuint64_t)w->q_bytes, (cuuint64_t)w->n};
     cuuint64_t strides[1] = {(cuuint64_t)w->pitch};
-    cuuint32_t box[2] = {BLOCK_K / 2, BLOCK_N};
+    cuuint32_t box[2] = {BLOCK_K / 2, (cuuint32_t)(BLOCK_N * NBsel)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)w->rows, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -463,10 +473,11 @@ int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, i
   P.bias = bias;
   P.bias_bcast = bias_bcast;
   P.residual = residual;
+  if (NBsel == 2) return T == 128 ? launch_t<128, 2>(mw, ma, P, st) : launch_t<256, 2>(mw, ma, P, st);
   switch (T) {
-    case 32: return launch_t<32>(mw, ma, P, st);
-    case 64: return launch_t<64>(mw, ma, P, st);
-    case 128: return launch_t<128>(mw, ma, P, st);
-    default: return launch_t<256>(mw, ma, P, st);
+    case 32: return launch_t<32, 1>(mw, ma, P, st);
+    case 64: return launch_t<64, 1>(mw, ma, P, st);
+    case 128: return launch_t<128, 1>(mw, ma, P, st);
+    default: return launch_t<256, 1>(mw, ma, P, st);
   }
 }
