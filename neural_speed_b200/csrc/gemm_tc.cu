@@ -30,11 +30,12 @@ namespace {
 constexpr int BLOCK_N = 128;  // weight rows per CTA (UMMA M)
 constexpr int BLOCK_K = 64;   // bf16 elements per k block (one 128-byte swizzle atom)
 constexpr int UMMA_K = 16;
-constexpr int PACKED_TILE = BLOCK_N * (BLOCK_K / 2);  // 4096: nibbles of one 128-row sub-tile and k block
+constexpr int PACKED_TILE = BLOCK_N * (BLOCK_K / 2);  // 4096: nibbles of one 128-row sub-tile and k block (x2 for int8 weights)
 constexpr int DEQ_TILE = BLOCK_N * BLOCK_K * 2;       // 16384: the same as bf16
 
 struct GemmParams {
   const uint8_t* rows;
+  int wfmt;
   int pitch, sc_off, zp_off, stype, asym, group, ngroups;
   int n, k, kpad, m;
   float* dst;
@@ -116,12 +117,14 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
 // NB = number of 128-row weight sub-tiles a CTA owns (each with its own TMEM accumulator).  The bf16 activation tile is the
 // expensive operand to re-read (2 B/element against 0.5 B for the weights): at T = 256, NB = 1 a CTA pulls 36 KB per 4.2 MFLOP
 // and the GEMM is bound by L2 -> SM bandwidth (measured 36 % of the tensor peak); NB = 2 halves the activation traffic per flop.
-template <int T, int NB>
+// W8: int8 weights (64 packed bytes per row and k block instead of 32).
+template <int T, int NB, bool W8 = false>
 struct Smem {
-  static constexpr int SP = NB == 2 ? 4 : 6;                 // packed-weight stages
+  static constexpr int SP = NB == 2 ? (W8 ? 3 : 4) : 6;      // packed-weight stages
   static constexpr int SD = NB == 2 ? 2 : 3;                 // dequantised-weight stages
   static constexpr int SA = NB == 2 ? (T >= 256 ? 3 : 4) : ((T >= 256) ? 4 : 6);  // activation stages
-  static constexpr int PACKED_STAGE = NB * PACKED_TILE;
+  static constexpr int ROW_BYTES = W8 ? BLOCK_K : BLOCK_K / 2;  // packed bytes per weight row and k block
+  static constexpr int PACKED_STAGE = NB * BLOCK_N * ROW_BYTES;
   static constexpr int DEQ_STAGE = NB * DEQ_TILE;
   static constexpr int kThreads = 256 + 128 * NB;
   static constexpr int ACT_STAGE = T * BLOCK_K * 2;
@@ -134,10 +137,11 @@ struct Smem {
   static constexpr int total = off_tmem_ptr + 16 + 1024;  // + slack for manual 1024-B alignment
 };
 
-template <int T, int NB>
+template <int T, int NB, bool W8>
 __global__ void __launch_bounds__(256 + 128 * NB, 1)
     gemm_w4_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const GemmParams P) {
-  using L = Smem<T, NB>;
+  using L = Smem<T, NB, W8>;
+  constexpr int ROW_BYTES = L::ROW_BYTES;
   constexpr int SA = L::SA, SP = L::SP, SD = L::SD, PACKED_STAGE = L::PACKED_STAGE, DEQ_STAGE = L::DEQ_STAGE;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -159,6 +163,8 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
   const int t0 = blockIdx.y * T;
   const int num_kb = (P.kpad + BLOCK_K - 1) / BLOCK_K;
 
+  __shared__ float nf4_lut[16];  // constant memory serialises divergent indices; shared memory broadcasts per bank
+  if (threadIdx.x >= 32 && threadIdx.x < 48) nf4_lut[threadIdx.x - 32] = NS_NF4_LUT[threadIdx.x - 32];
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int i = 0; i < SP; ++i) {
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
       const int pre = num_kb < SP ? num_kb : SP;
       for (int kb = 0; kb < pre; ++kb) {
         mbar_expect_tx(&p_full[kb], PACKED_STAGE);
-        tma_load_2d(packed + kb * PACKED_STAGE, &tmap_w, kb * (BLOCK_K / 2), n0, &p_full[kb]);
+        tma_load_2d(packed + kb * PACKED_STAGE, &tmap_w, kb * ROW_BYTES, n0, &p_full[kb]);
       }
       pdl_wait();  // activations were written by the preceding kernel
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
           const int sp = kp % SP;
           mbar_wait(&p_empty[sp], ((kp / SP) - 1) & 1);
           mbar_expect_tx(&p_full[sp], PACKED_STAGE);
-          tma_load_2d(packed + sp * PACKED_STAGE, &tmap_w, kp * (BLOCK_K / 2), n0, &p_full[sp]);
+          tma_load_2d(packed + sp * PACKED_STAGE, &tmap_w, kp * ROW_BYTES, n0, &p_full[sp]);
         }
       }
     }
@@ -254,7 +260,9 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
       if (g1 >= P.ngroups) g1 = P.ngroups - 1;
       const float sc0 = ns_scale_at(rowp + P.sc_off, P.stype, g0);
       const float sc1 = (g1 == g0) ? sc0 : ns_scale_at(rowp + P.sc_off, P.stype, g1);
-      float of0 = 136.f, of1 = 136.f;  // 128 (bf16 magic) + 8 (nibble bias) [+ zero point]
+      // offset subtracted in bf16 before the scale: 128 (bf16 magic) + 8 (nibble bias) [+ zero point] for packed int4,
+      // the zero point alone for int8 weights (all exactly representable)
+      float of0 = W8 ? 0.f : 136.f, of1 = of0;
       if (P.asym) {
         of0 += (float)(int)(signed char)rowp[P.zp_off + g0];
         of1 += (float)(int)(signed char)rowp[P.zp_off + g1];
@@ -263,23 +271,47 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
       const __nv_bfloat162 o2[2] = {__float2bfloat162_rn(of0), __float2bfloat162_rn(of1)};
 
       mbar_wait(&p_full[sp], (kb / SP) & 1);
-      const uint4* pk = reinterpret_cast<const uint4*>(packed + sp * PACKED_STAGE + r * 32);
-      const uint4 q0 = pk[0], q1 = pk[1];
+      const uint4* pk = reinterpret_cast<const uint4*>(packed + sp * PACKED_STAGE + r * ROW_BYTES);
+      uint32_t words[W8 ? 16 : 8];
+#pragma unroll
+      for (int i = 0; i < (W8 ? 4 : 2); ++i) {
+        const uint4 qv = pk[i];
+        words[4 * i] = qv.x, words[4 * i + 1] = qv.y, words[4 * i + 2] = qv.z, words[4 * i + 3] = qv.w;
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_empty[sp]);  // nibbles are in registers
+      if (lane == 0) mbar_arrive(&p_empty[sp]);  // packed bytes are in registers
       if (kb >= SD) mbar_wait(&d_empty[sd], ((kb / SD) - 1) & 1);
       drow_base = deq + sd * DEQ_STAGE + (r >> 7) * DEQ_TILE + ((r & 127) >> 3) * 1024 + swz * 128;
-      const uint32_t words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {  // packed word c = k 8c..8c+7 = 16-byte chunk c of the bf16 row
+      for (int c = 0; c < 8; ++c) {  // 16-byte chunk c of the bf16 row = k 8c..8c+7
         const int h = c >> 2;
         uint32_t o[4];
+        if (W8) {
+          // int8 weights, natural byte order: words[2c] = k 8c..8c+3, words[2c+1] = k 8c+4..8c+7
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t t = ((words[c] >> (4 * j)) & 0x000F000Fu) | 0x43004300u;  // bf16x2 (128 + e(2j), 128 + e(2j+1))
-          __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&t);
-          v = __hmul2(__hsub2(v, o2[h]), s2[h]);
-          o[j] = *reinterpret_cast<uint32_t*>(&v);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t wsrc = words[2 * c + (j >> 1)];
+            const int b0 = (int)(signed char)((wsrc >> (16 * (j & 1))) & 0xffu), b1 = (int)(signed char)((wsrc >> (16 * (j & 1) + 8)) & 0xffu);
+            __nv_bfloat162 v = __floats2bfloat162_rn((float)b0, (float)b1);
+            v = __hmul2(__hsub2(v, o2[h]), s2[h]);
+            o[j] = *reinterpret_cast<uint32_t*>(&v);
+          }
+        } else if (P.wfmt == NS_W_NF4) {
+          // NF4 codes: level from the table (kernel_ref.h:1325-1368), rounded to bf16, times the bf16 scale
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float l0 = nf4_lut[(words[c] >> (4 * j)) & 0xFu], l1 = nf4_lut[(words[c] >> (4 * j + 16)) & 0xFu];
+            __nv_bfloat162 v = __hmul2(__floats2bfloat162_rn(l0, l1), s2[h]);
+            o[j] = *reinterpret_cast<uint32_t*>(&v);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t t = ((words[c] >> (4 * j)) & 0x000F000Fu) | 0x43004300u;  // bf16x2 (128 + e(2j), 128 + e(2j+1))
+            __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&t);
+            v = __hmul2(__hsub2(v, o2[h]), s2[h]);
+            o[j] = *reinterpret_cast<uint32_t*>(&v);
+          }
         }
         *reinterpret_cast<uint4*>(drow_base + ((c ^ swz) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
       }
@@ -354,16 +386,17 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <int T, int NB>
+template <int T, int NB, bool W8>
 int launch_t(const CUtensorMap& mw, const CUtensorMap& ma, const GemmParams& P, cudaStream_t st) {
-  auto kern = gemm_w4_tc_kernel<T, NB>;
+  using L = Smem<T, NB, W8>;
+  auto kern = gemm_w4_tc_kernel<T, NB, W8>;
   static bool attr_set = false;
   if (!attr_set) {
-    NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<T, NB>::total));
+    NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total));
     attr_set = true;
   }
   dim3 grid((P.n + BLOCK_N * NB - 1) / (BLOCK_N * NB), (P.m + T - 1) / T);
-  NS_CUDA_TRY(ns_launch_pdl(kern, grid, dim3(Smem<T, NB>::kThreads), (size_t)Smem<T, NB>::total, st, mw, ma, P));
+  NS_CUDA_TRY(ns_launch_pdl(kern, grid, dim3(L::kThreads), (size_t)L::total, st, mw, ma, P));
   ns_count_launch();
   return NS_OK;
 }
@@ -372,7 +405,9 @@ int launch_t(const CUtensorMap& mw, const CUtensorMap& ma, const GemmParams& P, 
 
 size_t ns_gemm_tc_workspace_bytes(int m, int kpad) { return ns_round_up((size_t)m * kpad * 2, 256); }
 
-bool ns_gemm_tc_supported(const ns_weight* w) { return w->wfmt == NS_W_S4 && (w->group % 32 == 0 || w->group == w->k); }
+bool ns_gemm_tc_supported(const ns_weight* w) {
+  return (w->wfmt == NS_W_S4 || w->wfmt == NS_W_NF4 || w->wfmt == NS_W_S8) && (w->group % 32 == 0 || w->group == w->k);
+}
 
 // phase 1: fp32 activations -> bf16 [m][kpad] in ws (ns_gemm_tc_workspace_bytes(m, kpad) bytes)
 int ns_launch_act_bf16(const ns_weight* w, const float* act, int lda, int m, void* ws, cudaStream_t st) {
@@ -417,7 +452,7 @@ int ns_launch_gelu(float* x, size_t total, cudaStream_t st) {
 int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, int m, const float* bias, int bias_bcast,
                       const float* residual, cudaStream_t st) {
   if (!ns_gemm_tc_supported(w)) {
-    ns_set_error("tensor-core GEMM: only 4-bit integer weights with 32-multiple groups are supported");
+    ns_set_error("tensor-core GEMM: int4 / NF4 / int8 weights with 32-multiple groups are supported");
     return NS_E_UNSUPPORTED;
   }
   EncodeTiledFn enc = get_encode();
@@ -429,12 +464,13 @@ int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, i
   int T = m <= 32 ? 32 : (m <= 64 ? 64 : (m <= 128 ? 128 : 256));
   static const int force_nb = getenv("NS_TC_NB") ? atoi(getenv("NS_TC_NB")) : 0;  // tuning aid
   const int NBsel = force_nb ? force_nb : ((T >= 128 && w->n >= 2 * BLOCK_N) ? 2 : 1);
+  const bool w8 = w->wfmt == NS_W_S8;
   CUtensorMap mw, ma;
   {
     // packed nibbles: uint8 [n][q_bytes] with row pitch `pitch`; box = 32 bytes (64 k) x 128 rows, no swizzle
     cuuint64_t dims[2] = {(cuuint64_t)w->q_bytes, (cuuint64_t)w->n};
     cuuint64_t strides[1] = {(cuuint64_t)w->pitch};
-    cuuint32_t box[2] = {BLOCK_K / 2, (cuuint32_t)(BLOCK_N * NBsel)};
+    cuuint32_t box[2] = {(cuuint32_t)(w8 ? BLOCK_K : BLOCK_K / 2), (cuuint32_t)(BLOCK_N * NBsel)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)w->rows, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -457,6 +493,7 @@ int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, i
   }
   GemmParams P;
   P.rows = w->rows;
+  P.wfmt = w->wfmt;
   P.pitch = w->pitch;
   P.sc_off = w->sc_off;
   P.zp_off = w->zp_off;
@@ -473,11 +510,20 @@ int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, i
   P.bias = bias;
   P.bias_bcast = bias_bcast;
   P.residual = residual;
-  if (NBsel == 2) return T == 128 ? launch_t<128, 2>(mw, ma, P, st) : launch_t<256, 2>(mw, ma, P, st);
+  if (w8) {
+    if (NBsel == 2) return T == 128 ? launch_t<128, 2, true>(mw, ma, P, st) : launch_t<256, 2, true>(mw, ma, P, st);
+    switch (T) {
+      case 32: return launch_t<32, 1, true>(mw, ma, P, st);
+      case 64: return launch_t<64, 1, true>(mw, ma, P, st);
+      case 128: return launch_t<128, 1, true>(mw, ma, P, st);
+      default: return launch_t<256, 1, true>(mw, ma, P, st);
+    }
+  }
+  if (NBsel == 2) return T == 128 ? launch_t<128, 2, false>(mw, ma, P, st) : launch_t<256, 2, false>(mw, ma, P, st);
   switch (T) {
-    case 32: return launch_t<32, 1>(mw, ma, P, st);
-    case 64: return launch_t<64, 1>(mw, ma, P, st);
-    case 128: return launch_t<128, 1>(mw, ma, P, st);
-    default: return launch_t<256, 1>(mw, ma, P, st);
+    case 32: return launch_t<32, 1, false>(mw, ma, P, st);
+    case 64: return launch_t<64, 1, false>(mw, ma, P, st);
+    case 128: return launch_t<128, 1, false>(mw, ma, P, st);
+    default: return launch_t<256, 1, false>(mw, ma, P, st);
   }
 }

@@ -330,7 +330,8 @@ int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
   const int act_row = (int)ns_round_up((size_t)P.kpad, 1024);
   const size_t act_region = ns_round_up((size_t)mt * act_row + (size_t)mt * P.meta_stride * 8, 128);
   // Shared-memory plan: half an SM (two CTAs per SM), or a whole SM for very long rows.
-  const size_t budgets[2] = {113 * 1024, 200 * 1024};
+  static const int env_budget = getenv("NS_RING_BUDGET_KB") ? atoi(getenv("NS_RING_BUDGET_KB")) : 0;  // tuning aid
+  const size_t budgets[2] = {(size_t)(env_budget > 0 ? env_budget : 113) * 1024, 200 * 1024};
   int stages = 0;
   size_t budget = 0;
   for (int i = 0; i < 2; ++i) {
@@ -346,7 +347,10 @@ int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
   }
   if (stages > 32) stages = 32;
   const size_t smem = act_region + (size_t)stages * stage_bytes + (size_t)stages * 16;
-  const int ctas_per_sm = budget > 113 * 1024 ? 1 : 2;
+  static const int env_cps = getenv("NS_RING_CPS") ? atoi(getenv("NS_RING_CPS")) : 0;  // tuning aid
+  const int ctas_per_sm = budget > 113 * 1024 ? 1 : (env_cps > 0 ? env_cps : 2);
+  static const bool dbg = getenv("NS_RING_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "gemv_ring: k=%d pitch=%d stages=%d smem=%zu cps=%d\n", P.k, P.pitch, stages, smem, ctas_per_sm);
   int grid = ns_num_sms() * ctas_per_sm;
   if (grid > P.npairs) grid = P.npairs;
   if (grid < 1) grid = 1;

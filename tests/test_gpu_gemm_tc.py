@@ -71,6 +71,39 @@ def test_tc_gemm_int4_vs_oracle(m, n, k, g, asym):
     assert np.abs(got - ref32).max() <= 1e-2 * np.abs(ref32).max()
 
 
+@pytest.mark.parametrize("m,n,k,g", [(9, 128, 256, 32), (130, 384, 1024, 128), (300, 512, 4096, 32)])
+def test_tc_gemm_nf4_vs_oracle(m, n, k, g):
+    """config 4 (NF4): level = table[code] (kernel_ref.h:1325-1368), bf16 operands on the tensor cores"""
+    rng = np.random.default_rng(m + n)
+    w = rng.uniform(-0.5, 0.5, (k, n)).astype(np.float32)
+    a = rng.uniform(-0.5, 0.5, (m, k)).astype(np.float32)
+    q, sc = oracle.btla_quantize_nf4(w, g)
+    wd = ns.Weight.from_unpacked(q, sc, None, g, ns.W_NF4, ns.S_F32, ns.COMP_BF16)
+    got = run(wd, a)
+    wdq = oracle.btla_dequant(q, sc, None, g, nf4=True)
+    gi = np.arange(k) // g
+    lut = wdq / np.where(sc[gi] == 0, 1, sc[gi])                    # the table levels
+    want = oracle.gemm_f64acc(bf16r(a), bf16r(bf16r(lut) * bf16r(sc)[gi]))
+    assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max()
+    ref32 = oracle.gemm_f64acc(a, wdq)
+    assert np.abs(got - ref32).max() <= 1e-2 * np.abs(ref32).max()
+
+
+@pytest.mark.parametrize("m,n,k,g,asym", [(9, 128, 256, 32, False), (130, 384, 1024, 128, True), (300, 512, 4096, 32, False)])
+def test_tc_gemm_int8_weights_vs_oracle(m, n, k, g, asym):
+    """config 4 (INT8 weights): 64 packed bytes per row and k block, (q - zp) exact in bf16"""
+    rng = np.random.default_rng(m + n + 1)
+    w = rng.uniform(-0.5, 0.5, (k, n)).astype(np.float32)
+    a = rng.uniform(-0.5, 0.5, (m, k)).astype(np.float32)
+    q, sc, zp = oracle.btla_quantize(w, g, 8, asym)
+    wd = ns.Weight.from_unpacked(q, sc, zp, g, ns.W_S8, ns.S_F32, ns.COMP_BF16)
+    got = run(wd, a)
+    want = expect_bf16(a, q, sc, zp, g)
+    assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max()
+    ref32 = oracle.gemm_f64acc(a, oracle.btla_dequant(q, sc, zp, g))
+    assert np.abs(got - ref32).max() <= 1e-2 * np.abs(ref32).max()
+
+
 def test_tc_gemm_q4_0_prefill_vs_cpu_path():
     """ggml Q4_0 weights, 128-token prompt batch: tensor-core result vs the reference CPU numerics (Q8_0 activations)"""
     rng = np.random.default_rng(3)
