@@ -262,6 +262,20 @@ NS_API int ns_llama_eval(ns_llama* ctx, const int32_t* tokens, int n_tokens, int
 NS_API int ns_llama_generate(ns_llama* ctx, int32_t first_token, int n_past, int n_new, int32_t* out_tokens);
 NS_API unsigned long long ns_llama_kv_bytes(const ns_llama* ctx);
 
+/* ---- tensor-parallel exchange step over NVLink peer memory --------------------------------------------
+ * One-shot sum all-reduce replacing reduce_add / ne_all_reduce (core/parallel_context.cpp:47, ne_layers.c:5466) for the
+ * [M, n_embd] fp32 partials after o-proj / down-proj (llama.cpp:592,693).  One process per GPU: each creates a context,
+ * the hosts exchange the ns_comm_get_handle blobs (e.g. torch.distributed all_gather) and call ns_comm_open_peers.
+ * Every rank gets bit-identical sums (fixed rank order).  max_elems bounds n of later calls. */
+typedef struct ns_comm ns_comm;
+NS_API size_t ns_comm_handle_bytes(void);
+NS_API ns_comm* ns_comm_create(int rank, int world, size_t max_elems, void* queue);
+NS_API int ns_comm_get_handle(ns_comm* c, void* handle_out);
+NS_API int ns_comm_open_peers(ns_comm* c, const void* all_handles);
+NS_API int ns_comm_all_reduce_f32(ns_comm* c, float* data, size_t n, const float* residual, void* queue);
+NS_API int ns_comm_status(ns_comm* c);
+NS_API void ns_comm_free(ns_comm* c);
+
 /* core/layers/bestla_gemm.h:37-56 (C++ in the reference; same names/argument meaning, extern "C" here).
  * QuantType/ScaleDtype are raw BTLA_DTYPE values, CompType an ne_comp_type.  ThreadPool is ignored. */
 NS_API size_t BTLAGemmPackBSize(size_t N, size_t K, size_t BlkSize, uint32_t QuantType, uint32_t ScaleDtype, bool isAsym,

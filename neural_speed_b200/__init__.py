@@ -57,6 +57,8 @@ EXPORTS = [
     "BTLAGemmPackBSize", "BTLAGemmQuantPackB", "BTLAGemmPackB", "BTLAGemmUnPackB", "ns_quantize_row_q4_0", "ns_split_weight_size", "ns_split_weight",
     "ns_llama_create", "ns_llama_free", "ns_llama_set_f32", "ns_llama_set_weight", "ns_llama_eval", "ns_llama_generate",
     "ns_llama_kv_bytes",
+    "ns_comm_handle_bytes", "ns_comm_create", "ns_comm_get_handle", "ns_comm_open_peers", "ns_comm_all_reduce_f32",
+    "ns_comm_status", "ns_comm_free",
 ]
 
 _lib = None
@@ -172,6 +174,15 @@ def lib() -> C.CDLL:
     L.ns_llama_generate.argtypes = [vp, C.c_int32, i, i, vp]
     L.ns_llama_kv_bytes.restype = C.c_ulonglong
     L.ns_llama_kv_bytes.argtypes = [vp]
+    L.ns_comm_handle_bytes.restype = sz
+    L.ns_comm_create.restype = vp
+    L.ns_comm_create.argtypes = [i, i, sz, vp]
+    L.ns_comm_get_handle.argtypes = [vp, vp]
+    L.ns_comm_open_peers.argtypes = [vp, vp]
+    L.ns_comm_all_reduce_f32.argtypes = [vp, vp, sz, vp, vp]
+    L.ns_comm_status.argtypes = [vp]
+    L.ns_comm_free.restype = None
+    L.ns_comm_free.argtypes = [vp]
     L.ns_split_weight_size.restype = sz
     L.ns_split_weight_size.argtypes = [vp, sz, sz]
     L.ns_split_weight.restype = C.c_bool

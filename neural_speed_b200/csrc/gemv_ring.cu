@@ -122,6 +122,7 @@ __device__ __forceinline__ PairSrc resolve_pair(const GemvParams& P, int p) {
 struct RingCfg {
   int ring_off;     // byte offset of the ring inside dynamic shared memory
   int stages;
+  int active;       // consumer warps that own ring stages (<= kConsumers; `stages` is a multiple of it)
   int act_row;      // bytes per activation row in the staged image
   uint32_t cpg_magic;  // ceil(2^32 / cpg): gi = umulhi(c, magic)
 };
@@ -190,13 +191,15 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
   const uint32_t meta_s = smem_base + P.meta_off;
   const int nchunks = P.kpad >> 5;
 
-  // This warp visits units warp, warp+kConsumers, ... .  `stages` is a multiple of kConsumers (launcher), so stage s is only ever
-  // consumed by warp s % kConsumers: every mbarrier is waited on by ONE warp that observes all of its phases in order.
+  // This warp visits units warp, warp+active, ... .  `stages` is a multiple of `active` (launcher), so stage s is only ever
+  // consumed by warp s % active: every mbarrier is waited on by ONE warp that observes all of its phases in order.
   // (A parity wait issued a whole phase early returns true immediately -- waiters must never run ahead of a barrier.)
   int s = warp;
   uint32_t phase = 0;
 
-  for (int j = warp; j < my_units; j += kConsumers) {
+  const int active = R.active;  // long rows leave room for fewer stages than consumer warps: the surplus warps only helped quantise
+  if (warp >= active) return;
+  for (int j = warp; j < my_units; j += active) {
     const PairSrc ps = resolve_pair(P, first + j * gstride);
     mbar_wait(full0 + 8 * s, phase);
     const uint32_t r0 = ring + (uint32_t)s * stage_bytes;
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + 8 * s);  // slot may be refilled
-    s += kConsumers;
+    s += active;
     if (s >= stages) {
       s -= stages;
       phase ^= 1u;
@@ -332,16 +335,24 @@ int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
   // Shared-memory plan: half an SM (two CTAs per SM), or a whole SM for very long rows.
   static const int env_budget = getenv("NS_RING_BUDGET_KB") ? atoi(getenv("NS_RING_BUDGET_KB")) : 0;  // tuning aid
   const size_t budgets[2] = {(size_t)(env_budget > 0 ? env_budget : 113) * 1024, 200 * 1024};
-  int stages = 0;
+  int stages = 0, active = 0;
   size_t budget = 0;
-  for (int i = 0; i < 2; ++i) {
-    budget = budgets[i];
-    if (budget > act_region + 64) stages = (int)((budget - act_region - 64) / (stage_bytes + 16));
-    stages -= stages % kConsumers;  // one consumer warp per stage residue class (see kernel)
-    if (stages >= kConsumers) break;
-    stages = 0;
+  {
+    // plan for both budgets; prefer the one that keeps more consumer warps per SM streaming (2 CTAs x active vs 1 x active)
+    int st[2] = {0, 0}, ac[2] = {0, 0};
+    for (int i = 0; i < 2; ++i) {
+      int raw = 0;
+      if (budgets[i] > act_region + 64) raw = (int)((budgets[i] - act_region - 64) / (stage_bytes + 16));
+      if (raw > 32) raw = 32;
+      ac[i] = raw < kConsumers ? raw : kConsumers;
+      st[i] = ac[i] > 0 ? raw - raw % ac[i] : 0;  // one consumer warp per stage residue class (see kernel)
+    }
+    const int pick = (2 * ac[0] >= ac[1] && ac[0] > 0) ? 0 : 1;
+    stages = st[pick];
+    active = ac[pick];
+    budget = budgets[pick];
   }
-  if (stages < kConsumers) {
+  if (stages < 1) {
     ns_set_error("gemv_ring: row pitch %d too large for shared memory", P.pitch);
     return NS_E_UNSUPPORTED;
   }
@@ -350,13 +361,14 @@ int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
   static const int env_cps = getenv("NS_RING_CPS") ? atoi(getenv("NS_RING_CPS")) : 0;  // tuning aid
   const int ctas_per_sm = budget > 113 * 1024 ? 1 : (env_cps > 0 ? env_cps : 2);
   static const bool dbg = getenv("NS_RING_DEBUG") != nullptr;
-  if (dbg) fprintf(stderr, "gemv_ring: k=%d pitch=%d stages=%d smem=%zu cps=%d\n", P.k, P.pitch, stages, smem, ctas_per_sm);
+  if (dbg) fprintf(stderr, "gemv_ring: k=%d pitch=%d stages=%d active=%d smem=%zu cps=%d\n", P.k, P.pitch, stages, active, smem, ctas_per_sm);
   int grid = ns_num_sms() * ctas_per_sm;
   if (grid > P.npairs) grid = P.npairs;
   if (grid < 1) grid = 1;
   RingCfg R;
   R.ring_off = (int)act_region;
   R.stages = stages;
+  R.active = active;
   R.act_row = act_row;
   R.cpg_magic = P.cpg > 1 ? (uint32_t)((0x100000000ull + (uint64_t)P.cpg - 1) / (uint64_t)P.cpg) : 0u;
   NS_CUDA_TRY(ns_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, st, P, R));

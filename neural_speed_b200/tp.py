@@ -108,10 +108,49 @@ class TPContext:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
 
-    def all_reduce(self, t):
-        """in-place sum over ranks (reduce_add(sendBuf == recvBuf), ne_layers.c:5474)"""
+    def enable_p2p(self, max_elems: int, queue=None) -> bool:
+        """Set up the one-shot NVLink all-reduce (ns_comm_*): exchange the cudaIpc handles through torch.distributed and map
+        every peer's buffer.  Returns False (and keeps NCCL) when the world is 1 or the tensors are not on CUDA."""
+        torch, dist = self.torch, self.dist
+        if self.world == 1 or not torch.cuda.is_available():
+            return False
+        from . import lib, last_error
+        L = lib()
+        comm = L.ns_comm_create(self.rank, self.world, max_elems, queue)
+        if not comm:
+            raise RuntimeError("ns_comm_create failed: " + last_error())
+        hb = int(L.ns_comm_handle_bytes())
+        mine = np.zeros(hb, np.uint8)
+        if L.ns_comm_get_handle(C.c_void_p(comm), mine.ctypes.data_as(C.c_void_p)) != 0:
+            raise RuntimeError("ns_comm_get_handle failed: " + last_error())
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t_mine = torch.from_numpy(mine).to(dev)
+        gathered = [torch.empty_like(t_mine) for _ in range(self.world)]
+        dist.all_gather(gathered, t_mine)
+        allh = np.concatenate([g.cpu().numpy() for g in gathered])
+        if L.ns_comm_open_peers(C.c_void_p(comm), allh.ctypes.data_as(C.c_void_p)) != 0:
+            raise RuntimeError("ns_comm_open_peers failed: " + last_error())
+        dist.barrier()
+        self._comm, self._comm_max, self._comm_queue = C.c_void_p(comm), max_elems, queue
+        return True
+
+    def all_reduce(self, t, residual=None):
+        """in-place sum over ranks (reduce_add(sendBuf == recvBuf), ne_layers.c:5474); `residual` (same shape) is added
+        once after the reduction.  Uses the one-shot NVLink kernel when enable_p2p() was called and the tensor qualifies."""
+        comm = getattr(self, "_comm", None)
+        if (comm is not None and t.is_cuda and t.dtype == self.torch.float32 and t.is_contiguous() and t.numel() <= self._comm_max
+                and t.numel() % 4 == 0):
+            from . import lib, last_error
+            q = self._comm_queue if self._comm_queue is not None else C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+            rc = lib().ns_comm_all_reduce_f32(comm, C.c_void_p(t.data_ptr()), t.numel(),
+                                              C.c_void_p(residual.data_ptr()) if residual is not None else None, q)
+            if rc != 0:
+                raise RuntimeError("ns_comm_all_reduce_f32 failed: " + last_error())
+            return t
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        if residual is not None:
+            t += residual
         return t
 
     def barrier(self):
@@ -121,37 +160,43 @@ class TPContext:
 
 class TPLlamaMatmuls:
     """The matmul nodes of Llama decoder layers under tensor parallelism, device-resident (torch tensors for buffers,
-    libns_b200 kernels for the matmuls, torch.distributed NCCL for the two all-reduces per layer).
+    libns_b200 kernels for the matmuls, one sum all-reduce after o-proj and after down-proj with the residual add folded in).
 
     `layers` is a list of dicts name -> neural_speed_b200.Weight holding THIS RANK's shards (shapes per LlamaShardPlan).
-    forward() maps the layer input x [M, n_embd] to the layer output contribution the way llama.cpp does around the
-    attention core, which is supplied as `attn_fn(q, k, v) -> [M, n_head_local*head_dim]` (identity on q by default)."""
+    layer() maps the layer input x [M, n_embd] to the layer output the way llama.cpp does around the attention core, which
+    is supplied as `attn_fn(q, k, v) -> [M, n_head_local*head_dim]` (identity on q by default).  Buffers are allocated once
+    per M, kernels go to torch's CURRENT stream, so a whole token can be captured in a torch.cuda.CUDAGraph."""
 
-    def __init__(self, plan: LlamaShardPlan, layers, ctx: TPContext, stream=None):
+    def __init__(self, plan: LlamaShardPlan, layers, ctx: TPContext):
         import torch
         self.plan, self.layers, self.ctx, self.torch = plan, layers, ctx, torch
-        self.stream = stream if stream is not None else torch.cuda.current_stream()
-        self.queue = C.c_void_p(self.stream.cuda_stream)
+        self._bufs = {}
 
-    def layer(self, li: int, x, attn_fn=None):
+    def _buffers(self, m, device):
+        b = self._bufs.get(m)
+        if b is None:
+            torch, p = self.torch, self.plan
+            hd, w = p.head_dim, p.world
+            nq, nkv, ff = p.n_head // w * hd, p.n_head_kv // w * hd, p.n_ff // w
+            b = dict(q=torch.empty(m, nq, device=device), k=torch.empty(m, nkv, device=device), v=torch.empty(m, nkv, device=device),
+                     o=torch.empty(m, p.n_embd, device=device), h=torch.empty(m, p.n_embd, device=device),
+                     tmp=torch.empty(2 if m > 4 else 1, m, ff, device=device), dn=torch.empty(m, p.n_embd, device=device))
+            self._bufs[m] = b
+        return b
+
+    def layer(self, li: int, x, attn_fn=None, out=None):
         from . import mul_mat, ffn_silu
         torch, p, lay = self.torch, self.plan, self.layers[li]
         m = x.shape[0]
-        hd, w = p.head_dim, p.world
-        nq, nkv = p.n_head // w * hd, p.n_head_kv // w * hd
-        q = torch.empty(m, nq, device=x.device)
-        k = torch.empty(m, nkv, device=x.device)
-        v = torch.empty(m, nkv, device=x.device)
-        for wt, out in ((lay["wq"], q), (lay["wk"], k), (lay["wv"], v)):   # GQA: n differs, so three plain matmuls
-            mul_mat(wt, x.data_ptr(), p.n_embd, out.data_ptr(), out.shape[1], m, queue=self.queue)
+        b = self._buffers(m, x.device)
+        queue = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        q, k, v = b["q"], b["k"], b["v"]
+        for wt, dst in ((lay["wq"], q), (lay["wk"], k), (lay["wv"], v)):   # GQA: n differs, so three plain matmuls
+            mul_mat(wt, x.data_ptr(), p.n_embd, dst.data_ptr(), dst.shape[1], m, queue=queue)
         a = attn_fn(q, k, v) if attn_fn is not None else q
-        o = torch.empty(m, p.n_embd, device=x.device)
-        mul_mat(lay["wo"], a.data_ptr(), nq, o.data_ptr(), p.n_embd, m, queue=self.queue)
-        self.ctx.all_reduce(o)                                            # llama.cpp:592
-        h = x + o
-        ff = p.n_ff // w
-        tmp = torch.empty(2 if m > 4 else 1, m, ff, device=x.device)
-        dn = torch.empty(m, p.n_embd, device=x.device)
-        ffn_silu(lay["w1"], lay["w2"], lay["w3"], h.data_ptr(), p.n_embd, tmp.data_ptr(), dn.data_ptr(), p.n_embd, m, self.queue)
-        self.ctx.all_reduce(dn)                                           # llama.cpp:693
-        return h + dn
+        o = b["o"]
+        mul_mat(lay["wo"], a.data_ptr(), a.shape[1], o.data_ptr(), p.n_embd, m, queue=queue)
+        h = self.ctx.all_reduce(o, residual=x)                            # llama.cpp:592 + inpFF = cur + inpSA (:598)
+        dn = out if out is not None else b["dn"]
+        ffn_silu(lay["w1"], lay["w2"], lay["w3"], h.data_ptr(), p.n_embd, b["tmp"].data_ptr(), dn.data_ptr(), p.n_embd, m, queue)
+        return self.ctx.all_reduce(dn, residual=h)                        # llama.cpp:693 + cur = cur + inpFF (:698)

@@ -117,7 +117,8 @@ def test_q4_0_repack_is_lossless():
     assert np.array_equal(_dequant_dev(w), oracle.dequantize_q4_0(rows, k))
 
 
-@pytest.mark.parametrize("n,k,m", [(64, 512, 1), (4096, 4096, 1), (1000, 11008, 1), (257, 1024, 3), (96, 4096, 4), (128, 2048, 7)])
+@pytest.mark.parametrize("n,k,m", [(64, 512, 1), (4096, 4096, 1), (1000, 11008, 1), (257, 1024, 3), (96, 4096, 4), (128, 2048, 7),
+                                   (600, 14336, 1), (300, 28672, 2)])  # long rows: fewer ring stages than consumer warps
 def test_q4_0_mul_mat_vs_oracle(n, k, m):
     rng = np.random.default_rng(100 + n + m)
     w = rng.normal(0, 0.02, (n, k)).astype(np.float32)

@@ -69,6 +69,74 @@ def _worker(rank, world, port, q):
         q.put((rank, traceback.format_exc()))
 
 
+def _worker_p2p(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import traceback
+    try:
+        import time
+        import torch.distributed as dist
+        import neural_speed_b200 as ns
+        from neural_speed_b200 import tp
+        torch.cuda.set_device(rank)
+        ns.lib().bestla_init()
+        ctx = tp.TPContext(backend="nccl")
+        assert ctx.enable_p2p(16384)
+        g = torch.Generator(device="cuda").manual_seed(100 + rank)
+        gsame = torch.Generator(device="cuda").manual_seed(7)      # the residual (layer input) is the same on every rank
+        for n in (4096, 8192, 16384, 4):
+            for it in range(6):
+                x = torch.randn(n, device="cuda", generator=g)
+                res = torch.randn(n, device="cuda", generator=gsame) if it % 2 else None
+                want = x.clone()
+                dist.all_reduce(want)                       # NCCL
+                if res is not None:
+                    want = want + res
+                got = ctx.all_reduce(x.clone(), residual=res)
+                torch.cuda.synchronize()
+                assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), (n, it, float((got - want).abs().max()))
+                gathered = [torch.empty_like(got) for _ in range(world)]
+                dist.all_gather(gathered, got)
+                assert all(torch.equal(gathered[0], t) for t in gathered)  # fixed rank order -> bit-identical on every rank
+        assert ns.lib().ns_comm_status(ctx._comm) == 0
+        # latency, 8192 floats (the [1, n_embd] partial of Llama-2-70B), back to back on one stream
+        x = torch.randn(8192, device="cuda")
+        for fn, name in ((lambda: ctx.all_reduce(x), "p2p"), (lambda: dist.all_reduce(x), "nccl")):
+            for _ in range(20):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(200):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if rank == 0:
+                print(f"all-reduce 32 KB {name}: {e0.elapsed_time(e1) / 200 * 1e3:.2f} us", flush=True)
+            x.normal_()
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+
+
+def test_two_gpu_oneshot_nvlink_all_reduce(capfd):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_p2p, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def test_two_gpu_tensor_parallel_layer():
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
