@@ -122,16 +122,35 @@ __device__ __forceinline__ PairSrc resolve_pair(const GemvParams& P, int p) {
 struct RingCfg {
   int ring_off;     // byte offset of the ring inside dynamic shared memory
   int stages;
+  int units;        // row pairs (ROWS == 2) or rows (ROWS == 1) of this launch
   int active;       // consumer warps that own ring stages (<= kConsumers; `stages` is a multiple of it)
   int act_row;      // bytes per activation row in the staged image
   uint32_t cpg_magic;  // ceil(2^32 / cpg): gi = umulhi(c, magic)
 };
 
-template <int AMODE, int M, bool ASYM, int STYPE>
+// ROWS == 1: unit u is row u of the concatenated weights (long rows: a pair would leave one ring stage per consumer warp)
+__device__ __forceinline__ PairSrc resolve_single(const GemvParams& P, int u) {
+  PairSrc s;
+  int row = u, wi = 0;
+  if (P.nw > 1 && row >= P.n[0]) {
+    row -= P.n[0];
+    wi = 1;
+    if (P.nw > 2 && row >= P.n[1]) {
+      row -= P.n[1];
+      wi = 2;
+    }
+  }
+  s.r0 = s.r1 = P.rows[wi] + (size_t)row * P.pitch;
+  s.out0 = s.out1 = P.dst_off[wi] + row;
+  s.valid1 = false;
+  return s;
+}
+
+template <int AMODE, int M, bool ASYM, int STYPE, int ROWS>
 __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams P, const RingCfg R) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int stage_bytes = 2 * P.pitch;
+  const int stage_bytes = ROWS * P.pitch;
   const int stages = R.stages;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t ring = smem_base + R.ring_off;
@@ -150,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
 
   const int first = blockIdx.x;
   const int gstride = (int)gridDim.x;
-  const int my_units = first < P.npairs ? (P.npairs - first + gstride - 1) / gstride : 0;
+  const int my_units = first < R.units ? (R.units - first + gstride - 1) / gstride : 0;
 
   if (warp == kConsumers) {
     // ===================== producer: stream whole row pairs, never touches activations =====================
@@ -159,11 +178,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
       uint32_t phase = 0;
       for (int j = 0; j < my_units; ++j) {
         if (j >= stages) mbar_wait(empty0 + 8 * s, phase ^ 1);
-        const PairSrc ps = resolve_pair(P, first + j * gstride);
+        const PairSrc ps = ROWS == 2 ? resolve_pair(P, first + j * gstride) : resolve_single(P, first + j * gstride);
         const uint32_t dst = ring + (uint32_t)s * stage_bytes;
         mbar_expect_tx(full0 + 8 * s, (uint32_t)stage_bytes);
         bulk_g2s(dst, ps.r0, (uint32_t)P.pitch, full0 + 8 * s);
-        bulk_g2s(dst + P.pitch, ps.r1, (uint32_t)P.pitch, full0 + 8 * s);
+        if (ROWS == 2) bulk_g2s(dst + P.pitch, ps.r1, (uint32_t)P.pitch, full0 + 8 * s);
         if (++s == stages) {
           s = 0;
           phase ^= 1;
@@ -200,32 +219,37 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
   const int active = R.active;  // long rows leave room for fewer stages than consumer warps: the surplus warps only helped quantise
   if (warp >= active) return;
   for (int j = warp; j < my_units; j += active) {
-    const PairSrc ps = resolve_pair(P, first + j * gstride);
+    const PairSrc ps = ROWS == 2 ? resolve_pair(P, first + j * gstride) : resolve_single(P, first + j * gstride);
     mbar_wait(full0 + 8 * s, phase);
     const uint32_t r0 = ring + (uint32_t)s * stage_bytes;
-    const uint32_t r1 = r0 + P.pitch;
+    const uint32_t r1 = ROWS == 2 ? r0 + P.pitch : r0;
+    const uint32_t rb[2] = {r0, r1};
 
-    float acc[2][M];
+    float acc[ROWS][M];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < ROWS; ++r)
 #pragma unroll
       for (int m = 0; m < M; ++m) acc[r][m] = 0.f;
 
 #pragma unroll 2
     for (int c = lane; c < nchunks; c += 32) {
-      const uint4 wv[2] = {lds128(r0 + 16 * c), lds128(r1 + 16 * c)};
       const int gi = (P.cpg == 1) ? c : (int)__umulhi((uint32_t)c, R.cpg_magic);
-      const float ws[2] = {lds_scale<STYPE>(r0 + P.sc_off, gi), lds_scale<STYPE>(r1 + P.sc_off, gi)};
-      int off[2] = {8, 8};
-      if (ASYM) {
-        off[0] += lds8s(r0 + P.zp_off + gi);
-        off[1] += lds8s(r1 + P.zp_off + gi);
+      uint4 wv[ROWS];
+      float ws[ROWS];
+      int off[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        wv[r] = lds128(rb[r] + 16 * c);
+        ws[r] = lds_scale<STYPE>(rb[r] + P.sc_off, gi);
+        off[r] = 8;
+        if (ASYM) off[r] += lds8s(rb[r] + P.zp_off + gi);
       }
       // low nibbles as bytes, high nibbles as bytes * 16 (no shift): exact, divided out after the dot
-      uint32_t lo[2][4], hi[2][4];
-      int su[2] = {0, 0};
+      uint32_t lo[ROWS][4], hi[ROWS][4];
+      int su[ROWS];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
+      for (int r = 0; r < ROWS; ++r) {
+        su[r] = 0;
         const uint32_t ww[4] = {wv[r].x, wv[r].y, wv[r].z, wv[r].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -252,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
         const float a_scale = __uint_as_float(mt.x);
         const int sa = (int)(short)(mt.y & 0xffff);
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
           int pl = 0, ph = 0;
           // NSB4: word i pairs with activation words (Alo_i, Ahi_i) = ((a0,a4,a1,a5),(a2,a6,a3,a7)) of 8-group i
           if (AMODE == A_U8) {
@@ -285,15 +309,15 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
     }
 
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < ROWS; ++r)
 #pragma unroll
       for (int m = 0; m < M; ++m) acc[r][m] = warp_sum(acc[r][m]);
     if (lane == 0) {
-      if (P.mode == NS_GEMV_GATE_UP_SILU) {
+      if (ROWS == 2 && P.mode == NS_GEMV_GATE_UP_SILU) {
 #pragma unroll
         for (int m = 0; m < M; ++m) {
           if (m < P.m) {
-            const float g = acc[0][m], up = acc[1][m];
+            const float g = acc[0][m], up = acc[ROWS - 1][m];
             const float sg = P.eltop == NS_ELT_GELU ? ns_gelu(g) : ns_silu(g);  // kernel_ref.h:1569-1576
             if (P.aux) P.aux[(size_t)m * P.ldo + ps.out0] = sg;
             P.dst[(size_t)m * P.ldo + ps.out0] = sg * up;
@@ -301,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
           if (r == 1 && !ps.valid1) continue;
           const long long out = r ? ps.out1 : ps.out0;
 #pragma unroll
@@ -321,59 +345,88 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
   }
 }
 
-template <int AMODE, int M, bool ASYM, int STYPE>
-int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
-  auto kern = gemv_ring_kernel<AMODE, M, ASYM, STYPE>;
+struct RingPlan {
+  int rows, stages, active, ctas;
+  size_t budget;
+  double score;
+};
+
+// Shared-memory plan.  Candidates: row pairs or single rows per stage, half an SM (two CTAs per SM) or a whole SM.  The score
+// is the number of consumer warps per SM that own a stage; pairs share the activation loads between two rows (measured:
+// K = 11008 with 7 pair stages beats 14 single-row stages, 950 vs 937 tok/s), so single rows are only taken when pairs would
+// leave consumer warps without a stage (K >= ~14000).  Ties go to the deeper ring.
+static RingPlan plan_ring(const GemvParams& P, size_t act_region) {
+  static const int env_budget = getenv("NS_RING_BUDGET_KB") ? atoi(getenv("NS_RING_BUDGET_KB")) : 0;  // tuning aids
+  static const int env_rows = getenv("NS_RING_ROWS") ? atoi(getenv("NS_RING_ROWS")) : 0;
+  const size_t budgets[2] = {(size_t)(env_budget > 0 ? env_budget : 113) * 1024, 200 * 1024};
+  RingPlan best = {0, 0, 0, 0, 0, -1.0};
+  for (int rows = 2; rows >= 1; --rows) {
+    if (rows == 1 && P.mode == NS_GEMV_GATE_UP_SILU) continue;  // the gate/up epilogue needs both rows in one warp
+    if (env_rows && rows != env_rows && !(env_rows == 1 && P.mode == NS_GEMV_GATE_UP_SILU)) continue;
+    const int stage_bytes = rows * P.pitch;
+    for (int i = 0; i < 2; ++i) {
+      int raw = 0;
+      if (budgets[i] > act_region + 64) raw = (int)((budgets[i] - act_region - 64) / (stage_bytes + 16));
+      if (raw > 32) raw = 32;
+      const int ac = raw < kConsumers ? raw : kConsumers;
+      if (ac < 1) continue;
+      const int st = raw - raw % ac;  // one consumer warp per stage residue class (see kernel)
+      const int ctas = i == 0 ? 2 : 1;
+      const double score = ctas * ac * (rows == 2 ? 1.1 : 1.0) + 0.001 * st;
+      if (score > best.score) best = RingPlan{rows, st, ac, ctas, budgets[i], score};
+    }
+  }
+  return best;
+}
+
+template <int AMODE, int M, bool ASYM, int STYPE, int ROWS>
+int launch_rows(const GemvParams& P, const RingPlan& plan, size_t act_region, int act_row, cudaStream_t st) {
+  auto kern = gemv_ring_kernel<AMODE, M, ASYM, STYPE, ROWS>;
   static bool attr_set = false;
   if (!attr_set) {
     NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  const int stage_bytes = 2 * P.pitch;
-  const int act_row = (int)ns_round_up((size_t)P.kpad, 1024);
-  const size_t act_region = ns_round_up((size_t)mt * act_row + (size_t)mt * P.meta_stride * 8, 128);
-  // Shared-memory plan: half an SM (two CTAs per SM), or a whole SM for very long rows.
-  static const int env_budget = getenv("NS_RING_BUDGET_KB") ? atoi(getenv("NS_RING_BUDGET_KB")) : 0;  // tuning aid
-  const size_t budgets[2] = {(size_t)(env_budget > 0 ? env_budget : 113) * 1024, 200 * 1024};
-  int stages = 0, active = 0;
-  size_t budget = 0;
-  {
-    // plan for both budgets; prefer the one that keeps more consumer warps per SM streaming (2 CTAs x active vs 1 x active)
-    int st[2] = {0, 0}, ac[2] = {0, 0};
-    for (int i = 0; i < 2; ++i) {
-      int raw = 0;
-      if (budgets[i] > act_region + 64) raw = (int)((budgets[i] - act_region - 64) / (stage_bytes + 16));
-      if (raw > 32) raw = 32;
-      ac[i] = raw < kConsumers ? raw : kConsumers;
-      st[i] = ac[i] > 0 ? raw - raw % ac[i] : 0;  // one consumer warp per stage residue class (see kernel)
-    }
-    const int pick = (2 * ac[0] >= ac[1] && ac[0] > 0) ? 0 : 1;
-    stages = st[pick];
-    active = ac[pick];
-    budget = budgets[pick];
-  }
-  if (stages < 1) {
-    ns_set_error("gemv_ring: row pitch %d too large for shared memory", P.pitch);
-    return NS_E_UNSUPPORTED;
-  }
-  if (stages > 32) stages = 32;
-  const size_t smem = act_region + (size_t)stages * stage_bytes + (size_t)stages * 16;
+  const int stage_bytes = ROWS * P.pitch;
+  const size_t smem = act_region + (size_t)plan.stages * stage_bytes + (size_t)plan.stages * 16;
   static const int env_cps = getenv("NS_RING_CPS") ? atoi(getenv("NS_RING_CPS")) : 0;  // tuning aid
-  const int ctas_per_sm = budget > 113 * 1024 ? 1 : (env_cps > 0 ? env_cps : 2);
-  static const bool dbg = getenv("NS_RING_DEBUG") != nullptr;
-  if (dbg) fprintf(stderr, "gemv_ring: k=%d pitch=%d stages=%d active=%d smem=%zu cps=%d\n", P.k, P.pitch, stages, active, smem, ctas_per_sm);
-  int grid = ns_num_sms() * ctas_per_sm;
-  if (grid > P.npairs) grid = P.npairs;
-  if (grid < 1) grid = 1;
+  const int ctas_per_sm = plan.ctas == 1 ? 1 : (env_cps > 0 ? env_cps : 2);
   RingCfg R;
   R.ring_off = (int)act_region;
-  R.stages = stages;
-  R.active = active;
+  R.stages = plan.stages;
+  R.active = plan.active;
   R.act_row = act_row;
+  if (ROWS == 2) {
+    R.units = P.npairs;
+  } else {
+    long long rows = 0;
+    for (int i = 0; i < P.nw; ++i) rows += P.n[i];
+    R.units = (int)rows;
+  }
   R.cpg_magic = P.cpg > 1 ? (uint32_t)((0x100000000ull + (uint64_t)P.cpg - 1) / (uint64_t)P.cpg) : 0u;
+  int grid = ns_num_sms() * ctas_per_sm;
+  if (grid > R.units) grid = R.units;
+  if (grid < 1) grid = 1;
+  static const bool dbg = getenv("NS_RING_DEBUG") != nullptr;
+  if (dbg)
+    fprintf(stderr, "gemv_ring: k=%d pitch=%d rows/stage=%d stages=%d active=%d smem=%zu ctas/sm=%d\n", P.k, P.pitch, ROWS, plan.stages,
+            plan.active, smem, ctas_per_sm);
   NS_CUDA_TRY(ns_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, st, P, R));
   ns_count_launch();
   return NS_OK;
+}
+
+template <int AMODE, int M, bool ASYM, int STYPE>
+int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
+  const int act_row = (int)ns_round_up((size_t)P.kpad, 1024);
+  const size_t act_region = ns_round_up((size_t)mt * act_row + (size_t)mt * P.meta_stride * 8, 128);
+  const RingPlan plan = plan_ring(P, act_region);
+  if (plan.stages < 1) {
+    ns_set_error("gemv_ring: row pitch %d too large for shared memory", P.pitch);
+    return NS_E_UNSUPPORTED;
+  }
+  if (plan.rows == 2) return launch_rows<AMODE, M, ASYM, STYPE, 2>(P, plan, act_region, act_row, st);
+  return launch_rows<AMODE, M, ASYM, STYPE, 1>(P, plan, act_region, act_row, st);
 }
 
 template <int AMODE, bool ASYM, int STYPE>
