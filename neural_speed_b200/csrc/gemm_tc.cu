@@ -43,6 +43,7 @@ struct GemmParams {
   const float* bias;
   int bias_bcast;
   const float* residual;
+  int dbg;  // NS_TC_DEBUG: 1 = dequant warps skip the conversion, 2 = no MMAs issued, 4 = epilogue skipped (timing experiments)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(deq + sd * DEQ_STAGE);
         const uint32_t b_addr = smem_u32(act + sa * L::ACT_STAGE);
+        if (!(P.dbg & 2))
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
       if (lane == 0) mbar_arrive(&p_empty[sp]);  // packed bytes are in registers
       if (kb >= SD) mbar_wait(&d_empty[sd], ((kb / SD) - 1) & 1);
       drow_base = deq + sd * DEQ_STAGE + (r >> 7) * DEQ_TILE + ((r & 127) >> 3) * 1024 + swz * 128;
+      if (!(P.dbg & 1))
 #pragma unroll
       for (int c = 0; c < 8; ++c) {  // 16-byte chunk c of the bf16 row = k 8c..8c+7
         const int h = c >> 2;
@@ -319,14 +322,19 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&d_full[sd]);
     }
-  } else if (warp >= 4) {
-    // ============================ epilogue: TMEM -> registers -> global ============================
-    const int q = warp - 4;  // TMEM lane quarter == warp % 4
+  }
+  // ============================ epilogue: TMEM -> registers -> global, ALL warps ============================
+  // A warp can read the TMEM lanes of quarter (warp % 4); the warps of a quarter split the accumulator columns.  With only
+  // four epilogue warps the 128 x 512 fp32 tile took 27 us of a 112 us GEMM (nothing else runs in the CTA by then).
+  {
+    __syncwarp();
+    const int q = warp & 3;
+    const int per_quarter = (int)(blockDim.x >> 7);  // warps per lane quarter: 3 (NB = 1) or 4 (NB = 2)
     pdl_wait();  // dst / residual may still be in use by the preceding kernel
     mbar_wait(tmem_full, 0);
     tcgen05_fence_after();
 #pragma unroll 1
-    for (int cc = 0; cc < NB * T; cc += 32) {
+    for (int cc = (warp >> 2) * 32; cc < ((P.dbg & 4) ? 0 : NB * T); cc += per_quarter * 32) {
       const int nb = cc / T, c0 = cc % T;
       const int nrow = n0 + nb * BLOCK_N + q * 32 + lane;
       const bool nvalid = nrow < P.n;
@@ -510,6 +518,8 @@ int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, i
   P.bias = bias;
   P.bias_bcast = bias_bcast;
   P.residual = residual;
+  static const int dbg = getenv("NS_TC_DEBUG") ? atoi(getenv("NS_TC_DEBUG")) : 0;
+  P.dbg = dbg;
   if (w8) {
     if (NBsel == 2) return T == 128 ? launch_t<128, 2, true>(mw, ma, P, st) : launch_t<256, 2, true>(mw, ma, P, st);
     switch (T) {
