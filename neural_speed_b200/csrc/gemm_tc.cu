@@ -43,6 +43,7 @@ struct GemmParams {
   const float* bias;
   int bias_bcast;
   const float* residual;
+  int kb_per_split;  // k blocks per grid.z slice (>= total: no split)
   int dbg;  // NS_TC_DEBUG: 1 = dequant warps skip the conversion, 2 = no MMAs issued, 4 = epilogue skipped (timing experiments)
 };
 
@@ -162,7 +163,11 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * (BLOCK_N * NB);
   const int t0 = blockIdx.y * T;
-  const int num_kb = (P.kpad + BLOCK_K - 1) / BLOCK_K;
+  // split-K (small M: too few output tiles to fill 148 SMs): this CTA owns k blocks [kb0, kb0 + num_kb) and adds its partial
+  // tile to dst with fp32 atomics (dst zeroed by the launcher; bias / residual applied by split 0)
+  const int total_kb = (P.kpad + BLOCK_K - 1) / BLOCK_K;
+  const int kb0 = blockIdx.z * P.kb_per_split;
+  const int num_kb = (total_kb - kb0 < P.kb_per_split) ? total_kb - kb0 : P.kb_per_split;
 
   __shared__ float nf4_lut[16];  // constant memory serialises divergent indices; shared memory broadcasts per bank
   if (threadIdx.x >= 32 && threadIdx.x < 48) nf4_lut[threadIdx.x - 32] = NS_NF4_LUT[threadIdx.x - 32];
@@ -204,20 +209,20 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
       const int pre = num_kb < SP ? num_kb : SP;
       for (int kb = 0; kb < pre; ++kb) {
         mbar_expect_tx(&p_full[kb], PACKED_STAGE);
-        tma_load_2d(packed + kb * PACKED_STAGE, &tmap_w, kb * ROW_BYTES, n0, &p_full[kb]);
+        tma_load_2d(packed + kb * PACKED_STAGE, &tmap_w, (kb0 + kb) * ROW_BYTES, n0, &p_full[kb]);
       }
       pdl_wait();  // activations were written by the preceding kernel
       for (int kb = 0; kb < num_kb; ++kb) {
         const int sa = kb % SA;
         if (kb >= SA) mbar_wait(&a_empty[sa], ((kb / SA) - 1) & 1);
         mbar_expect_tx(&a_full[sa], L::ACT_STAGE);
-        tma_load_2d(act + sa * L::ACT_STAGE, &tmap_a, kb * BLOCK_K, t0, &a_full[sa]);
+        tma_load_2d(act + sa * L::ACT_STAGE, &tmap_a, (kb0 + kb) * BLOCK_K, t0, &a_full[sa]);
         const int kp = kb + SP;  // keep the packed ring SP blocks ahead
         if (kp < num_kb) {
           const int sp = kp % SP;
           mbar_wait(&p_empty[sp], ((kp / SP) - 1) & 1);
           mbar_expect_tx(&p_full[sp], PACKED_STAGE);
-          tma_load_2d(packed + sp * PACKED_STAGE, &tmap_w, kp * ROW_BYTES, n0, &p_full[sp]);
+          tma_load_2d(packed + sp * PACKED_STAGE, &tmap_w, (kb0 + kp) * ROW_BYTES, n0, &p_full[sp]);
         }
       }
     }
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
     for (int kb = 0; kb < num_kb; ++kb) {
       const int sp = kb % SP, sd = kb % SD;
       // group scale / zero point of the two 32-element halves of this k block
-      int g0 = (kb * BLOCK_K) / P.group, g1 = (kb * BLOCK_K + 32) / P.group;
+      int g0 = ((kb0 + kb) * BLOCK_K) / P.group, g1 = ((kb0 + kb) * BLOCK_K + 32) / P.group;
       if (g0 >= P.ngroups) g0 = P.ngroups - 1;
       if (g1 >= P.ngroups) g1 = P.ngroups - 1;
       const float sc0 = ns_scale_at(rowp + P.sc_off, P.stype, g0);
@@ -348,10 +353,14 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
         const int t = t0 + c0 + j;
         if (nvalid && t < P.m) {
           const size_t o = (size_t)t * P.ldo + nrow;
-          float x = __uint_as_float(v[j]) + bcast_bias;
-          if (P.bias && !P.bias_bcast) x += P.bias[o];
-          if (P.residual) x += P.residual[o];
-          P.dst[o] = x;
+          float x = __uint_as_float(v[j]);
+          if (blockIdx.z == 0) {
+            x += bcast_bias;
+            if (P.bias && !P.bias_bcast) x += P.bias[o];
+            if (P.residual) x += P.residual[o];
+          }
+          if (gridDim.z > 1) atomicAdd(P.dst + o, x);
+          else P.dst[o] = x;
         }
       }
     }
@@ -404,7 +413,23 @@ int launch_t(const CUtensorMap& mw, const CUtensorMap& ma, const GemmParams& P, 
     attr_set = true;
   }
   dim3 grid((P.n + BLOCK_N * NB - 1) / (BLOCK_N * NB), (P.m + T - 1) / T);
-  NS_CUDA_TRY(ns_launch_pdl(kern, grid, dim3(L::kThreads), (size_t)L::total, st, mw, ma, P));
+  GemmParams Q = P;
+  const int total_kb = (P.kpad + BLOCK_K - 1) / BLOCK_K;
+  int splits = 1;
+  const int tiles = (int)(grid.x * grid.y);
+  static const int env_splits = getenv("NS_TC_SPLITS") ? atoi(getenv("NS_TC_SPLITS")) : 0;  // tuning aid
+  if (tiles < 96 && P.residual != P.dst && P.bias != P.dst) {
+    splits = ns_num_sms() / tiles;  // floor: one CTA per SM is resident (TMEM + ~100-200 KB smem), a partial second wave doubles the time
+    if (splits > total_kb / 8) splits = total_kb / 8;  // keep >= 8 k blocks (512 k) per slice
+    if (splits > 16) splits = 16;
+    if (splits < 1) splits = 1;
+  }
+  if (env_splits > 0) splits = env_splits;
+  Q.kb_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + Q.kb_per_split - 1) / Q.kb_per_split;
+  grid.z = (unsigned)splits;
+  if (splits > 1) NS_CUDA_TRY(cudaMemset2DAsync(P.dst, (size_t)P.ldo * 4, 0, (size_t)P.n * 4, (size_t)P.m, st));
+  NS_CUDA_TRY(ns_launch_pdl(kern, grid, dim3(L::kThreads), (size_t)L::total, st, mw, ma, Q));
   ns_count_launch();
   return NS_OK;
 }
