@@ -539,7 +539,9 @@ static void* pick_ws(void* workspace, cudaStream_t st, size_t bytes) { return wo
 static bool use_tc(const ns_weight* w, int m, int flags) {
   if (flags & NS_MM_FORCE_GEMV) return false;
   if (!ns_gemm_tc_supported(w)) return false;
-  return m > 4 || (flags & NS_MM_FORCE_TC);
+  // Measured on 4096x4096 Q4_0 (profiles/r01_summary.md): the tensor-core GEMM costs ~30 us at small M (pipeline fill, split-K
+  // epilogue) while a 4-row GEMV tile costs ~7 us and keeps the exact-integer numerics: GEMV tiles win up to 16 rows.
+  return m > 16 || (flags & NS_MM_FORCE_TC);
 }
 static size_t ws_need(const ns_weight* w, int m, bool tc) {
   return tc ? ns_gemm_tc_workspace_bytes(m, w->kpad) : ns_act_workspace_bytes(4, w->kpad);
@@ -570,7 +572,7 @@ extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* 
   void* ws = pick_ws(workspace, st, ws_need(w, m, tc));
   if (!ws) return NS_E_CUDA;
   if (tc) {
-    // M > 4: tcgen05 tensor-core GEMM, bf16 numerics (the reference switches from GEMV to GEMM at M > 4 as well)
+    // M > 16: tcgen05 tensor-core GEMM, bf16 numerics (the reference switches from its GEMV to the blocked GEMM at M > 4)
     if (int rc = ns_launch_act_bf16(w, act, lda, m, ws, st)) return rc;
     return ns_launch_gemm_tc(w, ws, dst, ldo, m, bias, bcast, residual, st);
   }
