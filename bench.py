@@ -323,11 +323,12 @@ def run_ours(args):
         else:
             step_calls()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, collective=True):
+        """device time of `steps` calls; collective=True: every rank calls this (barrier before, max over ranks after)"""
         for _ in range(warmup):
             fn()
         L.bestla_device_sync(queue)
-        if world > 1:
+        if world > 1 and collective:
             import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
@@ -339,7 +340,7 @@ def run_ours(args):
         e1.synchronize()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        if world > 1:
+        if world > 1 and collective:
             import torch.distributed as dist
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -391,7 +392,7 @@ def run_ours(args):
         prefill_calls()
         L.bestla_device_sync(queue)
         psteps = max(2, min(5, args.steps))
-        ms_pf = timed(prefill_calls, psteps, 1)
+        ms_pf = timed(prefill_calls, psteps, 1, collective=False)  # rank 0 only: no collectives in here
         flops = 2.0 * MP * sum(w.n * w.k for lay in layers for w in lay.values())
         tf = flops / (ms_pf * 1e-3) / 1e12
         tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))

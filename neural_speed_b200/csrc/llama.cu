@@ -205,22 +205,23 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const float* __restr
   }
 }
 
-// Decode-shaped attention for head sizes 64 / 128: 8 warps per (head, token); a warp streams whole K/V rows (one 4- or 8-byte
+// Decode-shaped attention for head sizes 64 / 128: kAW warps per (head, token); a warp streams whole K/V rows (one 4- or 8-byte
 // load per lane), four rows in flight; with FUSE (single new token) the kernel also applies RoPE to its q head and to the
 // new k row and appends k,v to the cache, so rope_kv_kernel is not launched.
+constexpr int kAW = 16;  // warps per CTA: the kernel is a chain of dependent cache-row loads, more warps = more rows in flight
 template <int HD, bool FUSE>
-__global__ void __launch_bounds__(256) attn_fast_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ knew, int ldk,
+__global__ void __launch_bounds__(kAW * 32) attn_fast_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ knew, int ldk,
                                                         const float* __restrict__ vnew, int ldv, __half* __restrict__ kc,
                                                         __half* __restrict__ vc, const int* __restrict__ state, float* __restrict__ out, int ldo,
                                                         int n_head, int n_head_kv, int n_ctx, float scale, float theta_scale,
                                                         float freq_scale) {
   constexpr int EPL = HD / 32;  // elements per lane
-  extern __shared__ float sm[];  // [HD] q | [HD] new k | [HD] new v | [8][HD] partial out | [n_ctx] scores
+  extern __shared__ float sm[];  // [HD] q | [HD] new k | [HD] new v | [kAW][HD] partial out | [n_ctx] scores
   float* sq = sm;
   float* sk = sm + HD;
   float* sv = sm + 2 * HD;
   float* part = sm + 3 * HD;
-  float* sc = sm + 3 * HD + 8 * HD;
+  float* sc = sm + 3 * HD + kAW * HD;
   pdl_launch_dependents();
   pdl_wait();
   const int h = blockIdx.x, t = blockIdx.y;
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(256) attn_fast_kernel(const float* __restrict_
     }
   };
   // pass 1: scores
-  for (int i0 = warp * 4; i0 < ncache; i0 += 32) {
+  for (int i0 = warp * 4; i0 < ncache; i0 += kAW * 4) {
     float kr[4][EPL];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(256) attn_fast_kernel(const float* __restrict_
     if (lane == 0) sc[len - 1] = acc * scale;
   }
   __syncthreads();
-  __shared__ float red[8];
+  __shared__ float red[kAW];
   __shared__ float bcast;
   float lmax = -INFINITY;
   for (int i = threadIdx.x; i < len; i += blockDim.x) lmax = fmaxf(lmax, sc[i]);
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(256) attn_fast_kernel(const float* __restrict_
   __syncthreads();
   if (threadIdx.x == 0) {
     float m = red[0];
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    for (int i = 1; i < kAW; ++i) m = fmaxf(m, red[i]);
     bcast = m;
   }
   __syncthreads();
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(256) attn_fast_kernel(const float* __restrict_
   __syncthreads();
   if (threadIdx.x == 0) {
     float s2 = 0.f;
-    for (int i = 0; i < 8; ++i) s2 += red[i];
+    for (int i = 0; i < kAW; ++i) s2 += red[i];
     bcast = 1.f / s2;
   }
   __syncthreads();
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(256) attn_fast_kernel(const float* __restrict_
   float acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-  for (int i0 = warp * 4; i0 < ncache; i0 += 32) {
+  for (int i0 = warp * 4; i0 < ncache; i0 += kAW * 4) {
     float vr[4][EPL];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(256) attn_fast_kernel(const float* __restrict_
   for (int d = threadIdx.x; d < HD; d += blockDim.x) {
     float s2 = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s2 += part[w * HD + d];
+    for (int w = 0; w < kAW; ++w) s2 += part[w * HD + d];
     out[(size_t)t * ldo + (size_t)h * HD + d] = s2;
   }
 }
@@ -651,7 +652,7 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
     NS_CUDA_TRY(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
     attn_attr = attn_smem;
   }
-  const size_t fast_smem = (size_t)(11 * hd + hp.n_ctx) * sizeof(float);
+  const size_t fast_smem = (size_t)((3 + kAW) * hd + hp.n_ctx) * sizeof(float);
   if (fast_smem > 48 * 1024) {
     static size_t fast_attr = 0;
     if (fast_smem > 220 * 1024) {
@@ -683,7 +684,7 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
     const bool fast = (hd == 128 || hd == 64);
     if (fast && m == 1) {  // rope + KV append + attention in one launch
       auto kern = hd == 128 ? attn_fast_kernel<128, true> : attn_fast_kernel<64, true>;
-      NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)hp.n_head, 1u), dim3(256), fast_smem, st, (const float*)q, E, (const float*)k, kvd,
+      NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)hp.n_head, 1u), dim3(kAW * 32), fast_smem, st, (const float*)q, E, (const float*)k, kvd,
                                 (const float*)v, kvd, kc, vc, (const int*)c->state, c->attn, E, hp.n_head, hp.n_head_kv, hp.n_ctx,
                                 attn_scale, theta_scale, freq_scale));
       ns_count_launch();
@@ -694,7 +695,7 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
       ns_count_launch();
       if (fast) {
         auto kern = hd == 128 ? attn_fast_kernel<128, false> : attn_fast_kernel<64, false>;
-        NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)hp.n_head, (unsigned)m), dim3(256), fast_smem, st, (const float*)q, E,
+        NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)hp.n_head, (unsigned)m), dim3(kAW * 32), fast_smem, st, (const float*)q, E,
                                   (const float*)k, kvd, (const float*)v, kvd, kc, vc, (const int*)c->state, c->attn, E, hp.n_head,
                                   hp.n_head_kv, hp.n_ctx, attn_scale, theta_scale, freq_scale));
       } else {

@@ -20,6 +20,13 @@ from dataclasses import dataclass
 
 import numpy as np
 
+def current_queue(torch):
+    """torch's current CUDA stream as a libns_b200 queue.  The legacy default stream has handle 0, which the C ABI reads as
+    "use the library's own stream" -- work would then race with torch ops; cudaStreamLegacy (0x1) names it explicitly."""
+    h = torch.cuda.current_stream().cuda_stream
+    return C.c_void_p(h if h else 1)
+
+
 SPLIT_N = "n"   # reference TP_1D_ROW
 SPLIT_K = "k"   # reference TP_1D_COLUMN
 
@@ -141,7 +148,7 @@ class TPContext:
         if (comm is not None and t.is_cuda and t.dtype == self.torch.float32 and t.is_contiguous() and t.numel() <= self._comm_max
                 and t.numel() % 4 == 0):
             from . import lib, last_error
-            q = self._comm_queue if self._comm_queue is not None else C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+            q = self._comm_queue if self._comm_queue is not None else current_queue(self.torch)
             rc = lib().ns_comm_all_reduce_f32(comm, C.c_void_p(t.data_ptr()), t.numel(),
                                               C.c_void_p(residual.data_ptr()) if residual is not None else None, q)
             if rc != 0:
@@ -189,7 +196,7 @@ class TPLlamaMatmuls:
         torch, p, lay = self.torch, self.plan, self.layers[li]
         m = x.shape[0]
         b = self._buffers(m, x.device)
-        queue = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        queue = current_queue(torch)
         q, k, v = b["q"], b["k"], b["v"]
         for wt, dst in ((lay["wq"], q), (lay["wk"], k), (lay["wv"], v)):   # GQA: n differs, so three plain matmuls
             mul_mat(wt, x.data_ptr(), p.n_embd, dst.data_ptr(), dst.shape[1], m, queue=queue)
