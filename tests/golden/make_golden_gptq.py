@@ -39,20 +39,16 @@ def reference_canonical(qweight, scales, qzeros, g_idx, q_config):
                                                             torch.from_numpy(qzeros), q_config)
     int_weight = int_weight.view(-1, int_weight.shape[-1])
     if q_config.get("desc_act"):
-        gi = torch.from_numpy(g_idx)
-        int_weight2 = int_weight.clone()
+        # the act-order step of convert_q4_bestla_tensor (common.py:667-683), driven row by row exactly as the reference does:
+        # row i goes to the next free slot of its group g_idx[i]
         group_size = q_config["group_size"]
-        group_dict = {}
-        for i in range(len(gi)):
-            group_idx = gi[i].item()
-            if group_idx not in group_dict:
-                target_idx = group_idx * group_size
-                group_dict[group_idx] = 0
-            else:
-                group_dict[group_idx] = group_dict[group_idx] + 1
-                target_idx = group_idx * group_size + group_dict[group_idx]
-            int_weight2[target_idx] = int_weight[i]
-        int_weight = int_weight2
+        filled = {}
+        regrouped = int_weight.clone()
+        for i, grp in enumerate(g_idx.tolist()):
+            slot = filled.get(grp, 0)
+            regrouped[grp * group_size + slot] = int_weight[i]
+            filled[grp] = slot + 1
+        int_weight = regrouped
     if q_config["bits"] == 4:
         int_weight = int_weight - 8
         gptq_zeros = gptq_zeros - 8
