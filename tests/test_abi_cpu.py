@@ -155,3 +155,29 @@ def test_packweight_copyattr_matches_direct_quantisation():
         ns.lib().bestla_packweight_copyattr(w_kn.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), n, k, n,
                                             src.ctypes.data_as(C.c_void_p))
         assert dst.size == want.size and np.array_equal(dst, want), (alg, sdt, cdt, g)
+
+
+def test_public_header_is_plain_c_and_matches_the_ctypes_structs(tmp_path):
+    """include/ns_b200.h is the drop-in boundary: it must compile as C99 (what cgo / JNI / ctypes-gen consume) and as C++, and
+    the struct the Python binding passes by pointer must have the header's layout."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc missing")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ns_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(ns_llama_hparams), offsetof(ns_llama_hparams, n_vocab),'
+                   ' offsetof(ns_llama_hparams, n_ctx), offsetof(ns_llama_hparams, norm_eps), offsetof(ns_llama_hparams, rope_scale));'
+                   'return 0;}\n')
+    inc = os.path.join(ROOT, "include")
+    exe = tmp_path / "t"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    H = ns.LlamaHParams
+    assert got == [C.sizeof(H), H.n_vocab.offset, H.n_ctx.offset, H.norm_eps.offset, H.rope_scale.offset]
+    if shutil.which("g++"):
+        r = subprocess.run(["g++", "-std=c++14", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
