@@ -34,7 +34,8 @@ BTLA_BF16 = 16 | (1 << 16)
 def build(force: bool = False) -> None:
     """Compile liboracle.so and (when /root/reference exists) oracle/_ref/."""
     need = force or not os.path.exists(os.path.join(_HERE, "liboracle.so"))
-    if os.path.isdir("/root/reference/neural_speed") and not os.path.exists(os.path.join(_HERE, "_ref", "libref_btla.so")):
+    if os.path.isdir("/root/reference/neural_speed") and not all(
+            os.path.exists(os.path.join(_HERE, "_ref", f)) for f in ("libref_ggml.so", "libref_btla.so", "libref_ne.so")):
         need = True
     if need:
         subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
@@ -43,6 +44,37 @@ def build(force: bool = False) -> None:
 _lib = None
 _ref_ggml = None
 _ref_btla = None
+_ref_ne = None
+
+
+def ref_ne():
+    """The reference's graph engine (core/ne_layers.c through its public API; oracle/_ref/libref_ne.so) or None."""
+    global _ref_ne
+    if _ref_ne is None:
+        p = os.path.join(_HERE, "_ref", "libref_ne.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if not os.path.exists(p):
+            return None
+        L = C.CDLL(p)
+        L.ref_ne_rope.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+        L.ref_ne_soft_max.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_ne_rms_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float]
+        L.ref_ne_attn_1tok.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]
+        for f in (L.ref_ne_rope, L.ref_ne_soft_max, L.ref_ne_rms_norm, L.ref_ne_attn_1tok):
+            f.restype = None
+        L.ref_ne_llama_create.restype = C.c_void_p
+        L.ref_ne_llama_create.argtypes = [C.c_int] * 6 + [C.c_float] * 3
+        L.ref_ne_llama_set.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        L.ref_ne_llama_eval.restype = None
+        L.ref_ne_llama_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_ne_llama_free.restype = None
+        L.ref_ne_llama_free.argtypes = [C.c_void_p]
+        _ref_ne = L
+    return _ref_ne
 
 
 def lib():
@@ -404,3 +436,42 @@ def f32_to_bf16_bits(x):
 
 def bf16_bits_to_f32(b):
     return (np.asarray(b, np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+class RefNeLlama:
+    """A Llama model evaluated by the REFERENCE's own graph engine (oracle/ref_ne.c: core/ne_layers.c through the public ne_*
+    API, graph of models/llama/llama.cpp).  Same constructor arguments as oracle.llama_model.OracleLlama (n_head == n_head_kv,
+    Q4_0 weights).  Only available where oracle/_ref was built (needs /root/reference)."""
+
+    NAMES = ["attn_norm", "wq", "wk", "wv", "wo", "ffn_norm", "w1", "w2", "w3"]
+
+    def __init__(self, hp, tok_embd, out_norm, output_rows, layers):
+        L = ref_ne()
+        if L is None:
+            raise RuntimeError("oracle/_ref/libref_ne.so not built")
+        assert hp["n_head"] == hp["n_head_kv"]
+        self.L, self.n_vocab = L, hp["n_vocab"]
+        self.h = C.c_void_p(L.ref_ne_llama_create(hp["n_vocab"], hp["n_embd"], hp["n_head"], hp["n_layer"], hp["n_ff"], hp["n_ctx"],
+                                                  hp.get("norm_eps", 1e-6), hp.get("rope_theta", 10000.0), hp.get("rope_scale", 1.0)))
+
+        def put(layer, which, arr, dt):
+            a = _c(arr, dt)
+            assert L.ref_ne_llama_set(self.h, layer, which, _p(a), a.nbytes) == 0, (layer, which, a.nbytes)
+
+        put(0, -1, tok_embd, np.float32)
+        put(0, -2, out_norm, np.float32)
+        put(0, -3, output_rows, np.uint8)
+        for il, lay in enumerate(layers):
+            for j, name in enumerate(self.NAMES):
+                put(il, j, lay[name], np.float32 if "norm" in name else np.uint8)
+
+    def eval(self, tokens, n_past):
+        t = _c(tokens, np.int32)
+        logits = np.zeros(self.n_vocab, np.float32)
+        self.L.ref_ne_llama_eval(self.h, _p(t), t.size, n_past, _p(logits))
+        return logits
+
+    def close(self):
+        if self.h:
+            self.L.ref_ne_llama_free(self.h)
+            self.h = None

@@ -64,6 +64,62 @@ def main():
         as8, ass = oracle.btla_quantize_act_s8(a2, g, "ref")
         d[f"act_s8_g{g}_q"], d[f"act_s8_g{g}_sc"] = as8, ass
     np.savez_compressed(os.path.join(HERE, "btla_quant.npz"), **d)
+
+    # ---- element-wise ops of the Llama eval graph, from the reference's own engine (oracle/_ref/libref_ne.so = core/ne_layers.c)
+    import ctypes as C
+    ne = oracle.ref_ne()
+    assert ne is not None
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rl = np.random.default_rng(777)
+    g = {}
+    hd, H, T, n_past = 64, 3, 2, 9
+    x = rl.normal(0, 1, (T, H, hd)).astype(np.float32)
+    y = x.copy()
+    ne.ref_ne_rope(vp(y), hd, H, T, n_past, 10000.0, 1.0)
+    g["rope_x"], g["rope_y"], g["rope_cfg"] = x, y, np.array([hd, H, T, n_past], np.int32)
+    s = rl.normal(0, 3, (3, 77)).astype(np.float32)
+    sm = s.copy()
+    ne.ref_ne_soft_max(vp(sm), 77, 3)
+    g["softmax_x"], g["softmax_y"] = s, sm
+    xr = rl.normal(0, 2, (2, 512)).astype(np.float32)
+    yr = np.zeros_like(xr)
+    ne.ref_ne_rms_norm(vp(xr), vp(yr), 512, 2, 1e-5)
+    g["rms_x"], g["rms_y"] = xr, yr
+    Ha, hda, ln = 2, 128, 45
+    q = rl.normal(0, 1, (Ha, hda)).astype(np.float32)
+    kc = rl.normal(0, 1, (Ha, ln, hda)).astype(np.float16)
+    vc = rl.normal(0, 1, (Ha, ln, hda)).astype(np.float16)
+    out = np.zeros((Ha, hda), np.float32)
+    ne.ref_ne_attn_1tok(vp(q), vp(kc), vp(np.ascontiguousarray(vc.transpose(0, 2, 1))), vp(out), hda, Ha, ln,
+                        float(np.float32(1.0) / np.float32(np.sqrt(np.float32(hda)))))
+    g["attn_q"], g["attn_k"], g["attn_v"], g["attn_out"] = q, kc, vc, out
+    np.savez_compressed(os.path.join(HERE, "llama_ops.npz"), **g)
+
+    # ---- a tiny Llama evaluated by the reference's engine (graph of models/llama/llama.cpp; oracle.RefNeLlama): logits of a
+    # 4-token prompt and of three single-token steps
+    rm = np.random.default_rng(4242)
+    hp = dict(n_vocab=96, n_embd=128, n_head=2, n_head_kv=2, n_layer=2, n_ff=192, n_ctx=16, norm_eps=1e-5, rope_theta=10000.0,
+              rope_scale=1.0)
+    E, FF, V = hp["n_embd"], hp["n_ff"], hp["n_vocab"]
+    qw = lambda n, k: oracle.quantize_q4_0(rm.normal(0, 1.0 / np.sqrt(k), (n, k)).astype(np.float32), "ref")
+    mdl = dict(tok=rm.normal(0, 1, (V, E)).astype(np.float32), out_norm=rm.uniform(0.5, 1.5, E).astype(np.float32), output=qw(V, E))
+    layers = []
+    for il in range(hp["n_layer"]):
+        L = dict(attn_norm=rm.uniform(0.5, 1.5, E).astype(np.float32), ffn_norm=rm.uniform(0.5, 1.5, E).astype(np.float32),
+                 wq=qw(E, E), wk=qw(E, E), wv=qw(E, E), wo=qw(E, E), w1=qw(FF, E), w2=qw(E, FF), w3=qw(FF, E))
+        layers.append(L)
+        for k2, v2 in L.items():
+            mdl[f"l{il}.{k2}"] = v2
+    ref = oracle.RefNeLlama(hp, mdl["tok"], mdl["out_norm"], mdl["output"], layers)
+    steps = [[1, 40, 7, 91], [13], [55], [2]]
+    pos = 0
+    for i, t in enumerate(steps):
+        mdl[f"logits{i}"] = ref.eval(t, pos)
+        mdl[f"tokens{i}"] = np.array(t, np.int32)
+        pos += len(t)
+    ref.close()
+    mdl["hp"] = np.array([hp[k2] for k2 in ("n_vocab", "n_embd", "n_head", "n_head_kv", "n_layer", "n_ff", "n_ctx")], np.int32)
+    np.savez_compressed(os.path.join(HERE, "llama_tiny.npz"), **mdl)
     print("wrote", sorted(os.listdir(HERE)))
 
 

@@ -45,3 +45,37 @@ def test_btla_quant_golden(g):
     assert np.array_equal(q, z[f"act_u8_g{g}_q"]) and np.array_equal(sc, z[f"act_u8_g{g}_sc"]) and np.array_equal(zp, z[f"act_u8_g{g}_zp"])
     q, sc = oracle.btla_quantize_act_s8(a, g)
     assert np.array_equal(q, z[f"act_s8_g{g}_q"]) and np.array_equal(sc, z[f"act_s8_g{g}_sc"])
+
+
+def test_llama_elementwise_ops_golden():
+    """rope / soft_max / rms_norm / single-token attention of the Llama eval graph: the numpy restatement in
+    oracle/llama_model.py against outputs of the reference's own engine (tests/golden/llama_ops.npz)"""
+    from oracle import llama_model as lm
+    z = np.load(os.path.join(G, "llama_ops.npz"))
+    hd, H, T, n_past = (int(v) for v in z["rope_cfg"])
+    got = np.stack([lm.rope_mode0(z["rope_x"][t], n_past + t, hd) for t in range(T)])
+    assert np.array_equal(got, z["rope_y"])
+    assert np.array_equal(np.stack([lm.soft_max_f16table(r) for r in z["softmax_x"]]), z["softmax_y"])
+    assert np.array_equal(lm.rms_norm(z["rms_x"], 1e-5), z["rms_y"])
+    q, kc, vc = z["attn_q"], z["attn_k"], z["attn_v"]
+    scale = np.float32(1.0) / np.float32(np.sqrt(np.float32(q.shape[1])))
+    for h in range(q.shape[0]):
+        s = lm.vec_dot_f16_rows(kc[h].astype(np.float32), lm._f16(q[h])) * scale
+        p = lm.soft_max_f16table(s)
+        assert np.array_equal(lm.vec_dot_f16_rows(np.ascontiguousarray(vc[h].astype(np.float32).T), lm._f16(p)), z["attn_out"][h])
+
+
+def test_llama_tiny_model_golden():
+    """whole eval graph: logits produced by the reference's engine for a tiny Q4_0 Llama (prompt + single-token steps)"""
+    from oracle.llama_model import OracleLlama
+    z = np.load(os.path.join(G, "llama_tiny.npz"))
+    keys = ("n_vocab", "n_embd", "n_head", "n_head_kv", "n_layer", "n_ff", "n_ctx")
+    hp = dict(zip(keys, (int(v) for v in z["hp"])), norm_eps=1e-5, rope_theta=10000.0, rope_scale=1.0)
+    layers = [{k: z[f"l{il}.{k}"] for k in ("attn_norm", "ffn_norm", "wq", "wk", "wv", "wo", "w1", "w2", "w3")}
+              for il in range(hp["n_layer"])]
+    orc = OracleLlama(hp, z["tok"], z["out_norm"], z["output"], layers)
+    pos = 0
+    for i in range(4):
+        t = list(z[f"tokens{i}"])
+        assert np.array_equal(orc.eval(t, pos), z[f"logits{i}"]), i
+        pos += len(t)

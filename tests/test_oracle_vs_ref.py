@@ -171,3 +171,99 @@ def test_q6_K_random_bytes_dot():
     a = r.normal(0, 2.0, (2, k)).astype(np.float32)
     assert np.array_equal(oracle.mul_mat_q6_K_f32(wq, a, "oracle"), oracle.mul_mat_q6_K_f32(wq, a, "ref", nth=1))
     assert np.array_equal(oracle.dequantize_q6_K(wq, k, "oracle"), oracle.dequantize_q6_K(wq, k, "ref"))
+
+
+# ------------------------------------------------------------------------- element-wise ops of the Llama eval graph
+# pinned against the reference's own graph engine (core/ne_layers.c through its public ne_* API, oracle/ref_ne.c)
+ref_n = oracle.ref_ne()
+need_ref_n = pytest.mark.skipif(ref_n is None, reason="oracle/_ref/libref_ne.so not built (no /root/reference)")
+
+
+def _vp(a):
+    import ctypes as C
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@need_ref_n
+@pytest.mark.parametrize("hd", [64, 128])
+def test_llama_rope_mode0_bit_exact(hd):
+    from oracle import llama_model as lm
+    r = _rng(31)
+    for pos in (0, 1, 7, 33, 127, 2047):
+        x = r.normal(0, 1, (3, hd)).astype(np.float32)
+        want = x.copy().reshape(1, 3, hd)
+        ref_n.ref_ne_rope(_vp(want), hd, 3, 1, pos, 10000.0, 1.0)
+        assert np.array_equal(lm.rope_mode0(x, pos, hd), want[0]), pos
+    # several tokens in one call: position n_past + t
+    x = r.normal(0, 1, (2, 3, hd)).astype(np.float32)
+    want = x.copy()
+    ref_n.ref_ne_rope(_vp(want), hd, 3, 2, 10, 10000.0, 1.0)
+    assert np.array_equal(np.stack([lm.rope_mode0(x[t], 10 + t, hd) for t in range(2)]), want)
+
+
+@need_ref_n
+def test_llama_softmax_and_rms_norm_bit_exact():
+    from oracle import llama_model as lm
+    r = _rng(32)
+    for n in (1, 5, 37, 300, 2048):
+        s = r.normal(0, 3, (2, n)).astype(np.float32)
+        want = s.copy()
+        ref_n.ref_ne_soft_max(_vp(want), n, 2)
+        assert np.array_equal(np.stack([lm.soft_max_f16table(row) for row in s]), want)
+    for n, eps in ((256, 1e-5), (4096, 1e-6)):
+        x = r.normal(0, 2, (3, n)).astype(np.float32)
+        want = np.zeros_like(x)
+        ref_n.ref_ne_rms_norm(_vp(x), _vp(want), n, 3, eps)
+        assert np.array_equal(lm.rms_norm(x, eps), want)
+
+
+@need_ref_n
+@pytest.mark.parametrize("n_head,hd,length", [(4, 64, 23), (2, 128, 40), (4, 64, 1), (3, 96, 77), (2, 128, 300)])
+def test_llama_single_token_attention_bit_exact(n_head, hd, length):
+    """K.Q (fp16 K, Q rounded to fp16, SIMD ne_vec_dot_f16) -> scale -> soft_max -> V.P of llama.cpp:286-302"""
+    from oracle import llama_model as lm
+    r = _rng(33 + length)
+    q = r.normal(0, 1, (n_head, hd)).astype(np.float32)
+    kc = r.normal(0, 1, (n_head, length, hd)).astype(np.float16)
+    vc = r.normal(0, 1, (n_head, length, hd)).astype(np.float16)
+    vt = np.ascontiguousarray(vc.transpose(0, 2, 1))      # the reference's V cache is [head][hd][n_ctx]
+    want = np.zeros((n_head, hd), np.float32)
+    scale = float(np.float32(1.0) / np.float32(np.sqrt(np.float32(hd))))
+    ref_n.ref_ne_attn_1tok(_vp(q), _vp(kc), _vp(vt), _vp(want), hd, n_head, length, scale)
+    got = np.zeros_like(want)
+    for h in range(n_head):
+        s = lm.vec_dot_f16_rows(kc[h].astype(np.float32), lm._f16(q[h])) * np.float32(scale)
+        p = lm.soft_max_f16table(s)
+        got[h] = lm.vec_dot_f16_rows(np.ascontiguousarray(vc[h].astype(np.float32).T), lm._f16(p))
+    assert np.array_equal(got, want)
+
+
+def _tiny_llama(seed, n_head=4, n_layer=2):
+    r = _rng(seed)
+    hp = dict(n_vocab=160, n_embd=256, n_head=n_head, n_head_kv=n_head, n_layer=n_layer, n_ff=384, n_ctx=40, norm_eps=1e-5,
+              rope_theta=10000.0, rope_scale=1.0)
+    E, FF, V = hp["n_embd"], hp["n_ff"], hp["n_vocab"]
+    w = lambda n, k: oracle.quantize_q4_0(r.normal(0, 1.0 / np.sqrt(k), (n, k)).astype(np.float32))
+    tok = r.normal(0, 1, (V, E)).astype(np.float32)
+    on = r.uniform(0.5, 1.5, E).astype(np.float32)
+    layers = [dict(attn_norm=r.uniform(0.5, 1.5, E).astype(np.float32), ffn_norm=r.uniform(0.5, 1.5, E).astype(np.float32),
+                   wq=w(E, E), wk=w(E, E), wv=w(E, E), wo=w(E, E), w1=w(FF, E), w2=w(E, FF), w3=w(FF, E)) for _ in range(n_layer)]
+    return hp, tok, on, w(V, E), layers
+
+
+@need_ref_n
+@pytest.mark.parametrize("n_head", [4, 2])
+def test_llama_eval_graph_end_to_end_bit_exact(n_head):
+    """oracle/llama_model.py == the reference's own engine running the graph of models/llama/llama.cpp (Q4_0 weights, fp16 KV
+    cache, prompt evals with the causal mask and single-token steps): logits bit for bit, hence identical greedy ids"""
+    from oracle.llama_model import OracleLlama, greedy
+    hp, tok, on, out, layers = _tiny_llama(50 + n_head, n_head)
+    ref = oracle.RefNeLlama(hp, tok, on, out, layers)
+    orc = OracleLlama(hp, tok, on, out, layers)
+    pos = 0
+    for toks in ([1], [17], [150, 5, 9, 33], [44], [2, 3]):
+        a, b = orc.eval(toks, pos), ref.eval(toks, pos)
+        assert np.array_equal(a, b), (toks, pos, float(np.abs(a - b).max()))
+        assert greedy(a) == int(np.flatnonzero(b == b.max())[0])
+        pos += len(toks)
+    ref.close()
