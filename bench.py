@@ -559,7 +559,11 @@ def run_ours(args):
                        "l2_policy": "inputs (3.7 GB of weights per step) exceed the 126 MB L2; no flush needed",
                        "parallelism": "replicas" if world > 1 else "single"},
             "roofline": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
-                         "traffic": None, "kernel": "gemv_ring_kernel<S8,M=1,sym,f16> (fused Q8_0 activation quantisation)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, averaged over the 903 launches of
+                         # the committed ncu list profiles/r01_launches_bench_final.csv (same command, same synthetic weights; the
+                         # weights are read exactly once: 28.89 MB against 28.81 MB algorithmic); null for other formats / sizes
+                         "traffic": 28891941 if (args.fmt == "q4_0" and n_layers == N_LAYER) else None,
+                         "traffic_source": "ncu launch list, profiles/r01_launches_bench_final.csv", "kernel": "gemv_ring_kernel<S8,M=1,sym,f16> (fused Q8_0 activation quantisation)",
                          "launches_per_step": launches_per_step, "avg_launch_us": ms_step * 1e3 / max(1, launches_per_step),
                          "peak_source": peak_kind, "algorithmic_bytes_per_launch": int(alg_bytes // max(1, launches_per_step)),
                          "note": "the timed region contains only this kernel (129 launches per token, one CUDA graph, PDL)",

@@ -46,6 +46,17 @@ def test_compute_fails_loudly_without_device():
     assert rc == -2  # NS_E_NODEVICE
 
 
+def test_engine_and_comm_fail_loudly_without_device():
+    """the eval step and the NVLink exchange have no CPU implementation either"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        ns.Llama(32, 64, 2, 2, 1, 64, 8)
+    assert not ns.lib().ns_comm_create(0, 2, 1024, None)
+    assert "no CUDA device" in ns.last_error()
+
+
 def test_host_q4_0_quantiser_matches_oracle():
     w = np.random.default_rng(3).normal(0, 0.02, (16, 512)).astype(np.float32)
     w[2, 32:64] = 0
