@@ -33,7 +33,14 @@ os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 os.environ.setdefault("OMP_PROC_BIND", "false")
 
 N_EMBD, N_FF, N_LAYER, N_VOCAB = 4096, 11008, 32, 32000
-METRIC = "decode tokens/s, Llama-2-7B Q4_0, batch=1 (weight-only matmul path)"
+# BASELINE.json's metric, verbatim.  `value` is its first component (decode tokens/s, batch 1, weight-only matmul path); the
+# second (prefill tok/s with the tensor roofline) is reported under "prefill", the % of the HBM roofline under "roofline".
+METRIC = "decode tokens/s + prefill tok/s Llama-2-7B Q4_0 @1 GPU; % HBM roofline"
+try:
+    with open(os.path.join(ROOT, "BASELINE.json")) as _f:
+        METRIC = json.load(_f).get("metric", METRIC)
+except (OSError, ValueError):
+    pass
 
 
 def shapes():
@@ -548,6 +555,7 @@ def run_ours(args):
         scale = n_layers / N_LAYER
         line = {
             "metric": METRIC if args.fmt == "q4_0" else METRIC.replace("Q4_0", "int4 g128 sym"),
+            "value_is": "decode tokens/s (first component of the metric); prefill tok/s is prefill.tokens_per_s",
             "value": world * 1000.0 / ms_step, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8xint4->f32 (q8_0 x q4_0)" if args.fmt == "q4_0" else "u8xint4->f32",
