@@ -67,7 +67,7 @@ def ref_ne():
         for f in (L.ref_ne_rope, L.ref_ne_soft_max, L.ref_ne_rms_norm, L.ref_ne_attn_1tok):
             f.restype = None
         L.ref_ne_llama_create.restype = C.c_void_p
-        L.ref_ne_llama_create.argtypes = [C.c_int] * 6 + [C.c_float] * 3
+        L.ref_ne_llama_create.argtypes = [C.c_int] * 7 + [C.c_float] * 3
         L.ref_ne_llama_set.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.ref_ne_llama_eval.restype = None
         L.ref_ne_llama_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -440,8 +440,8 @@ def bf16_bits_to_f32(b):
 
 class RefNeLlama:
     """A Llama model evaluated by the REFERENCE's own graph engine (oracle/ref_ne.c: core/ne_layers.c through the public ne_*
-    API, graph of models/llama/llama.cpp).  Same constructor arguments as oracle.llama_model.OracleLlama (n_head == n_head_kv,
-    Q4_0 weights).  Only available where oracle/_ref was built (needs /root/reference)."""
+    API, graph of models/llama/llama.cpp).  Same constructor arguments as oracle.llama_model.OracleLlama (Q4_0 weights; GQA
+    through ne_mul_mat's head broadcast).  Only available where oracle/_ref was built (needs /root/reference)."""
 
     NAMES = ["attn_norm", "wq", "wk", "wv", "wo", "ffn_norm", "w1", "w2", "w3"]
 
@@ -449,9 +449,9 @@ class RefNeLlama:
         L = ref_ne()
         if L is None:
             raise RuntimeError("oracle/_ref/libref_ne.so not built")
-        assert hp["n_head"] == hp["n_head_kv"]
         self.L, self.n_vocab = L, hp["n_vocab"]
-        self.h = C.c_void_p(L.ref_ne_llama_create(hp["n_vocab"], hp["n_embd"], hp["n_head"], hp["n_layer"], hp["n_ff"], hp["n_ctx"],
+        self.h = C.c_void_p(L.ref_ne_llama_create(hp["n_vocab"], hp["n_embd"], hp["n_head"], hp["n_head_kv"], hp["n_layer"], hp["n_ff"],
+                                                  hp["n_ctx"],
                                                   hp.get("norm_eps", 1e-6), hp.get("rope_theta", 10000.0), hp.get("rope_scale", 1.0)))
 
         def put(layer, which, arr, dt):

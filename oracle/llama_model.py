@@ -10,11 +10,10 @@ the reference's Llama eval graph, models/llama/llama.cpp:190-720, ggml (non-fuse
 Parity status: PINNED.  The matmuls are the pinned C oracle (bit-exact with oracle/_ref/libref_ggml.so); rope_mode0,
 soft_max_f16table, rms_norm and the fp16 dot products are bit-exact with the reference's own graph engine (oracle/ref_ne.c compiles
 core/ne_layers.c in place and drives it through the public ne_* API), and OracleLlama.eval reproduces, bit for bit, the logits that
-engine computes for the graph of models/llama/llama.cpp (prompt evals with the causal mask and single-token steps, n_head ==
-n_head_kv) -- tests/test_oracle_vs_ref.py, fixtures tests/golden/llama_ops.npz and llama_tiny.npz.  One stub sits under the
+engine computes for the graph of models/llama/llama.cpp (prompt evals with the causal mask and single-token steps, MHA and GQA)
+-- tests/test_oracle_vs_ref.py, fixtures tests/golden/llama_ops.npz and llama_tiny.npz.  One stub sits under the
 engine: bestla_layernormalization is served by the reference's portable kernel_ref.h body (its AVX2 / AVX-512 bodies need xbyak to
-build; they vectorise the same sum).  GQA (n_head != n_head_kv) is an extension of the same code that the reference only runs
-through its fused-attention kernels and is not covered by the pin.  The GPU engine is held to the north-star tolerance against
+build; they vectorise the same sum).  The GPU engine is held to the north-star tolerance against
 this oracle (1e-2 on logits, greedy ids equal wherever the top-2 margin exceeds that tolerance).
 """
 import ctypes as C

@@ -156,20 +156,23 @@ REF_API void ref_ne_attn_1tok(const float* q, const uint16_t* kc, const uint16_t
 /* ---- a whole Llama eval through the reference's engine ----------------------------------------------------------------
  * The graph of models/llama/llama.cpp:190-720 for ggml-type weights, batch 1, n_head == n_head_kv, the non-fused attention
  * path (:362-420 KV append, :286-302 shape of the K.Q / soft_max / V.P chain), built node by node with the public API and
- * executed by ne_graph_compute.  Weights are Q4_0 rows (NE_TYPE_Q4_0 tensors: the ggml mul_mat path of ne_layers.c:7085);
+ * executed by ne_graph_compute.  n_head_kv < n_head (GQA) relies on ne_mul_mat's head broadcast (ne_can_mul_mat,
+ * ne_layers.c:618-623: consecutive query heads share a KV head).  Weights are Q4_0 rows (NE_TYPE_Q4_0 tensors: the ggml mul_mat path of ne_layers.c:7085);
  * norms and the embedding table fp32; KV cache fp16, K as [hd, n_ctx, head], V transposed [n_ctx, hd, head]. */
 typedef struct ref_ne_llama {
-  int n_vocab, n_embd, n_head, n_layer, n_ff, n_ctx;
+  int n_vocab, n_embd, n_head, n_head_kv, n_layer, n_ff, n_ctx;
   float eps, freq_base, freq_scale;
   struct ne_context* wctx; /* weights + KV cache */
   struct ne_tensor *tok, *out_norm, *output, *kc, *vc;
   struct ne_tensor** lw; /* per layer: attn_norm, wq, wk, wv, wo, ffn_norm, w1, w2, w3 */
 } ref_ne_llama;
 
-REF_API ref_ne_llama* ref_ne_llama_create(int n_vocab, int n_embd, int n_head, int n_layer, int n_ff, int n_ctx, float eps,
-                                          float freq_base, float freq_scale) {
+REF_API ref_ne_llama* ref_ne_llama_create(int n_vocab, int n_embd, int n_head, int n_head_kv, int n_layer, int n_ff, int n_ctx,
+                                          float eps, float freq_base, float freq_scale) {
   ref_ne_llama* m = (ref_ne_llama*)calloc(1, sizeof(*m));
-  m->n_vocab = n_vocab, m->n_embd = n_embd, m->n_head = n_head, m->n_layer = n_layer, m->n_ff = n_ff, m->n_ctx = n_ctx;
+  m->n_vocab = n_vocab, m->n_embd = n_embd, m->n_head = n_head, m->n_head_kv = n_head_kv, m->n_layer = n_layer, m->n_ff = n_ff;
+  m->n_ctx = n_ctx;
+  const int kvd = n_embd / n_head * n_head_kv;
   m->eps = eps, m->freq_base = freq_base, m->freq_scale = freq_scale;
   size_t bytes = (size_t)n_vocab * n_embd * 4 + (size_t)n_vocab * n_embd + (size_t)n_layer * ((size_t)4 * n_embd * n_embd + (size_t)3 * n_embd * n_ff) +
                  (size_t)n_layer * n_ctx * n_embd * 4 + (64u << 20);
@@ -177,15 +180,16 @@ REF_API ref_ne_llama* ref_ne_llama_create(int n_vocab, int n_embd, int n_head, i
   m->tok = ne_new_tensor_2d(m->wctx, NE_TYPE_F32, n_embd, n_vocab, NE_SIZE_CALC, NE_BACKEND_CPU);
   m->out_norm = ne_new_tensor_1d(m->wctx, NE_TYPE_F32, n_embd, NE_SIZE_CALC, NE_BACKEND_CPU);
   m->output = ne_new_tensor_2d(m->wctx, NE_TYPE_Q4_0, n_embd, n_vocab, NE_SIZE_CALC, NE_BACKEND_CPU);
-  m->kc = ne_new_tensor_1d(m->wctx, NE_TYPE_F16, (int64_t)n_layer * n_ctx * n_embd, NE_SIZE_CALC, NE_BACKEND_CPU);
-  m->vc = ne_new_tensor_1d(m->wctx, NE_TYPE_F16, (int64_t)n_layer * n_ctx * n_embd, NE_SIZE_CALC, NE_BACKEND_CPU);
+  m->kc = ne_new_tensor_1d(m->wctx, NE_TYPE_F16, (int64_t)n_layer * n_ctx * kvd, NE_SIZE_CALC, NE_BACKEND_CPU);
+  m->vc = ne_new_tensor_1d(m->wctx, NE_TYPE_F16, (int64_t)n_layer * n_ctx * kvd, NE_SIZE_CALC, NE_BACKEND_CPU);
   memset(m->kc->data, 0, ne_nbytes(m->kc));
   memset(m->vc->data, 0, ne_nbytes(m->vc));
   m->lw = (struct ne_tensor**)calloc((size_t)n_layer * 9, sizeof(struct ne_tensor*));
   for (int il = 0; il < n_layer; ++il) {
     struct ne_tensor** w = m->lw + il * 9;
     w[0] = ne_new_tensor_1d(m->wctx, NE_TYPE_F32, n_embd, NE_SIZE_CALC, NE_BACKEND_CPU);
-    for (int j = 1; j <= 4; ++j) w[j] = ne_new_tensor_2d(m->wctx, NE_TYPE_Q4_0, n_embd, n_embd, NE_SIZE_CALC, NE_BACKEND_CPU);
+    for (int j = 1; j <= 4; ++j)
+      w[j] = ne_new_tensor_2d(m->wctx, NE_TYPE_Q4_0, n_embd, (j == 2 || j == 3) ? kvd : n_embd, NE_SIZE_CALC, NE_BACKEND_CPU);
     w[5] = ne_new_tensor_1d(m->wctx, NE_TYPE_F32, n_embd, NE_SIZE_CALC, NE_BACKEND_CPU);
     w[6] = ne_new_tensor_2d(m->wctx, NE_TYPE_Q4_0, n_embd, n_ff, NE_SIZE_CALC, NE_BACKEND_CPU);
     w[7] = ne_new_tensor_2d(m->wctx, NE_TYPE_Q4_0, n_ff, n_embd, NE_SIZE_CALC, NE_BACKEND_CPU);
@@ -207,7 +211,8 @@ REF_API void ref_ne_llama_free(ref_ne_llama* m) {
 }
 
 REF_API void ref_ne_llama_eval(ref_ne_llama* m, const int* tokens, int N, int n_past, float* logits_last) {
-  const int n_embd = m->n_embd, n_head = m->n_head, hd = n_embd / n_head, n_ctx = m->n_ctx, n_ff = m->n_ff;
+  const int n_embd = m->n_embd, n_head = m->n_head, n_head_kv = m->n_head_kv, hd = n_embd / n_head, n_ctx = m->n_ctx, n_ff = m->n_ff;
+  const int kvd = hd * n_head_kv;
   struct ne_context* ctx0 = ref_ne_ctx((size_t)N * ((size_t)n_embd * 64 + (size_t)n_ff * 16 + (size_t)n_ctx * n_head * 16) * m->n_layer +
                                        (size_t)m->n_vocab * 8 + (256u << 20));
   struct ne_cgraph gf;
@@ -224,24 +229,24 @@ REF_API void ref_ne_llama_eval(ref_ne_llama* m, const int* tokens, int N, int n_
     struct ne_tensor* cur = ne_rms_norm(ctx0, inpL, m->eps);
     cur = ne_mul(ctx0, cur, w[0]);
     struct ne_tensor* Qcur = ne_reshape_3d(ctx0, ne_mul_mat(ctx0, w[1], cur), hd, n_head, N);
-    struct ne_tensor* Kcur = ne_reshape_3d(ctx0, ne_mul_mat(ctx0, w[2], cur), hd, n_head, N);
+    struct ne_tensor* Kcur = ne_reshape_3d(ctx0, ne_mul_mat(ctx0, w[2], cur), hd, n_head_kv, N);
     struct ne_tensor* Vcur = ne_mul_mat(ctx0, w[3], cur);
     Qcur = ne_rope_inplace(ctx0, Qcur, n_past, hd, 0, 0, m->freq_base, m->freq_scale);
     Kcur = ne_rope_inplace(ctx0, Kcur, n_past, hd, 0, 0, m->freq_base, m->freq_scale);
     /* store key and value to the cache (llama.cpp:362-412) */
-    struct ne_tensor* k_cache = ne_view_1d(ctx0, m->kc, (int64_t)n_ctx * n_embd, (size_t)il * n_ctx * e16 * n_embd);
-    struct ne_tensor* v_cache = ne_view_1d(ctx0, m->vc, (int64_t)n_ctx * n_embd, (size_t)il * n_ctx * e16 * n_embd);
-    struct ne_tensor* k_dst = ne_view_3d(ctx0, k_cache, hd, N, n_head, e16 * hd, e16 * hd * n_ctx, (size_t)hd * n_past * e16);
-    struct ne_tensor* v_dst = ne_view_3d(ctx0, v_cache, N, hd, n_head, (size_t)n_ctx * e16, (size_t)n_ctx * e16 * hd, (size_t)n_past * e16);
+    struct ne_tensor* k_cache = ne_view_1d(ctx0, m->kc, (int64_t)n_ctx * kvd, (size_t)il * n_ctx * e16 * kvd);
+    struct ne_tensor* v_cache = ne_view_1d(ctx0, m->vc, (int64_t)n_ctx * kvd, (size_t)il * n_ctx * e16 * kvd);
+    struct ne_tensor* k_dst = ne_view_3d(ctx0, k_cache, hd, N, n_head_kv, e16 * hd, e16 * hd * n_ctx, (size_t)hd * n_past * e16);
+    struct ne_tensor* v_dst = ne_view_3d(ctx0, v_cache, N, hd, n_head_kv, (size_t)n_ctx * e16, (size_t)n_ctx * e16 * hd, (size_t)n_past * e16);
     ne_build_forward_expand(&gf, ne_cpy(ctx0, ne_permute(ctx0, Kcur, 0, 2, 1, 3), k_dst));
-    ne_build_forward_expand(&gf, ne_cpy(ctx0, ne_permute(ctx0, ne_reshape_3d(ctx0, Vcur, hd, n_head, N), 1, 2, 0, 3), v_dst));
+    ne_build_forward_expand(&gf, ne_cpy(ctx0, ne_permute(ctx0, ne_reshape_3d(ctx0, Vcur, hd, n_head_kv, N), 1, 2, 0, 3), v_dst));
     struct ne_tensor* Q = ne_permute(ctx0, Qcur, 0, 2, 1, 3);
-    struct ne_tensor* K = ne_view_3d(ctx0, k_cache, hd, n_past + N, n_head, e16 * hd, e16 * hd * n_ctx, 0);
+    struct ne_tensor* K = ne_view_3d(ctx0, k_cache, hd, n_past + N, n_head_kv, e16 * hd, e16 * hd * n_ctx, 0);
     struct ne_tensor* KQ = ne_mul_mat(ctx0, K, Q);
     struct ne_tensor* KQ_scaled = ne_scale_inplace(ctx0, KQ, ne_new_f32(ctx0, attn_scale));
     if (N > 1) KQ_scaled = ne_diag_mask_inf_inplace(ctx0, KQ_scaled, n_past);
     struct ne_tensor* KQ_soft_max = ne_soft_max_inplace(ctx0, KQ_scaled);
-    struct ne_tensor* V = ne_view_3d(ctx0, v_cache, n_past + N, hd, n_head, (size_t)n_ctx * e16, (size_t)n_ctx * e16 * hd, 0);
+    struct ne_tensor* V = ne_view_3d(ctx0, v_cache, n_past + N, hd, n_head_kv, (size_t)n_ctx * e16, (size_t)n_ctx * e16 * hd, 0);
     struct ne_tensor* KQV = ne_mul_mat(ctx0, V, KQ_soft_max);
     struct ne_tensor* KQV_merged = ne_permute(ctx0, KQV, 0, 2, 1, 3);
     cur = ne_cpy(ctx0, KQV_merged, ne_new_tensor_2d(ctx0, NE_TYPE_F32, n_embd, N, NE_SIZE_CALC, NE_BACKEND_CPU));

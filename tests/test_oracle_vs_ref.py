@@ -238,26 +238,29 @@ def test_llama_single_token_attention_bit_exact(n_head, hd, length):
     assert np.array_equal(got, want)
 
 
-def _tiny_llama(seed, n_head=4, n_layer=2):
+def _tiny_llama(seed, n_head=4, n_layer=2, n_head_kv=None):
     r = _rng(seed)
-    hp = dict(n_vocab=160, n_embd=256, n_head=n_head, n_head_kv=n_head, n_layer=n_layer, n_ff=384, n_ctx=40, norm_eps=1e-5,
+    n_head_kv = n_head_kv or n_head
+    hp = dict(n_vocab=160, n_embd=256, n_head=n_head, n_head_kv=n_head_kv, n_layer=n_layer, n_ff=384, n_ctx=40, norm_eps=1e-5,
               rope_theta=10000.0, rope_scale=1.0)
     E, FF, V = hp["n_embd"], hp["n_ff"], hp["n_vocab"]
+    kvd = E // n_head * n_head_kv
     w = lambda n, k: oracle.quantize_q4_0(r.normal(0, 1.0 / np.sqrt(k), (n, k)).astype(np.float32))
     tok = r.normal(0, 1, (V, E)).astype(np.float32)
     on = r.uniform(0.5, 1.5, E).astype(np.float32)
     layers = [dict(attn_norm=r.uniform(0.5, 1.5, E).astype(np.float32), ffn_norm=r.uniform(0.5, 1.5, E).astype(np.float32),
-                   wq=w(E, E), wk=w(E, E), wv=w(E, E), wo=w(E, E), w1=w(FF, E), w2=w(E, FF), w3=w(FF, E)) for _ in range(n_layer)]
+                   wq=w(E, E), wk=w(kvd, E), wv=w(kvd, E), wo=w(E, E), w1=w(FF, E), w2=w(E, FF), w3=w(FF, E)) for _ in range(n_layer)]
     return hp, tok, on, w(V, E), layers
 
 
 @need_ref_n
-@pytest.mark.parametrize("n_head", [4, 2])
-def test_llama_eval_graph_end_to_end_bit_exact(n_head):
+@pytest.mark.parametrize("n_head,n_head_kv", [(4, 4), (2, 2), (4, 2), (8, 2)])
+def test_llama_eval_graph_end_to_end_bit_exact(n_head, n_head_kv):
     """oracle/llama_model.py == the reference's own engine running the graph of models/llama/llama.cpp (Q4_0 weights, fp16 KV
-    cache, prompt evals with the causal mask and single-token steps): logits bit for bit, hence identical greedy ids"""
+    cache, GQA through ne_mul_mat's head broadcast, prompt evals with the causal mask and single-token steps): logits bit for
+    bit, hence identical greedy ids"""
     from oracle.llama_model import OracleLlama, greedy
-    hp, tok, on, out, layers = _tiny_llama(50 + n_head, n_head)
+    hp, tok, on, out, layers = _tiny_llama(50 + n_head, n_head, n_head_kv=n_head_kv)
     ref = oracle.RefNeLlama(hp, tok, on, out, layers)
     orc = OracleLlama(hp, tok, on, out, layers)
     pos = 0
