@@ -116,6 +116,8 @@ def load_into_engine(model: GGUFLlama, n_ctx: int | None = None, queue=None):
 
     def weight(tr, n, k):
         typ, rows = tr
+        if typ == "btla":  # a serialized BesTLA blob (NE files, neural_speed_b200/ne_loader.py)
+            return Weight.from_blob(rows, queue)
         return Weight.from_q6_K_host(rows, n, k, queue) if typ == "q6_K" else Weight.from_q4_0_host(rows, n, k, queue)
 
     E, FF = hp["n_embd"], hp["n_ff"]
