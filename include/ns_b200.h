@@ -210,10 +210,22 @@ NS_API ns_program* ns_program_create(int m);
 NS_API int ns_program_add_matmul(ns_program* p, const ns_weight* const* weights, int nw, int mode, const float* in, int lda,
                                  float* dst, int ldo, const float* bias, int bias_bcast, const float* residual, float* aux,
                                  int barrier_before);
+/* extended form: norm_w != NULL fuses llama.cpp:205-210's rms_norm * weight into the op's activation prologue (eps = norm_eps);
+ * in_index / res_index (device ints, read when the op starts) offset the input / residual by index * stride floats, e.g. the
+ * embedding row of the token picked by the previous step (llama.cpp:190 ne_get_rows); eltop = NS_ELT_* (0 default, 1 GELU). */
+NS_API int ns_program_add_matmul_ex(ns_program* p, const ns_weight* const* weights, int nw, int mode, const float* in, int lda,
+                                    float* dst, int ldo, const float* bias, int bias_bcast, const float* residual, float* aux,
+                                    int barrier_before, const float* norm_w, float norm_eps, const int* in_index,
+                                    long long in_stride, const int* res_index, long long res_stride, int eltop);
 NS_API int ns_program_finalize(ns_program* p, void* queue);
 NS_API int ns_program_run(ns_program* p, void* queue);
+/* the op list executed `iters` times inside one launch (a generation loop whose ops read device-side state) */
+NS_API int ns_program_run_n(ns_program* p, int iters, void* queue);
 NS_API size_t ns_program_algorithmic_bytes(const ns_program* p);
 NS_API void ns_program_free(ns_program* p);
+/* debug aid: per-op, per-CTA clock stamps of the last run (only when NS_PROG_TIMELINE was set at finalize) */
+NS_API int ns_program_timeline(ns_program* p, unsigned long long* host, size_t cap_words, int* nops, int* grid);
+NS_API int ns_program_unit_trace(ns_program* p, unsigned long long* host, size_t cap_words);
 
 /* ggml drop-in with HOST buffers: ne_compute_forward_mul_mat_q_f32 (ne_layers.c:7085) for NE_TYPE_Q4_0:
  * dst[ne11][ne01] = src1[ne11][ne00] x src0 rows.  src0 is uploaded/repacked once and cached by address. */
