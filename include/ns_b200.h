@@ -25,6 +25,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "ns_ne_abi.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -115,6 +117,22 @@ NS_API void bestla_unpackweight_fp32(void* wptr, int n, int k, float* fp32data, 
 /* ne_bestla.h:77: quantise f32 [n][ld] into dstptr with the attributes of the blob srcptr (host only) */
 NS_API void bestla_packweight_copyattr(const float* f32ptr, void* dstptr, int n, int k, int ld, void* srcptr);
 
+/* The entry points that take the graph engine's own structs (ne_bestla.h:24-32,85; core/layers/ne_bestla.cpp:42,114-166,176,205).
+ * The struct layouts are restated in ns_ne_abi.h (struct ns_ne_tensor == struct ne_tensor, ne.h:161-206); with these exported,
+ * the reference's ne_graph_compute (ne_layers.c:11915) links against this library unchanged.
+ *   bestla_support           which nodes the library takes (BesTLA matmuls, fused QKV / FFN, contiguous add / mul / norms), host
+ *                            work-buffer size, n_tasks = 1
+ *   bestla_backend_support   every result lives on the host (NE_BACKEND_CPU) outside the device-resident route
+ *   bestla_parallel_for      INIT / COMPUTE / FINALIZE over the node's tasks (host threads for the engine's own ggml nodes)
+ *   bestla_mul / _add / _layernormalization  host-buffer element-wise ops ne_layers.c:4622,5677,6541,6625 call directly (CUDA
+ *                            kernels behind host staging, like the matmul drop-ins) */
+NS_API bool bestla_support(struct ns_ne_tensor* node, int n_threads, size_t* workspace, size_t* dev_workspace);
+NS_API int bestla_backend_support(struct ns_ne_tensor* src0, struct ns_ne_tensor* src1, int op);
+NS_API void bestla_parallel_for(ns_forward_compute_fptr fcomp, struct ns_ne_compute_params* mainparams, struct ns_ne_tensor* node);
+NS_API void bestla_mul(int batch, int vsize, const float* tensor, const float* vector, int vstep, float* out);
+NS_API void bestla_add(int batch, int vsize, const float* tensor, const float* vector, int vstep, float* out);
+NS_API void bestla_layernormalization(int norm_count, int norm_size, bool isrms, float epsilon, const float* FpIn, float* FpOut);
+
 /* ------------------------------------------------------------------ 2. device-resident set (NS_SYCL analogue) */
 /* ne_bestla.h:86-95.  device = opaque context owning one CUDA stream on cuda:<current>; queue = cudaStream_t */
 NS_API void* bestla_create_device(bool profile);
@@ -150,6 +168,8 @@ NS_API ns_weight* ns_weight_from_q4_0(const void* rows, int n, int k, size_t nb0
  * (vectors/cpu/quantize.h:1020, core/layers/vec_dot.h:907) bit for bit; plain matmul only (no fused QKV/FFN). */
 NS_API ns_weight* ns_weight_from_q6_K(const void* rows, int n, int k, size_t nb01, int rows_on_device, void* queue);
 NS_API ns_weight* ns_weight_from_btla_blob(const void* blob, void* queue);
+/* same, with the number of bytes readable at `blob` (file-backed blobs: the parser never reads past it) */
+NS_API ns_weight* ns_weight_from_btla_blob_n(const void* blob, size_t nbytes, void* queue);
 /* canonical unpacked container as BTLAGemmPackB takes it (bestla_gemm.h:46-50): q int8 [k][n] (values, e.g.
  * nibble-8), scales f32 [k/g][n], zp int8 [k/g][n] or NULL, shuffle int[k] or NULL.  Host pointers. */
 NS_API ns_weight* ns_weight_from_unpacked(const int8_t* q, const float* scales, const int8_t* zp, const int* shuffle, int n,
@@ -159,6 +179,8 @@ NS_API int ns_weight_info(const ns_weight* w, int* n, int* k, int* group, int* w
 NS_API int ns_weight_set_comp(ns_weight* w, int comp);
 /* packed bytes one GEMV must read from HBM for this weight (roofline numerator) */
 NS_API size_t ns_weight_algorithmic_bytes(const ns_weight* w);
+/* benchmark aid: device weight of the given geometry with random codes, scales in [0.005, 0.02] and zero points (no host data) */
+NS_API ns_weight* ns_weight_random(int n, int k, int group, int wfmt, int stype, int comp, int asym, unsigned seed, void* queue);
 /* dequantise to device fp32 [n][ld] (debug / parity; replaces bestla_unpackweight_fp32 on device) */
 NS_API int ns_weight_dequant_f32(const ns_weight* w, float* dst_dev, int ld, void* queue);
 
@@ -226,6 +248,12 @@ NS_API void ns_program_free(ns_program* p);
 /* debug aid: per-op, per-CTA clock stamps of the last run (only when NS_PROG_TIMELINE was set at finalize) */
 NS_API int ns_program_timeline(ns_program* p, unsigned long long* host, size_t cap_words, int* nops, int* grid);
 NS_API int ns_program_unit_trace(ns_program* p, unsigned long long* host, size_t cap_words);
+
+/* The host drop-ins (bestla_*_forward, ns_mul_mat_*_host) upload and repack a host weight once and cache the device copy by
+ * host address + a checksum sampled over the whole payload.  ns_host_cache_clear() releases every cached copy (call it when the
+ * model context that owned the host weights is freed: the reference frees its weights with the context, model_files.h:1490-1499). */
+NS_API void ns_host_cache_clear(void);
+NS_API size_t ns_host_cache_entries(void);
 
 /* ggml drop-in with HOST buffers: ne_compute_forward_mul_mat_q_f32 (ne_layers.c:7085) for NE_TYPE_Q4_0:
  * dst[ne11][ne01] = src1[ne11][ne00] x src0 rows.  src0 is uploaded/repacked once and cached by address. */

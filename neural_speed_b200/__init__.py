@@ -35,6 +35,8 @@ MM_BIAS_BCAST, MM_FORCE_GEMV, MM_FORCE_TC = 1, 2, 4
 EXPORTS = [
     "ns_last_error", "ns_version", "ns_launch_count",
     "bestla_init", "bestla_set_threads", "bestla_get_thread_handle", "bestla_timer",
+    "bestla_support", "bestla_backend_support", "bestla_parallel_for", "bestla_mul", "bestla_add", "bestla_layernormalization",
+    "ns_host_cache_clear", "ns_host_cache_entries",
     "bestla_f32f32_get_workspace_size", "bestla_f32f32_forward",
     "bestla_fusion_add_f32f32_support", "bestla_fusion_add_f32f32_forward",
     "bestla_fusion_QKV_f32f32_get_workspace_size", "bestla_fusion_QKV_f32f32_support", "bestla_fusion_QKV_f32f32_forward",
@@ -47,11 +49,11 @@ EXPORTS = [
     "bestla_device_malloc", "bestla_device_free", "bestla_device_memcpy", "bestla_device_memcpy_sync", "bestla_device_sync",
     "bestla_device_storage_size", "ns_device_storage_bytes", "bestla_device_load_storage", "ns_device_workspace_bytes",
     "bestla_device_f32f32_forward",
-    "ns_weight_from_q4_0", "ns_weight_from_q6_K", "ns_weight_from_btla_blob", "ns_weight_from_unpacked", "ns_weight_free", "ns_weight_info",
+    "ns_weight_from_q4_0", "ns_weight_from_q6_K", "ns_weight_from_btla_blob", "ns_weight_from_btla_blob_n", "ns_weight_random", "ns_weight_from_unpacked", "ns_weight_free", "ns_weight_info",
     "ns_weight_set_comp", "ns_weight_algorithmic_bytes", "ns_weight_dequant_f32",
     "ns_mul_mat", "ns_mul_qkv", "ns_ffn_silu", "ns_ffn_gelu", "ns_mul_mat_q4_0_f32_host", "ns_mul_mat_q6_K_f32_host",
     "ns_program_create", "ns_program_add_matmul", "ns_program_add_matmul_ex", "ns_program_finalize", "ns_program_run",
-    "ns_program_run_n", "ns_program_algorithmic_bytes", "ns_program_free", "ns_program_timeline",
+    "ns_program_run_n", "ns_program_algorithmic_bytes", "ns_program_free", "ns_program_timeline", "ns_program_unit_trace",
     "ns_prepare_activation", "ns_matmul_prepared", "ns_graph_begin", "ns_graph_end", "ns_graph_launch", "ns_graph_free",
     "ns_device_quantize_q4_0", "ns_device_quantize_act",
     "BTLAGemmPackBSize", "BTLAGemmQuantPackB", "BTLAGemmPackB", "BTLAGemmUnPackB", "ns_quantize_row_q4_0", "ns_split_weight_size", "ns_split_weight",
@@ -120,6 +122,10 @@ def lib() -> C.CDLL:
     L.ns_mul_mat_q6_K_f32_host.argtypes = [vp, sz, vp, vp, i, i, i]
     L.ns_weight_from_btla_blob.restype = vp
     L.ns_weight_from_btla_blob.argtypes = [vp, vp]
+    L.ns_weight_random.restype = vp
+    L.ns_weight_random.argtypes = [i, i, i, i, i, i, i, C.c_uint, vp]
+    L.ns_weight_from_btla_blob_n.restype = vp
+    L.ns_weight_from_btla_blob_n.argtypes = [vp, sz, vp]
     L.ns_weight_from_unpacked.restype = vp
     L.ns_weight_from_unpacked.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp]
     L.ns_weight_free.argtypes = [vp]
@@ -322,8 +328,13 @@ class Weight:
         return cls(lib().ns_weight_from_q6_K(_np_ptr(rows), n, k, rows.shape[1], 0, queue))
 
     @classmethod
+    def random(cls, n, k, group=32, wfmt=W_S4, stype=S_F32, comp=COMP_INT8, asym=False, seed=1, queue=None):
+        """benchmark aid: random codes / scales generated on the device (no host data, no quantisation pass)"""
+        return cls(lib().ns_weight_random(n, k, group, wfmt, stype, comp, 1 if asym else 0, seed, queue))
+
+    @classmethod
     def from_blob(cls, blob: np.ndarray, queue=None):
-        return cls(lib().ns_weight_from_btla_blob(_np_ptr(blob), queue))
+        return cls(lib().ns_weight_from_btla_blob_n(_np_ptr(blob), blob.nbytes, queue))
 
     @classmethod
     def from_unpacked(cls, q_kn, scales, zp, group, wfmt=W_S4, stype=S_F32, comp=COMP_INT8, shuffle=None, queue=None):

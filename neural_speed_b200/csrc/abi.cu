@@ -364,7 +364,8 @@ struct Reader {
   void aligned_buf(const uint8_t** data, size_t* bytes) {
     const size_t sz = get<size_t>();
     const size_t off = get<size_t>();
-    if (!ok || p + off + sz > end) {
+    // sizes come from an untrusted file: compare against what is left instead of forming p + off + sz (which can wrap)
+    if (!ok || off > (size_t)(end - p) || sz > (size_t)(end - p) - off) {
       ok = false;
       return;
     }
@@ -383,13 +384,14 @@ struct Reader {
 };
 }  // namespace
 
-static bool parse_blob(const void* blob, BlobView* v) {
-  if (!blob) return false;
+// avail: bytes readable at `blob` (0: unknown -- trust the blob's own size field, as the reference's deserialBuffer does)
+static bool parse_blob(const void* blob, BlobView* v, size_t avail = 0) {
+  if (!blob || (avail && avail < 64)) return false;
   memset(v, 0, sizeof(*v));
   size_t msize;
   memcpy(&msize, blob, sizeof(size_t));
-  if (msize < 64 || msize > ((size_t)1 << 40)) {
-    ns_set_error("blob: implausible size field %zu", msize);
+  if (msize < 64 || msize > ((size_t)1 << 40) || (avail && msize > avail)) {
+    ns_set_error("blob: implausible size field %zu (buffer holds %zu bytes)", msize, avail);
     return false;
   }
   Reader r{(const uint8_t*)blob, (const uint8_t*)blob, (const uint8_t*)blob + msize};
@@ -503,10 +505,12 @@ static int blob_upload_repack(const BlobView& v, ns_weight* w, cudaStream_t st) 
   return rc;
 }
 
-extern "C" ns_weight* ns_weight_from_btla_blob(const void* blob, void* queue) {
+// nbytes: bytes readable at `blob` (0: unknown, trust the blob's size field); a file-backed blob passes its tensor size so a
+// corrupt size field cannot make the parser read past the buffer
+extern "C" ns_weight* ns_weight_from_btla_blob_n(const void* blob, size_t nbytes, void* queue) {
   if (ns_ensure_device()) return nullptr;
   BlobView v;
-  if (!parse_blob(blob, &v)) return nullptr;
+  if (!parse_blob(blob, &v, nbytes)) return nullptr;
   ns_weight* w = new ns_weight();
   if (blob_to_weight_meta(v, w) || weight_alloc(w, v.shuffle != nullptr)) {
     delete w;
@@ -518,6 +522,34 @@ extern "C" ns_weight* ns_weight_from_btla_blob(const void* blob, void* queue) {
   }
   return w;
 }
+
+// Benchmark aid: a weight of the given geometry filled with random codes / scales / zero points on the device (the decode path is
+// bandwidth bound: speed does not depend on the values; parity tests never use this).
+extern "C" ns_weight* ns_weight_random(int n, int k, int group, int wfmt, int stype, int comp, int asym, unsigned seed, void* queue) {
+  if (ns_ensure_device()) return nullptr;
+  if (n <= 0 || k <= 0 || !(wfmt == NS_W_S4 || wfmt == NS_W_S8 || wfmt == NS_W_NF4) || stype < 0 || stype > NS_S_F16 || comp < 0 ||
+      comp > NS_COMP_INT8_S8 || (wfmt == NS_W_NF4 && (asym || !(comp == NS_COMP_F32 || comp == NS_COMP_BF16)))) {
+    ns_set_error("ns_weight_random: invalid geometry");
+    return nullptr;
+  }
+  ns_weight* w = new ns_weight();
+  memset(w, 0, sizeof(*w));
+  w->n = n;
+  w->k = k;
+  w->group = group;
+  w->wfmt = wfmt;
+  w->stype = stype;
+  w->comp = comp;
+  w->asym = asym ? 1 : 0;
+  weight_layout(w);
+  if (weight_alloc(w, false) || ns_launch_random_weight(w, seed, stream_of(queue))) {
+    ns_weight_free(w);
+    return nullptr;
+  }
+  return w;
+}
+
+extern "C" ns_weight* ns_weight_from_btla_blob(const void* blob, void* queue) { return ns_weight_from_btla_blob_n(blob, 0, queue); }
 
 extern "C" int ns_weight_dequant_f32(const ns_weight* w, float* dst_dev, int ld, void* queue) {
   if (int rc = ns_ensure_device()) return rc;
@@ -859,17 +891,34 @@ struct CacheEntry {
 };
 static std::unordered_map<const void*, CacheEntry> g_cache;
 
-static size_t blob_tag(const void* blob) {
-  // cheap identity check so a recycled address with a different tensor is re-uploaded
+// Identity check so a recycled address holding a different tensor is re-uploaded: FNV-1a over the header bytes AND 256 eight-byte
+// samples spread over the whole payload (two layers' wq share every header field; only the weights differ), plus the size.
+// Reads stay inside [blob, blob + nbytes).  ns_host_cache_clear() drops every entry (call it when a model is freed).
+static size_t blob_tag(const void* blob, size_t nbytes) {
   size_t t = 1469598103934665603ull;
   const unsigned char* p = (const unsigned char*)blob;
-  for (int i = 0; i < 64; ++i) t = (t ^ p[i]) * 1099511628211ull;
-  return t;
+  const size_t head = nbytes < 64 ? nbytes : 64;
+  for (size_t i = 0; i < head; ++i) t = (t ^ p[i]) * 1099511628211ull;
+  if (nbytes > 72) {
+    const size_t span = nbytes - 8, steps = 256;
+    for (size_t j = 0; j < steps; ++j) {
+      const size_t off = 64 + (size_t)((__uint128_t)(span - 64) * j / steps);
+      unsigned long long v;
+      memcpy(&v, p + off, 8);
+      t = (t ^ (size_t)v) * 1099511628211ull;
+    }
+  }
+  return (t ^ nbytes) * 1099511628211ull;
+}
+static size_t btla_blob_bytes(const void* blob) {  // the blob's own size field (validated by parse_blob on upload)
+  size_t msize = 0;
+  memcpy(&msize, blob, sizeof(size_t));
+  return (msize >= 64 && msize <= ((size_t)1 << 40)) ? msize : 64;
 }
 
 static const ns_weight* cached_blob(const void* blob) {
   if (ns_ensure_device()) ns_fatal("%s", g_err);
-  const size_t tag = blob_tag(blob);
+  const size_t tag = blob_tag(blob, btla_blob_bytes(blob));
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_cache.find(blob);
@@ -1107,6 +1156,17 @@ extern "C" void bestla_unpackweight_fp32(void* wptr, int n, int k, float* fp32da
   cudaFree(d);
 }
 
+// drops every device copy the host drop-ins cached by address (model free / reload); the device memory is released
+extern "C" void ns_host_cache_clear(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& kv : g_cache) ns_weight_free(kv.second.w);
+  g_cache.clear();
+}
+extern "C" size_t ns_host_cache_entries(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_cache.size();
+}
+
 // ggml host drop-in
 static int ggml_mul_mat_host(int q6k, const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01, int ne11) {
   if (int rc = ns_ensure_device()) return rc;
@@ -1116,7 +1176,8 @@ static int ggml_mul_mat_host(int q6k, const void* src0_rows, size_t nb01, const 
   }
   const ns_weight* w = nullptr;
   {
-    const size_t tag = blob_tag(src0_rows) ^ ((size_t)ne00 << 32) ^ (size_t)ne01 ^ ((size_t)q6k << 63);
+    const size_t tag = blob_tag(src0_rows, (size_t)(ne01 - 1) * nb01 + (size_t)(ne00 / (q6k ? 256 : 32)) * (q6k ? 210 : 18)) ^
+                       ((size_t)ne00 << 32) ^ (size_t)ne01 ^ ((size_t)q6k << 63);
     std::unique_lock<std::mutex> lk(g_mu);
     auto it = g_cache.find(src0_rows);
     if (it != g_cache.end() && it->second.tag == tag) {

@@ -83,6 +83,7 @@ int ns_launch_repack_canonical(const int8_t* q_kn_dev, const float* sc_dev, cons
 int ns_launch_repack_btla(const void* qbuf_dev, const void* sc_dev, int src_stype, const int8_t* zp_dev, int cstep,
                           int kpad_src, int ntile, int packrow, int is_float, ns_weight* w, cudaStream_t st);
 int ns_launch_dequant(const ns_weight* w, float* dst, int ld, cudaStream_t st);
+int ns_launch_random_weight(ns_weight* w, unsigned seed, cudaStream_t st);  // synthetic image for benchmarks
 
 // ggml Q6_K x Q8_K (q6k.cu)
 void ns_q6k_layout(ns_weight* w);

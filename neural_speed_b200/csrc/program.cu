@@ -76,6 +76,7 @@ struct ProgCfg {
   int iters;  // the op list is executed `iters` times (tokens) inside one launch
   int batch;     // units issued per producer-warp step (one lane each), <= nslots
   int inflight;  // at most this many units issued and not yet landed (>= batch); bounds the depth of the SM's request queue
+  int pf_units;  // L2 prefetch distance in units ahead of the load cursor (0: off)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,6 +107,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar)
                : "memory");
+}
+// TMA L2 prefetch of a byte range (no completion tracking; SASS UBLKPF)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 r;
@@ -343,6 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ ProgOp op_s[2];  // the consumers' current and next op (the next one is fetched during the current one)
   __shared__ ProgOp op_p;     // the producer's current op
+  __shared__ ProgOp op_q;     // the op under the producer's L2-prefetch cursor
   __shared__ float red_s[kConsumers];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t smem_base = smem_u32(smem);
@@ -369,9 +375,46 @@ __global__ void __launch_bounds__(kThreads, 1)
     // L1 is all but carved away by the 224 KB of shared memory, so every read of the descriptor array costs an L2 round trip:
     // the warp copies the op's descriptor to shared memory once per op.  Lane l < kBatch issues unit jb + l of each batch.
     int ubase = 0;  // CTA-wide index of the op's first unit
+    constexpr int kWords = (int)(sizeof(ProgOp) / 4);
+    // L2 prefetch cursor: runs pf_units units ahead of the load cursor, across op boundaries.  While the ring is full (the
+    // consumers are in a grid barrier) the prefetches already issued keep HBM streaming into L2; the ring refills from L2.
+    int pf_seq = 0, pf_j = 0, pf_my = 0, pf_ahead = 0;
+    bool pf_done = R.pf_units <= 0;
+    const int total_ops_p = nops * R.iters;
+    auto pf_open = [&]() {  // descriptor of op pf_seq under the prefetch cursor
+      __syncwarp();
+      for (int w = lane; w < kWords; w += 32)
+        reinterpret_cast<uint32_t*>(&op_q)[w] = reinterpret_cast<const uint32_t*>(ops + pf_seq % nops)[w];
+      __syncwarp();
+      const int nu = op_q.nunits;
+      pf_my = first < nu ? (nu - first + G - 1) / G : 0;
+      pf_j = 0;
+    };
+    if (!pf_done) pf_open();
+    auto pf_top_up = [&]() {
+      while (!pf_done && pf_ahead < R.pf_units) {
+        const int j = pf_j + lane;
+        if (j < pf_my) {
+          const PairSrc ps = op_q.unit_rows == 2 ? resolve_pair(op_q, first + j * G) : resolve_single(op_q, first + j * G);
+          const uint32_t pq = (uint32_t)op_q.pitch;
+          if (ps.valid1 && ps.r1 != ps.r0 + pq) {
+            bulk_prefetch_l2(ps.r0, pq);
+            bulk_prefetch_l2(ps.r1, pq);
+          } else {
+            bulk_prefetch_l2(ps.r0, (ps.valid1 ? 2u : 1u) * pq);
+          }
+        }
+        const int n = min(32, pf_my - pf_j);
+        pf_j += n;
+        pf_ahead += n;
+        if (pf_j >= pf_my) {
+          if (++pf_seq >= total_ops_p) pf_done = true;
+          else pf_open();
+        }
+      }
+    };
     for (int it = 0; it < R.iters; ++it) {
       for (int oi = 0; oi < nops; ++oi) {
-        constexpr int kWords = (int)(sizeof(ProgOp) / 4);
         __syncwarp();
         for (int w = lane; w < kWords; w += 32)
           reinterpret_cast<uint32_t*>(&op_p)[w] = reinterpret_cast<const uint32_t*>(ops + oi)[w];
@@ -382,6 +425,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         const size_t tli = ((size_t)(it * nops + oi) * G + first) * kTl;
         if (tl && lane == 0) tl[tli + 5] = clk64();
         for (int jb = 0; jb < my_units; jb += R.batch) {
+          pf_top_up();
+          pf_ahead -= min(R.batch, my_units - jb);
           const int j = jb + lane;
           if (lane < R.batch && j < my_units) {
             const int i = ubase + j;
@@ -773,6 +818,8 @@ extern "C" int ns_program_finalize(ns_program* p, void* queue) {
   static const int env_inflight = getenv("NS_PROG_INFLIGHT") ? atoi(getenv("NS_PROG_INFLIGHT")) : 0;
   p->cfg.batch = std::max(1, std::min(std::min(32, nslots), env_batch > 0 ? env_batch : kBatch));
   p->cfg.inflight = std::max(p->cfg.batch, env_inflight > 0 ? env_inflight : nslots);
+  static const int env_pf = getenv("NS_PROG_PF_UNITS") ? atoi(getenv("NS_PROG_PF_UNITS")) : -1;
+  p->cfg.pf_units = env_pf >= 0 ? env_pf : 0;
   p->smem = act_region + (size_t)nslots * slot + (size_t)nslots * 16;
   p->grid = ns_num_sms();
   const size_t nops = p->ops.size();

@@ -268,3 +268,35 @@ extern "C" int ns_device_quantize_q4_0(const float* src_dev, void* dst_dev, int 
   ns_count_launch();
   return NS_OK;
 }
+
+// ---- synthetic weight image for benchmarks: random codes, scales ~ U[0.005, 0.02], zero points in [-4, 3] -------------------
+namespace {
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+__global__ void __launch_bounds__(256) random_weight_kernel(uint8_t* __restrict__ rows, int n, int pitch, int q_bytes, int sc_off, int zp_off,
+                                                           int ngroups, int stype, int asym, uint32_t seed) {
+  const int row = blockIdx.x;
+  uint8_t* r = rows + (size_t)row * pitch;
+  for (int i = threadIdx.x; i < q_bytes / 4; i += 256) reinterpret_cast<uint32_t*>(r)[i] = mix32(seed ^ (uint32_t)(row * 0x9e3779b9u) ^ (uint32_t)i * 0x85ebca6bu);
+  for (int g = threadIdx.x; g < ngroups; g += 256) {
+    const float sc = 0.005f + 0.015f * (float)(mix32(seed + 77u + (uint32_t)row * 131071u + (uint32_t)g) & 0xffff) * (1.f / 65536.f);
+    if (stype == NS_S_F32) reinterpret_cast<float*>(r + sc_off)[g] = sc;
+    else if (stype == NS_S_F16) reinterpret_cast<__half*>(r + sc_off)[g] = __float2half_rn(sc);
+    else reinterpret_cast<__nv_bfloat16*>(r + sc_off)[g] = __float2bfloat16_rn(sc);
+    if (asym) reinterpret_cast<int8_t*>(r + zp_off)[g] = (int8_t)((int)(mix32(seed + 991u + (uint32_t)row * 8191u + (uint32_t)g) & 7) - 4);
+  }
+}
+}  // namespace
+
+int ns_launch_random_weight(ns_weight* w, unsigned seed, cudaStream_t st) {
+  random_weight_kernel<<<w->n, 256, 0, st>>>(w->rows, w->n, w->pitch, w->q_bytes, w->sc_off, w->zp_off, w->ngroups, w->stype, w->asym, seed);
+  NS_CUDA_TRY(cudaGetLastError());
+  ns_count_launch();
+  return NS_OK;
+}

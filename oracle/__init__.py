@@ -66,15 +66,43 @@ def ref_ne():
         L.ref_ne_attn_1tok.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]
         for f in (L.ref_ne_rope, L.ref_ne_soft_max, L.ref_ne_rms_norm, L.ref_ne_attn_1tok):
             f.restype = None
-        L.ref_ne_llama_create.restype = C.c_void_p
-        L.ref_ne_llama_create.argtypes = [C.c_int] * 7 + [C.c_float] * 3
-        L.ref_ne_llama_set.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
-        L.ref_ne_llama_eval.restype = None
-        L.ref_ne_llama_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
-        L.ref_ne_llama_free.restype = None
-        L.ref_ne_llama_free.argtypes = [C.c_void_p]
+        _bind_llama(L)
         _ref_ne = L
     return _ref_ne
+
+
+_ref_ne_ns = None
+
+
+def _bind_llama(L):
+    L.ref_ne_llama_create.restype = C.c_void_p
+    L.ref_ne_llama_create.argtypes = [C.c_int] * 7 + [C.c_float] * 3
+    L.ref_ne_llama_create_ex.restype = C.c_void_p
+    L.ref_ne_llama_create_ex.argtypes = [C.c_int] * 7 + [C.c_float] * 3 + [C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.ref_ne_llama_set.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    L.ref_ne_llama_eval.restype = None
+    L.ref_ne_llama_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.ref_ne_llama_free.restype = None
+    L.ref_ne_llama_free.argtypes = [C.c_void_p]
+
+
+def ref_ne_ns():
+    """The reference's graph engine LINKED AGAINST libns_b200.so (oracle/_ref/libref_ne_ns.so: every bestla_* entry point of
+    ne_layers.c resolves to the CUDA drop-ins) or None.  Needs a CUDA device to compute anything."""
+    global _ref_ne_ns
+    if _ref_ne_ns is None:
+        p = os.path.join(_HERE, "_ref", "libref_ne_ns.so")
+        if not os.path.exists(p) and os.path.isdir("/root/reference/neural_speed"):
+            try:
+                subprocess.run(["make", "-C", _HERE, "-s", "_ref/libref_ne_ns.so"], check=True)
+            except Exception:
+                pass
+        if not os.path.exists(p):
+            return None
+        L = C.CDLL(p, mode=C.RTLD_GLOBAL)
+        _bind_llama(L)
+        _ref_ne_ns = L
+    return _ref_ne_ns
 
 
 def lib():
@@ -444,15 +472,23 @@ class RefNeLlama:
     through ne_mul_mat's head broadcast).  Only available where oracle/_ref was built (needs /root/reference)."""
 
     NAMES = ["attn_norm", "wq", "wk", "wv", "wo", "ffn_norm", "w1", "w2", "w3"]
+    NE_TYPE_Q4_0, NE_TYPE_BTLA = 2, 19  # core/data_types.h:32-55
 
-    def __init__(self, hp, tok_embd, out_norm, output_rows, layers):
-        L = ref_ne()
+    def __init__(self, hp, tok_embd, out_norm, output_rows, layers, btla=False, fused=True, n_threads=1, on_ns=False):
+        """btla=True: the matmul weights are serialized BesTLA blobs (NE_TYPE_BTLA tensors), which only the engine linked against
+        libns_b200.so (on_ns=True) can execute; fused: ne_mul_qkv / ne_ffn_silu nodes where the *_support probes agree."""
+        L = ref_ne_ns() if on_ns else ref_ne()
         if L is None:
-            raise RuntimeError("oracle/_ref/libref_ne.so not built")
+            raise RuntimeError("oracle/_ref/libref_ne%s.so not built" % ("_ns" if on_ns else ""))
         self.L, self.n_vocab = L, hp["n_vocab"]
-        self.h = C.c_void_p(L.ref_ne_llama_create(hp["n_vocab"], hp["n_embd"], hp["n_head"], hp["n_head_kv"], hp["n_layer"], hp["n_ff"],
-                                                  hp["n_ctx"],
-                                                  hp.get("norm_eps", 1e-6), hp.get("rope_theta", 10000.0), hp.get("rope_scale", 1.0)))
+        sizes = None
+        if btla:
+            mats = [output_rows] + [lay[n] for lay in layers for n in ("wq", "wk", "wv", "wo", "w1", "w2", "w3")]
+            sizes = np.asarray([np.asarray(m).nbytes for m in mats], np.uint64)
+        self.h = C.c_void_p(L.ref_ne_llama_create_ex(hp["n_vocab"], hp["n_embd"], hp["n_head"], hp["n_head_kv"], hp["n_layer"], hp["n_ff"],
+                                                     hp["n_ctx"], hp.get("norm_eps", 1e-6), hp.get("rope_theta", 10000.0),
+                                                     hp.get("rope_scale", 1.0), self.NE_TYPE_BTLA if btla else self.NE_TYPE_Q4_0,
+                                                     _p(sizes) if btla else None, 1 if fused else 0, n_threads))
 
         def put(layer, which, arr, dt):
             a = _c(arr, dt)
