@@ -239,6 +239,9 @@ NS_API int ns_program_add_matmul_ex(ns_program* p, const ns_weight* const* weigh
                                     float* dst, int ldo, const float* bias, int bias_bcast, const float* residual, float* aux,
                                     int barrier_before, const float* norm_w, float norm_eps, const int* in_index,
                                     long long in_stride, const int* res_index, long long res_stride, int eltop);
+/* flag-in-data hand-over for the op added last (see program.cu): tagged input = polled 8-byte {value, tag} words written by the
+ * previous op's dst_tag -- replaces the grid barrier between the two ops */
+NS_API int ns_program_tag_last(ns_program* p, int in_tagged, void* dst_tag);
 NS_API int ns_program_finalize(ns_program* p, void* queue);
 NS_API int ns_program_run(ns_program* p, void* queue);
 /* the op list executed `iters` times inside one launch (a generation loop whose ops read device-side state) */

@@ -52,7 +52,7 @@ EXPORTS = [
     "ns_weight_from_q4_0", "ns_weight_from_q6_K", "ns_weight_from_btla_blob", "ns_weight_from_btla_blob_n", "ns_weight_random", "ns_weight_from_unpacked", "ns_weight_free", "ns_weight_info",
     "ns_weight_set_comp", "ns_weight_algorithmic_bytes", "ns_weight_dequant_f32",
     "ns_mul_mat", "ns_mul_qkv", "ns_ffn_silu", "ns_ffn_gelu", "ns_mul_mat_q4_0_f32_host", "ns_mul_mat_q6_K_f32_host",
-    "ns_program_create", "ns_program_add_matmul", "ns_program_add_matmul_ex", "ns_program_finalize", "ns_program_run",
+    "ns_program_create", "ns_program_add_matmul", "ns_program_add_matmul_ex", "ns_program_tag_last", "ns_program_finalize", "ns_program_run",
     "ns_program_run_n", "ns_program_algorithmic_bytes", "ns_program_free", "ns_program_timeline", "ns_program_unit_trace",
     "ns_prepare_activation", "ns_matmul_prepared", "ns_graph_begin", "ns_graph_end", "ns_graph_launch", "ns_graph_free",
     "ns_device_quantize_q4_0", "ns_device_quantize_act",
@@ -160,6 +160,7 @@ def lib() -> C.CDLL:
     L.ns_program_add_matmul.argtypes = [vp, vp, i, i, vp, i, vp, i, vp, i, vp, vp, i]
     L.ns_program_add_matmul_ex.argtypes = [vp, vp, i, i, vp, i, vp, i, vp, i, vp, vp, i, vp, C.c_float, vp, C.c_longlong, vp,
                                            C.c_longlong, i]
+    L.ns_program_tag_last.argtypes = [vp, i, vp]
     L.ns_program_finalize.argtypes = [vp, vp]
     L.ns_program_run.argtypes = [vp, vp]
     L.ns_program_run_n.argtypes = [vp, i, vp]
@@ -460,7 +461,7 @@ class Program:
 
     def add(self, weights, mode, in_ptr, lda, dst_ptr, ldo, bias_ptr=None, bias_bcast=0, residual_ptr=None, aux_ptr=None,
             barrier_before=1, norm_ptr=None, norm_eps=0.0, in_index_ptr=None, in_stride=0, res_index_ptr=None, res_stride=0,
-            eltop=0):
+            eltop=0, in_tagged=False, dst_tag_ptr=None):
         """one matmul node; norm_ptr fuses rms_norm * weight into the activation prologue, in_index_ptr / res_index_ptr
         (device int32) offset input / residual by index * stride floats (embedding row chosen on the device)"""
         arr = (C.c_void_p * 3)(*([w.h for w in weights] + [None] * (3 - len(weights))))
@@ -470,6 +471,9 @@ class Program:
                                               opt(bias_ptr), bias_bcast, opt(residual_ptr), opt(aux_ptr), barrier_before,
                                               opt(norm_ptr), float(norm_eps), opt(in_index_ptr), int(in_stride),
                                               opt(res_index_ptr), int(res_stride), int(eltop)), "ns_program_add_matmul")
+        if in_tagged or dst_tag_ptr:
+            # flag-in-data hand-over: in_ptr is the previous op's dst_tag_ptr ([m][lda] 8-byte {value, tag} words)
+            _check(lib().ns_program_tag_last(self.h, 1 if in_tagged else 0, opt(dst_tag_ptr)), "ns_program_tag_last")
 
     def finalize(self, queue=None):
         _check(lib().ns_program_finalize(self.h, queue), "ns_program_finalize")

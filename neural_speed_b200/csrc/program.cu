@@ -7,11 +7,12 @@
 // "ns_program" is the list of matmul nodes of one token; one cooperative launch of 148 CTAs x (15 consumer warps + 1 producer
 // warp) executes all of them:
 //   * producer warp: walks the op list and streams this CTA's weight rows with cp.async.bulk (TMA 1-D, SASS UBLKCP) into a
-//     ring of ~30 fixed-size slots (~190 KB) guarded by full/empty mbarriers.  A unit is a row pair (or one row when a pair
-//     does not fit a slot: K = 11008).  LANES issue units in parallel, 15 per batch: one thread needs ~1000 cycles per unit
-//     (a chain of ~100 dependent scalar instructions, try_wait, R2UR, UBLKCP -- measured with the per-unit trace below), which
-//     capped a single-thread producer at 9-12 GB/s per SM against the 45 GB/s an SM's share of HBM needs.  The producer never
-//     waits for activations: it runs ahead across op boundaries, so HBM stays busy while the consumers synchronise.
+//     ring of 8 slots (~200 KB) guarded by full/empty mbarriers.  A CTA owns a CONTIGUOUS range of an op's rows; a unit is a
+//     row pair (what one consumer warp computes at a time), a GROUP of up to 8 units is one contiguous byte range = one bulk
+//     copy = one ring slot.  Lanes issue groups in parallel: a thread needs ~1000 cycles per copy (a chain of ~100 dependent
+//     scalar instructions around try_wait, R2UR, UBLKCP -- measured with the per-unit trace), which capped a producer issuing
+//     one 4.6 KB pair per copy at 9-12 GB/s per SM against the 45 GB/s an SM's share of HBM needs.  The producer never waits
+//     for activations: it runs ahead across op boundaries, so HBM stays busy while the consumers synchronise.
 //   * consumers, per op: wait until every CTA has finished the previous op (one red.release on a per-op counter, one polling
 //     thread per CTA -- measured 1.3 us per round on 148 CTAs, profiles/ubench.cu; per-CTA flags polled by 148 threads cost
 //     4.8 us), optional RMSNorm + activation quantisation of the op's fp32 input into the shared-memory image
@@ -33,10 +34,9 @@ namespace {
 constexpr int kConsumers = 15;  // 15 + the producer warp = 512 threads: 128 registers per thread (17 warps would round up to 20: 96)
 constexpr int kConsumerThreads = kConsumers * 32;
 constexpr int kThreads = kConsumerThreads + 32;
-constexpr int kMaxSlots = 60;  // ring slots: a multiple of kConsumers, so slot s is only ever consumed by warp s % kConsumers
-constexpr int kBatch = 15;    // units issued per producer-warp step (one lane each); <= nslots
+constexpr int kMaxGs = 8;   // units per group (= arrivals on a slot's empty barrier) at most
 constexpr int kKcReg = 4;  // 32-element chunks per lane the register path holds (K <= 4096)
-constexpr int kTl = 8;     // timeline words per (op, CTA)
+constexpr int kTl = 12;    // timeline words per (op, CTA)
 constexpr int kUnitTrace = 8192;  // debug: per-unit stamps of CTA 0 (first units of a launch)
 
 struct ProgOp {
@@ -65,18 +65,28 @@ struct ProgOp {
   int barrier_before;
   int act_row, meta_off, meta_stride;
   int use_reg;  // 1: activations in registers (M == 1, nchunks <= 32 * kKcReg)
-  int unit_rows;  // 2: a unit is a row pair; 1: single rows (a pair does not fit a ring slot)
+  int unit_rows;  // 2: a unit is a row pair; 1: single rows
   int nunits;
+  int gs;  // units per group (one bulk copy, one ring slot)
+  // flag-in-data hand-over between ops (NCCL's LL idea): the op also writes every output as an 8-byte word {value, tag} to
+  // dst_tag [m][ldo] (tag = ops executed so far, one 64-bit store); an op with in_tagged reads `in` as such words and polls each
+  // one until its tag matches -- no counter, no fence, no grid barrier between the two ops
+  unsigned long long* dst_tag;
+  int in_tagged;
+  int publish;  // 1: a later op (or the end of the launch) waits on this op's arrival counter
+  // divisions done once on the host: kConsumers / gs, kConsumers % gs, ceil(2^32 / gs), 32 / cpg
+  int dgi, dwi, cstep;
+  uint32_t gs_magic;
 };
 
 struct ProgCfg {
-  int ring_off, slot_bytes, nslots;
-  int bar_off;  // full[nslots] | empty[nslots]
+  int ring_off, group_bytes, ngroups;  // ring of `ngroups` slots, each holding one group of up to gs units
+  int gs_max;   // arrival count of the empty barriers (= the largest gs of any op)
+  int bar_off;  // full[ngroups] | empty[ngroups]
   int m;
   int iters;  // the op list is executed `iters` times (tokens) inside one launch
-  int batch;     // units issued per producer-warp step (one lane each), <= nslots
-  int inflight;  // at most this many units issued and not yet landed (>= batch); bounds the depth of the SM's request queue
-  int pf_units;  // L2 prefetch distance in units ahead of the load cursor (0: off)
+  int batch;    // groups issued per producer-warp step (one lane each), <= ngroups
+  uint32_t g_magic;  // ceil(2^32 / gridDim.x): first * nunits / G without a 64-bit division (exact while first * nunits < 2^32 / G)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,6 +112,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!ok);
+}
+// non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -263,32 +287,44 @@ __device__ __forceinline__ int chunk_dot(const uint4& wv, const uint4& a0, const
 }
 
 // One unit (two weight rows) against register-resident activations: KC chunks per lane, same per-lane summation order as the
-// shared-memory loop (chunk c = lane + 32 i in increasing i).
+// shared-memory loop (chunk c = lane + 32 i in increasing i).  Two chunks (four 16-byte weight loads) are in flight at a time:
+// with 44 registers pinned by the activations, eight loads in flight spilled -- and with the L1 carved away a spill costs an
+// L2 round trip.
 template <int KC, int AMODE, bool ASYM, int STYPE>
 __device__ __forceinline__ void reg_unit(const uint32_t (&wb)[2], const uint32_t (&rb)[2], const uint4 (&A0)[kKcReg],
                                          const uint4 (&A1)[kKcReg], const float (&asc)[kKcReg], const int (&asa)[kKcReg],
-                                         const int (&aza)[kKcReg], const uint32_t (&soff)[kKcReg], const uint32_t (&zoff)[kKcReg],
+                                         const int (&aza)[kKcReg], uint32_t soff0, uint32_t sstep, uint32_t zoff0, uint32_t zstep,
                                          float& acc0, float& acc1) {
-  uint4 wv[KC][2];
-  float ws[KC][2];
-  int off[KC][2];
 #pragma unroll
-  for (int i = 0; i < KC; ++i)
+  for (int i0 = 0; i0 < KC; i0 += 2) {
+    uint4 wv[2][2];
+    float ws[2][2];
+    int off[2][2];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      wv[i][r] = lds128(wb[r] + 512u * i);
-      ws[i][r] = lds_scale<STYPE>(rb[r] + soff[i], 0);
-      off[i][r] = 8;
-      if (ASYM) off[i][r] += lds8s(rb[r] + zoff[i]);
+    for (int ii = 0; ii < 2; ++ii) {
+      const int i = i0 + ii;
+      if (i < KC) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          wv[ii][r] = lds128(wb[r] + 512u * i);
+          ws[ii][r] = lds_scale<STYPE>(rb[r] + soff0 + sstep * i, 0);
+          off[ii][r] = 8;
+          if (ASYM) off[ii][r] += lds8s(rb[r] + zoff0 + zstep * i);
+        }
+      }
     }
 #pragma unroll
-  for (int i = 0; i < KC; ++i) {
+    for (int ii = 0; ii < 2; ++ii) {
+      const int i = i0 + ii;
+      if (i < KC) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int isum = ASYM ? chunk_dot<AMODE>(wv[i][r], A0[i], A1[i], off[i][r], -off[i][r] * asa[i], aza[i])
-                            : chunk_dot<AMODE>(wv[i][r], A0[i], A1[i], 8, asa[i], aza[i]);
-      float& acc = r ? acc1 : acc0;
-      acc = fmaf((float)isum, asc[i] * ws[i][r], acc);
+        for (int r = 0; r < 2; ++r) {
+          const int isum = ASYM ? chunk_dot<AMODE>(wv[ii][r], A0[i], A1[i], off[ii][r], -off[ii][r] * asa[i], aza[i])
+                                : chunk_dot<AMODE>(wv[ii][r], A0[i], A1[i], 8, asa[i], aza[i]);
+          float& acc = r ? acc1 : acc0;
+          acc = fmaf((float)isum, asc[i] * ws[ii][r], acc);
+        }
+      }
     }
   }
 }
@@ -341,27 +377,195 @@ __device__ __forceinline__ void copy_op(ProgOp* dst, const ProgOp* src, int tid)
   if (tid >= 32 && tid < 32 + kWords) reinterpret_cast<uint32_t*>(dst)[tid - 32] = reinterpret_cast<const uint32_t*>(src)[tid - 32];
 }
 
-template <int COMP, int M, bool ASYM, int STYPE>
+// Where unit u of an op lands in its output, and whether its second row exists (unit_rows == 2: rows 2u, 2u + 1 of the
+// concatenated weights -- pairs never straddle two weights, the launcher checks even n; gate/up: gate row u, up row u)
+struct UnitOut {
+  int out0;
+  bool valid1;
+};
+// (the op's fields are read from its descriptor in shared memory: a handful of LDS per unit instead of nine pinned registers;
+// outputs are indexed with ints: m * ldo + n < 2^31)
+__device__ __forceinline__ UnitOut unit_out(const ProgOp& g, int u) {
+  UnitOut r;
+  if (g.mode == NS_GEMV_GATE_UP_SILU) {
+    r.out0 = u;
+    r.valid1 = true;
+    return r;
+  }
+  const int unit_rows = g.unit_rows, nw = g.nw;
+  int row = unit_rows * u, nn = g.n[0];
+  int off = (int)g.dst_off[0];
+  if (nw > 1 && row >= nn) {
+    row -= nn;
+    nn = g.n[1];
+    off = (int)g.dst_off[1];
+    if (nw > 2 && row >= nn) {
+      row -= nn;
+      nn = g.n[2];
+      off = (int)g.dst_off[2];
+    }
+  }
+  r.out0 = off + row;
+  r.valid1 = unit_rows == 2 && row + 1 < nn;
+  return r;
+}
+// both sums of a unit with six shuffles: after the xor-16 step lanes < 16 carry row 0, lanes >= 16 row 1 (every lane of a
+// butterfly holds the same bits at every step, so lane 0 / lane 16 end with exactly what two full butterflies give)
+__device__ __forceinline__ void warp_sum2(float& a, float& b, int lane) {
+  a += __shfl_xor_sync(0xffffffffu, a, 16);
+  b += __shfl_xor_sync(0xffffffffu, b, 16);
+  float v = lane < 16 ? a : b;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  a = __shfl_sync(0xffffffffu, v, 0);
+  b = __shfl_sync(0xffffffffu, v, 16);
+}
+
+// units [lo, hi) of an op owned by CTA `first` of G: floor(first * nunits / G); the host checks 148 * nunits < 2^32 / G
+__device__ __forceinline__ int cta_unit_lo(int first, int nunits, uint32_t g_magic) { return (int)__umulhi((uint32_t)first * (uint32_t)nunits, g_magic); }
+
+// {value, tag} as one 64-bit store: the reader polls the tag (flag-in-data, no fence needed: the word is written atomically)
+__device__ __forceinline__ void st_tagged(unsigned long long* base, size_t idx, float v, unsigned tag) {
+  if (base) {
+    const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)tag << 32);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(base + idx), "l"(w) : "memory");
+  }
+}
+
+// ---- a consumer warp's walk over its units of one op ---------------------------------------------------------------------
+struct UnitCursor {
+  int j;          // unit index inside this CTA's range of the op
+  int gi, within; // its group inside the op, its position inside the group
+  int slot;       // ring slot of that group
+  uint32_t lap;   // how often the ring had wrapped when the group was issued (mbarrier phase)
+};
+struct UnitEnv {
+  uint32_t ring, full0, empty0, group_bytes;
+  int NG, gs, pitch, lo, ucount, lane, m;
+  unsigned long long* tu;  // per-unit trace (CTA 0 of a TRACE build) or NULL
+  unsigned out_tag;        // tag of this op's outputs (ops executed before it + 1)
+};
+struct UnitPre {
+  uint32_t r0, r1;  // shared-memory addresses of the unit's rows
+  float ep_res, ep_bias;
+  int e_m, e_out;
+  bool e_live;
+};
+__device__ __forceinline__ void unit_advance(UnitCursor& c, const UnitEnv& e, const ProgOp& P) {  // to unit j + kConsumers
+  c.j += kConsumers;
+  int dg = P.dgi;
+  c.within += P.dwi;
+  if (c.within >= e.gs) {
+    c.within -= e.gs;
+    ++dg;
+  }
+  c.gi += dg;
+  c.slot += dg;
+  while (c.slot >= e.NG) {
+    c.slot -= e.NG;
+    ++c.lap;
+  }
+}
+// epilogue operands are fetched before the wait (their L2 latency hides behind the dot products); then the unit's bytes
+template <int M>
+__device__ __forceinline__ UnitPre unit_prologue(const ProgOp& P, const UnitEnv& e, const UnitCursor& c, const UnitOut& uo, bool gate_up,
+                                                 const float* residual) {
+  UnitPre p;
+  p.ep_res = p.ep_bias = 0.f;
+  p.e_m = gate_up ? e.lane : (e.lane >> 1);
+  const int e_r = gate_up ? 0 : (e.lane & 1);
+  p.e_live = p.e_m < e.m && p.e_m < M && (e_r == 0 || uo.valid1);
+  p.e_out = uo.out0 + e_r;
+  if (p.e_live && !gate_up) {
+    const size_t o = (size_t)p.e_m * P.ldo + p.e_out;
+    const float* bias = P.bias;
+    if (bias) p.ep_bias = P.bias_bcast ? ldcg1f(bias + p.e_out) : ldcg1f(bias + o);
+    if (residual) p.ep_res = ldcg1f(residual + o);
+  }
+  const int ui = e.ucount + c.j;
+  const bool trace = e.tu && ui < kUnitTrace && e.lane == 0;
+  if (trace) e.tu[(size_t)ui * 8 + 3] = clk64();
+  mbar_wait(e.full0 + 8u * c.slot, c.lap & 1u);
+  if (trace) e.tu[(size_t)ui * 8 + 4] = clk64();
+  const uint32_t gbase = e.ring + (uint32_t)c.slot * e.group_bytes;
+  const int unit_rows = P.unit_rows;
+  p.r0 = gbase + (uint32_t)(gate_up ? c.within : unit_rows * c.within) * (uint32_t)e.pitch;
+  p.r1 = gate_up ? gbase + (uint32_t)(e.gs + c.within) * (uint32_t)e.pitch : (uo.valid1 ? p.r0 + e.pitch : p.r0);
+  return p;
+}
+template <int M>
+__device__ __forceinline__ void unit_epilogue(const ProgOp& P, const UnitEnv& e, const UnitCursor& c, const UnitOut& uo, const UnitPre& p,
+                                              bool gate_up, const float* residual, float (&acc)[2][M]) {
+  __syncwarp();
+  const int ui = e.ucount + c.j;
+  if (e.tu && ui < kUnitTrace && e.lane == 0) e.tu[(size_t)ui * 8 + 5] = clk64();
+  if (e.lane == 0) mbar_arrive(e.empty0 + 8u * c.slot);  // one of the group's units is done with the slot
+  if (M == 1) {
+    warp_sum2(acc[0][0], acc[1][0], e.lane);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int m = 0; m < M; ++m) acc[r][m] = warp_sum(acc[r][m]);
+  }
+  float* dst = P.dst;
+  const int ldo = P.ldo, eltop = P.eltop;
+  if (gate_up) {
+    float g = 0.f, up = 0.f;
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+      if (e.lane == m) {
+        g = acc[0][m];
+        up = acc[1][m];
+      }
+    if (p.e_live) {
+      const float sg = eltop == NS_ELT_GELU ? ns_gelu(g) : ns_silu(g);  // kernel_ref.h:1569-1576
+      float* aux = P.aux;
+      if (aux) aux[(size_t)p.e_m * ldo + uo.out0] = sg;
+      dst[(size_t)p.e_m * ldo + uo.out0] = sg * up;
+      st_tagged(P.dst_tag, (size_t)p.e_m * ldo + uo.out0, sg * up, e.out_tag);
+    }
+  } else {
+    float v = 0.f;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int m = 0; m < M; ++m)
+        if (e.lane == 2 * m + r) v = acc[r][m];
+    if (p.e_live) {
+      if (P.bias) v += p.ep_bias;
+      if (eltop == NS_ELT_GELU) v = ns_gelu(v);
+      if (residual) v += p.ep_res;
+      dst[(size_t)p.e_m * ldo + p.e_out] = v;
+      st_tagged(P.dst_tag, (size_t)p.e_m * ldo + p.e_out, v, e.out_tag);
+    }
+  }
+}
+
+// TRACE: clock stamps per (op, CTA) and per unit of CTA 0 (debug builds of the common configuration only: the stamps cost
+// registers in the hot loop, and a spilled register costs an L2 round trip here)
+template <int COMP, int M, bool ASYM, int STYPE, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
     program_kernel(const ProgOp* __restrict__ ops, int nops, const ProgCfg R, unsigned* __restrict__ counters,
-                   unsigned* __restrict__ epoch_ptr, unsigned long long* __restrict__ tl, unsigned long long* __restrict__ tu_dbg) {
+                   unsigned* __restrict__ epoch_ptr, unsigned long long* __restrict__ tl_, unsigned long long* __restrict__ tu_) {
+  unsigned long long* const tl = TRACE ? tl_ : nullptr;
+  unsigned long long* const tu_dbg = TRACE ? tu_ : nullptr;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ ProgOp op_s[2];  // the consumers' current and next op (the next one is fetched during the current one)
   __shared__ ProgOp op_p;     // the producer's current op
-  __shared__ ProgOp op_q;     // the op under the producer's L2-prefetch cursor
   __shared__ float red_s[kConsumers];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t ring = smem_base + R.ring_off;
   const uint32_t full0 = smem_base + R.bar_off;
-  const uint32_t empty0 = full0 + 8u * (uint32_t)R.nslots;
-  const int NS = R.nslots;
+  const int NG = R.ngroups;
+  const uint32_t empty0 = full0 + 8u * (uint32_t)NG;
   const int first = blockIdx.x, G = (int)gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) {
+    for (int s = 0; s < NG; ++s) {
       mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, R.gs_max);  // one arrival per unit of the group (the producer stands in for missing ones)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -369,93 +573,87 @@ __global__ void __launch_bounds__(kThreads, 1)
   // launches completed so far: every CTA arrives once per op per launch on counters[op], so after `epoch` launches of `iters`
   // iterations each counter stands at (sum of earlier iterations) * G; epoch_ptr[0] holds that sum of iterations.
   const unsigned base_iters = ld_acquire(epoch_ptr);
+  const unsigned tag_base = ld_acquire(epoch_ptr + 1);  // ops executed by earlier launches + 1 (tags are never 0)
 
   if (warp == kConsumers) {
     // ===================== producer: streams the weights of ALL ops, never waits for activations =====================
-    // L1 is all but carved away by the 224 KB of shared memory, so every read of the descriptor array costs an L2 round trip:
-    // the warp copies the op's descriptor to shared memory once per op.  Lane l < kBatch issues unit jb + l of each batch.
-    int ubase = 0;  // CTA-wide index of the op's first unit
+    // A CTA owns a CONTIGUOUS range of an op's units, so a group of gs units is one contiguous byte range per weight: one
+    // bulk copy per group.  Lane l issues group gb + l of each step.  L1 is all but carved away by the shared memory, so the
+    // op descriptor is copied to shared memory once per op instead of being re-read through L2.
+    int gslot0 = 0;        // ring slot of the op's first group
+    uint32_t glap0 = 0;    // and how many times the ring has wrapped before it
+    int ucount = 0;        // CTA-wide index of the op's first unit (trace only)
     constexpr int kWords = (int)(sizeof(ProgOp) / 4);
-    // L2 prefetch cursor: runs pf_units units ahead of the load cursor, across op boundaries.  While the ring is full (the
-    // consumers are in a grid barrier) the prefetches already issued keep HBM streaming into L2; the ring refills from L2.
-    int pf_seq = 0, pf_j = 0, pf_my = 0, pf_ahead = 0;
-    bool pf_done = R.pf_units <= 0;
-    const int total_ops_p = nops * R.iters;
-    auto pf_open = [&]() {  // descriptor of op pf_seq under the prefetch cursor
-      __syncwarp();
-      for (int w = lane; w < kWords; w += 32)
-        reinterpret_cast<uint32_t*>(&op_q)[w] = reinterpret_cast<const uint32_t*>(ops + pf_seq % nops)[w];
-      __syncwarp();
-      const int nu = op_q.nunits;
-      pf_my = first < nu ? (nu - first + G - 1) / G : 0;
-      pf_j = 0;
-    };
-    if (!pf_done) pf_open();
-    auto pf_top_up = [&]() {
-      while (!pf_done && pf_ahead < R.pf_units) {
-        const int j = pf_j + lane;
-        if (j < pf_my) {
-          const PairSrc ps = op_q.unit_rows == 2 ? resolve_pair(op_q, first + j * G) : resolve_single(op_q, first + j * G);
-          const uint32_t pq = (uint32_t)op_q.pitch;
-          if (ps.valid1 && ps.r1 != ps.r0 + pq) {
-            bulk_prefetch_l2(ps.r0, pq);
-            bulk_prefetch_l2(ps.r1, pq);
-          } else {
-            bulk_prefetch_l2(ps.r0, (ps.valid1 ? 2u : 1u) * pq);
-          }
-        }
-        const int n = min(32, pf_my - pf_j);
-        pf_j += n;
-        pf_ahead += n;
-        if (pf_j >= pf_my) {
-          if (++pf_seq >= total_ops_p) pf_done = true;
-          else pf_open();
-        }
-      }
-    };
     for (int it = 0; it < R.iters; ++it) {
       for (int oi = 0; oi < nops; ++oi) {
         __syncwarp();
         for (int w = lane; w < kWords; w += 32)
           reinterpret_cast<uint32_t*>(&op_p)[w] = reinterpret_cast<const uint32_t*>(ops + oi)[w];
         __syncwarp();
-        const int nunits = op_p.nunits;
+        const int nunits = op_p.nunits, gs = op_p.gs, unit_rows = op_p.unit_rows, mode = op_p.mode;
         const uint32_t pitch = (uint32_t)op_p.pitch;
-        const int my_units = first < nunits ? (nunits - first + G - 1) / G : 0;
+        const int lo = cta_unit_lo(first, nunits, R.g_magic), hi = cta_unit_lo(first + 1, nunits, R.g_magic);
+        const int my_units = hi - lo, ng = op_p.gs_magic ? (int)__umulhi((uint32_t)(my_units + gs - 1), op_p.gs_magic) : my_units;
         const size_t tli = ((size_t)(it * nops + oi) * G + first) * kTl;
         if (tl && lane == 0) tl[tli + 5] = clk64();
-        for (int jb = 0; jb < my_units; jb += R.batch) {
-          pf_top_up();
-          pf_ahead -= min(R.batch, my_units - jb);
-          const int j = jb + lane;
-          if (lane < R.batch && j < my_units) {
-            const int i = ubase + j;
-            const bool trace = tu_dbg && first == 0 && i < kUnitTrace;
-            if (trace) tu_dbg[(size_t)i * 8 + 0] = clk64();
-            const PairSrc ps = op_p.unit_rows == 2 ? resolve_pair(op_p, first + j * G) : resolve_single(op_p, first + j * G);
-            const int slot = i % NS, lap = i / NS;
-            if (lap > 0) mbar_wait(empty0 + 8u * slot, (uint32_t)(lap - 1) & 1u);  // the slot's previous unit has been consumed
-            if (i >= R.inflight) {  // unit i - inflight (issued by an earlier batch) has landed
-              const int pi = i - R.inflight;
-              mbar_wait(full0 + 8u * (pi % NS), (uint32_t)(pi / NS) & 1u);
+        for (int gb = 0; gb < ng; gb += R.batch) {
+          const int gi = gb + lane;
+          bool pending = lane < R.batch && gi < ng;
+          int slot = gslot0 + gi;
+          uint32_t lap = glap0;
+          while (slot >= NG) {
+            slot -= NG;
+            ++lap;
+          }
+          const int u0 = lo + gi * gs, n = min(gs, hi - u0);
+          const bool trace = pending && tu_dbg && first == 0 && ucount + gi * gs < kUnitTrace;
+          if (trace) tu_dbg[(size_t)(ucount + gi * gs) * 8 + 0] = clk64();
+          // every lane issues its group as soon as ITS slot is free (a blocking wait would hold the whole warp back until the
+          // slowest slot of the step frees: the refill of the other slots then comes late and the consumers starve)
+          while (__any_sync(0xffffffffu, pending)) {
+            const bool ready = pending && (lap == 0 || mbar_test(empty0 + 8u * slot, (lap - 1) & 1u));
+            if (ready) {
+              if (trace) tu_dbg[(size_t)(ucount + gi * gs) * 8 + 1] = clk64();
+              const uint32_t dst = ring + (uint32_t)slot * (uint32_t)R.group_bytes;
+              const uint32_t bar = full0 + 8u * slot;
+              if (mode == NS_GEMV_GATE_UP_SILU) {  // [gs gate rows][gs up rows]
+                mbar_expect_tx(bar, 2u * (uint32_t)n * pitch);
+                bulk_g2s(dst, op_p.rows[0] + (size_t)u0 * pitch, (uint32_t)n * pitch, bar);
+                bulk_g2s(dst + (uint32_t)gs * pitch, op_p.rows[1] + (size_t)u0 * pitch, (uint32_t)n * pitch, bar);
+              } else {
+                // rows [ra, rb) of the concatenated weights, split where they cross from one weight into the next
+                int ra = unit_rows * u0, rb = unit_rows * (u0 + n);
+                const int ntot = op_p.n[0] + (op_p.nw > 1 ? op_p.n[1] : 0) + (op_p.nw > 2 ? op_p.n[2] : 0);
+                if (rb > ntot) rb = ntot;
+                mbar_expect_tx(bar, (uint32_t)(rb - ra) * pitch);
+                int seg0 = 0;
+                uint32_t d = dst;
+#pragma unroll
+                for (int sgi = 0; sgi < 3; ++sgi) {
+                  if (sgi < op_p.nw) {
+                    const int seg1 = seg0 + op_p.n[sgi];
+                    const int a2 = max(ra, seg0), b2 = min(rb, seg1);
+                    if (a2 < b2) {
+                      bulk_g2s(d, op_p.rows[sgi] + (size_t)(a2 - seg0) * pitch, (uint32_t)(b2 - a2) * pitch, bar);
+                      d += (uint32_t)(b2 - a2) * pitch;
+                    }
+                    seg0 = seg1;
+                  }
+                }
+              }
+              for (int e = n; e < R.gs_max; ++e) mbar_arrive(empty0 + 8u * slot);  // arrivals of the units this group does not have
+              if (trace) tu_dbg[(size_t)(ucount + gi * gs) * 8 + 2] = clk64();
+              pending = false;
             }
-            if (trace) tu_dbg[(size_t)i * 8 + 1] = clk64();
-            const uint32_t dst = ring + (uint32_t)slot * (uint32_t)R.slot_bytes;
-            const uint32_t bar = full0 + 8u * slot;
-            if (ps.valid1 && ps.r1 != ps.r0 + pitch) {  // gate row, up row
-              mbar_expect_tx(bar, 2u * pitch);
-              bulk_g2s(dst, ps.r0, pitch, bar);
-              bulk_g2s(dst + pitch, ps.r1, pitch, bar);
-            } else {
-              const uint32_t bytes = (ps.valid1 ? 2u : 1u) * pitch;
-              mbar_expect_tx(bar, bytes);
-              bulk_g2s(dst, ps.r0, bytes, bar);
-            }
-            if (trace) tu_dbg[(size_t)i * 8 + 2] = clk64();
           }
           __syncwarp();
         }
-        ubase += my_units;
+        gslot0 += ng;
+        while (gslot0 >= NG) {
+          gslot0 -= NG;
+          ++glap0;
+        }
+        ucount += my_units;
         if (tl && lane == 0) tl[tli + 6] = clk64();
       }
     }
@@ -465,28 +663,28 @@ __global__ void __launch_bounds__(kThreads, 1)
   // ===================== consumers =====================
   constexpr int AMODE = (COMP == NS_COMP_INT8) ? A_U8 : A_S8;
   const int total_ops = nops * R.iters;
-  int ubase = 0;  // CTA-wide index of this op's first unit
+  int gslot0 = 0;         // ring slot of this op's first group
+  uint32_t glap0 = 0;     // and how many times the ring has wrapped before it
+  int ucount = 0;         // CTA-wide index of this op's first unit
   copy_op(&op_s[0], ops, threadIdx.x);
   nsq::bar_sync<1, kConsumerThreads>();
   for (int seq = 0; seq < total_ops; ++seq) {
     const int it = seq / nops, oi = seq - it * nops;
     const size_t tli = ((size_t)seq * G + first) * kTl;
     // ---- op boundary: wait until every CTA has published the previous op (the descriptor is already in shared memory) ----
-    {
-      if (threadIdx.x == 0) {
-        if (tl) {
-          tl[tli + 0] = clk64();
-          tl[tli + 7] = gtimer();
-        }
-        if (seq > 0 && op_s[seq & 1].barrier_before) {
-          // the previous op in execution order: (it, oi - 1) or (it - 1, nops - 1)
-          const int po = oi > 0 ? oi - 1 : nops - 1;
-          const unsigned want = (base_iters + (unsigned)(oi > 0 ? it : it - 1) + 1u) * (unsigned)G;
-          while ((int)(ld_acquire(counters + po) - want) < 0) {
-          }
-        }
-        if (tl) tl[tli + 1] = clk64();
+    if (threadIdx.x == 0) {
+      if (tl) {
+        tl[tli + 0] = clk64();
+        tl[tli + 7] = gtimer();
       }
+      if (seq > 0 && op_s[seq & 1].barrier_before) {
+        // the previous op in execution order: (it, oi - 1) or (it - 1, nops - 1)
+        const int po = oi > 0 ? oi - 1 : nops - 1;
+        const unsigned want = (base_iters + (unsigned)(oi > 0 ? it : it - 1) + 1u) * (unsigned)G;
+        while ((int)(ld_acquire(counters + po) - want) < 0) {
+        }
+      }
+      if (tl) tl[tli + 1] = clk64();
     }
     nsq::bar_sync<1, kConsumerThreads>();
     const ProgOp& P = op_s[seq & 1];
@@ -494,34 +692,48 @@ __global__ void __launch_bounds__(kThreads, 1)
     {
       const float* in = P.in;
       if (P.in_index) in += (long long)ldcg1i(P.in_index) * P.in_stride;
-      const nsq::NormQuantIn qi{in, P.norm_w, P.norm_eps, P.lda, P.k, P.kpad, COMP == NS_COMP_Q8_0 ? 32 : P.group,
+      const nsq::NormQuantIn qi{in, P.in_tagged ? tag_base + (unsigned)seq : 0u, P.norm_w, P.norm_eps, P.lda, P.k, P.kpad, COMP == NS_COMP_Q8_0 ? 32 : P.group,
                                 P.act_row, P.meta_off, P.meta_stride};
       nsq::norm_quantise_to_smem<COMP, kConsumerThreads, 1>(qi, R.m, smem_base, red_s, threadIdx.x);
     }
     nsq::bar_sync<1, kConsumerThreads>();
     if (tl && threadIdx.x == 0) tl[tli + 2] = clk64();
 
-    // hot op fields into registers (op_s sits in shared memory; the inline-asm loads below would otherwise re-read it)
-    const int nunits = P.nunits, unit_rows = P.unit_rows, pitch = P.pitch, sc_off = P.sc_off, zp_off = P.zp_off, cpg = P.cpg, mode = P.mode;
-    const int act_row = P.act_row, meta_stride = P.meta_stride, ldo = P.ldo, eltop = P.eltop, bias_bcast = P.bias_bcast;
-    const uint32_t cpg_magic = P.cpg_magic;
-    const float* bias = P.bias;
-    float* dst = P.dst;
-    float* aux = P.aux;
-    const int my_units = first < nunits ? (nunits - first + G - 1) / G : 0;
-    const uint32_t meta_s = smem_base + P.meta_off;
-    const int nchunks = P.kpad >> 5;
+    // Only what the dot-product loop needs lives in registers; the epilogue re-reads the op's fields from shared memory (a few
+    // LDS per unit), and the two activation paths are two separate loops: with 44 registers pinned by register-resident
+    // activations, one merged loop spilled, and a spill costs an L2 round trip here (the L1 is carved away).
+    const int pitch = P.pitch, gs = P.gs;
+    const bool gate_up = P.mode == NS_GEMV_GATE_UP_SILU;
+    const int lo = cta_unit_lo(first, P.nunits, R.g_magic), hi = cta_unit_lo(first + 1, P.nunits, R.g_magic);
+    const int my_units = hi - lo, ng = P.gs_magic ? (int)__umulhi((uint32_t)(my_units + gs - 1), P.gs_magic) : my_units;
     const float* residual = P.residual;
     if (residual && P.res_index) residual += (long long)ldcg1i(P.res_index) * P.res_stride;
-
-    // register-resident activations (M == 1, nchunks a multiple of 32): chunk c = lane + 32 i, i < kc
-    uint4 A0[kKcReg], A1[kKcReg];
-    float asc[kKcReg];
-    int asa[kKcReg], aza[kKcReg];
-    uint32_t soff[kKcReg], zoff[kKcReg];  // byte offsets of the chunk's scale / zero point inside a weight row
     const bool use_reg = (M == 1) && P.use_reg;
-    const int kc = nchunks >> 5;
+
+    // this warp's units of the op: unit j (0 .. my_units) with (ucount + j) % kConsumers == warp
+    UnitCursor cur;
+    cur.j = warp - (ucount % kConsumers);
+    if (cur.j < 0) cur.j += kConsumers;
+    cur.gi = P.gs_magic ? (int)__umulhi((uint32_t)cur.j, P.gs_magic) : cur.j;
+    cur.within = cur.j - cur.gi * gs;
+    cur.slot = gslot0 + cur.gi;
+    cur.lap = glap0;
+    while (cur.slot >= NG) {
+      cur.slot -= NG;
+      ++cur.lap;
+    }
+    if (tl && threadIdx.x == 0) tl[tli + 8] = clk64();
+    const UnitEnv env{ring, full0, empty0, (uint32_t)R.group_bytes, NG, gs, pitch, lo, ucount, lane, R.m,
+                      TRACE && first == 0 ? tu_dbg : nullptr, tag_base + (unsigned)seq + 1u};
+    const unsigned out_tag = env.out_tag;
+
     if (use_reg) {
+      // register-resident activations (M == 1, nchunks a multiple of 32): chunk c = lane + 32 i, i < kc
+      const uint32_t meta_s = smem_base + P.meta_off;
+      const int kc = P.kpad >> 10;
+      uint4 A0[kKcReg], A1[kKcReg];
+      float asc[kKcReg];
+      int asa[kKcReg], aza[kKcReg];
 #pragma unroll
       for (int i = 0; i < kKcReg; ++i) {
         const int c = lane + 32 * i;
@@ -534,106 +746,137 @@ __global__ void __launch_bounds__(kThreads, 1)
           asa[i] = (int)(short)(mt.y & 0xffff);
           if (!ASYM) asa[i] *= -8;  // the dp4a chain starts from -off * Sa; off == 8 for symmetric weights
           aza[i] = (int)((mt.y >> 16) & 0xff);
-          const int gi = (cpg == 1) ? c : (int)__umulhi((uint32_t)c, cpg_magic);
-          soff[i] = (uint32_t)sc_off + (uint32_t)gi * (STYPE == NS_S_F32 ? 4u : 2u);
-          zoff[i] = (uint32_t)zp_off + (uint32_t)gi;
         } else {
           A0[i] = A1[i] = make_uint4(0, 0, 0, 0);
           asc[i] = 0.f;
           asa[i] = aza[i] = 0;
-          soff[i] = zoff[i] = 0;
         }
       }
-    }
-
-    // this warp's units of the op: CTA-wide unit index ubase + j with (ubase + j) % kConsumers == warp
-    int j0 = warp - (ubase % kConsumers);
-    if (j0 < 0) j0 += kConsumers;
-    for (int j = j0; j < my_units; j += kConsumers) {
-      const int ui = ubase + j;
-      const int d = ui % NS;
-      const PairSrc ps = unit_rows == 2 ? resolve_pair(P, first + j * G) : resolve_single(P, first + j * G);
-      // epilogue operands fetched before the wait (their L2 latency hides behind the dot products)
-      float ep_res = 0.f, ep_bias = 0.f;
-      const bool gate_up = mode == NS_GEMV_GATE_UP_SILU;
-      const int e_m = gate_up ? lane : (lane >> 1);
-      const int e_r = gate_up ? 0 : (lane & 1);
-      const bool e_live = e_m < R.m && e_m < M && (e_r == 0 || ps.valid1);
-      const long long e_out = e_r ? ps.out1 : ps.out0;
-      if (e_live && !gate_up) {
-        const size_t o = (size_t)e_m * ldo + e_out;
-        if (bias) ep_bias = bias_bcast ? ldcg1f(bias + e_out) : ldcg1f(bias + o);
-        if (residual) ep_res = ldcg1f(residual + o);
-      }
-      const bool trace = tu_dbg && first == 0 && ui < kUnitTrace && lane == 0;
-      if (trace) tu_dbg[(size_t)ui * 8 + 3] = clk64();
-      mbar_wait(full0 + 8u * d, (uint32_t)(ui / NS) & 1u);
-      if (trace) tu_dbg[(size_t)ui * 8 + 4] = clk64();
-      const uint32_t r0 = ring + (uint32_t)d * (uint32_t)R.slot_bytes;
-      const uint32_t r1 = ps.valid1 ? r0 + pitch : r0;
-      const uint32_t rb[2] = {r0, r1};
-      float acc[2][M];
-#pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int m = 0; m < M; ++m) acc[r][m] = 0.f;
-
-      if (use_reg) {
-        const uint32_t wb[2] = {r0 + 16u * lane, r1 + 16u * lane};
-        switch (kc) {  // straight-line code per row length: the loads of all chunks are in flight before the first dot
-          case 4: reg_unit<4, AMODE, ASYM, STYPE>(wb, rb, A0, A1, asc, asa, aza, soff, zoff, acc[0][0], acc[1][0]); break;
-          case 3: reg_unit<3, AMODE, ASYM, STYPE>(wb, rb, A0, A1, asc, asa, aza, soff, zoff, acc[0][0], acc[1][0]); break;
-          case 2: reg_unit<2, AMODE, ASYM, STYPE>(wb, rb, A0, A1, asc, asa, aza, soff, zoff, acc[0][0], acc[1][0]); break;
-          default: reg_unit<1, AMODE, ASYM, STYPE>(wb, rb, A0, A1, asc, asa, aza, soff, zoff, acc[0][0], acc[1][0]); break;
+      // byte offset of chunk i's scale / zero point inside a weight row: base + i * step (cpg divides 32 on this path)
+      const int cpg = P.cpg;
+      const int g0 = (cpg == 1) ? lane : (int)__umulhi((uint32_t)lane, P.cpg_magic);
+      const uint32_t ssz = STYPE == NS_S_F32 ? 4u : 2u;
+      const uint32_t soff0 = (uint32_t)P.sc_off + (uint32_t)g0 * ssz, sstep = (uint32_t)P.cstep * ssz;
+      const uint32_t zoff0 = (uint32_t)P.zp_off + (uint32_t)g0, zstep = (uint32_t)P.cstep;
+      if (tl && threadIdx.x == 0) tl[tli + 9] = clk64();
+      // TWO units per trip: the part of a unit after its dot products (reduction shuffles, epilogue, cursor, the next try_wait)
+      // is ~250 dependent instructions that all 15 warps run at the same time -- the SM idles through it (measured: 1000
+      // cycles of dots, 1100 cycles of the rest per unit).  Sharing that part between two units halves it per unit.
+      while (cur.j < my_units) {
+        const UnitCursor c0 = cur;
+        unit_advance(cur, env, P);
+        const bool has1 = cur.j < my_units;
+        const UnitCursor c1 = cur;
+        if (has1) unit_advance(cur, env, P);
+        const UnitOut uo0 = unit_out(P, lo + c0.j);
+        const UnitOut uo1 = has1 ? unit_out(P, lo + c1.j) : uo0;
+        // the lane that stores (unit k, row r): 16 r + 8 k; it fetches that output's bias / residual ahead of the dots
+        const int sk = (lane >> 3) & 1, sr = lane >> 4;
+        const UnitOut& suo = sk ? uo1 : uo0;
+        const bool s_live = (lane & 7) == 0 && (sk == 0 || has1) && (gate_up ? sr == 0 : (sr == 0 || suo.valid1));
+        const int s_out = suo.out0 + (gate_up ? 0 : sr);
+        float ep_res = 0.f, ep_bias = 0.f;
+        if (s_live && !gate_up) {
+          const float* bias = P.bias;
+          if (bias) ep_bias = ldcg1f(bias + s_out);  // M == 1: broadcast and per-row bias coincide
+          if (residual) ep_res = ldcg1f(residual + s_out);
         }
-      } else {
-        const SmemUnitArgs ua{rb[0], rb[1], smem_base, meta_s, sc_off, zp_off, cpg, cpg_magic, act_row, meta_stride, nchunks, lane};
-        if (unit_rows == 2) smem_unit<2, M, AMODE, ASYM, STYPE>(ua, acc);
-        else smem_unit<1, M, AMODE, ASYM, STYPE>(ua, acc);
-      }
-      __syncwarp();
-      if (trace) tu_dbg[(size_t)ui * 8 + 5] = clk64();
-      if (lane == 0) mbar_arrive(empty0 + 8u * d);  // the unit's bytes may be overwritten
-
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};  // [unit][row]
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int m = 0; m < M; ++m) acc[r][m] = warp_sum(acc[r][m]);
-      if (gate_up) {
-        float g = 0.f, up = 0.f;
-#pragma unroll
-        for (int m = 0; m < M; ++m)
-          if (lane == m) {
-            g = acc[0][m];
-            up = acc[1][m];
+        for (int k = 0; k < 2; ++k) {
+          if (k == 1 && !has1) break;
+          const UnitCursor& c = k ? c1 : c0;
+          const UnitOut& uo = k ? uo1 : uo0;
+          const int ui = env.ucount + c.j;
+          const bool trace = env.tu && ui < kUnitTrace && lane == 0;
+          if (trace) env.tu[(size_t)ui * 8 + 3] = clk64();
+          mbar_wait(full0 + 8u * c.slot, c.lap & 1u);
+          if (trace) env.tu[(size_t)ui * 8 + 4] = clk64();
+          const uint32_t gbase = ring + (uint32_t)c.slot * (uint32_t)R.group_bytes;
+          const uint32_t r0 = gbase + (uint32_t)(gate_up ? c.within : 2 * c.within) * (uint32_t)pitch;
+          const uint32_t r1 = gate_up ? gbase + (uint32_t)(gs + c.within) * (uint32_t)pitch : (uo.valid1 ? r0 + pitch : r0);
+          const uint32_t rb[2] = {r0, r1};
+          const uint32_t wb[2] = {r0 + 16u * lane, r1 + 16u * lane};
+          switch (kc) {  // straight-line code per row length
+            case 4: reg_unit<4, AMODE, ASYM, STYPE>(wb, rb, A0, A1, asc, asa, aza, soff0, sstep, zoff0, zstep, acc[k][0], acc[k][1]); break;
+            case 3: reg_unit<3, AMODE, ASYM, STYPE>(wb, rb, A0, A1, asc, asa, aza, soff0, sstep, zoff0, zstep, acc[k][0], acc[k][1]); break;
+            case 2: reg_unit<2, AMODE, ASYM, STYPE>(wb, rb, A0, A1, asc, asa, aza, soff0, sstep, zoff0, zstep, acc[k][0], acc[k][1]); break;
+            default: reg_unit<1, AMODE, ASYM, STYPE>(wb, rb, A0, A1, asc, asa, aza, soff0, sstep, zoff0, zstep, acc[k][0], acc[k][1]); break;
           }
-        if (e_live) {
-          const float sg = eltop == NS_ELT_GELU ? ns_gelu(g) : ns_silu(g);  // kernel_ref.h:1569-1576
-          if (aux) aux[(size_t)e_m * ldo + ps.out0] = sg;
-          dst[(size_t)e_m * ldo + ps.out0] = sg * up;
+          __syncwarp();
+          if (trace) env.tu[(size_t)ui * 8 + 5] = clk64();
+          if (lane == 0) mbar_arrive(empty0 + 8u * c.slot);  // one of the group's units is done with the slot
         }
-      } else {
-        float v = 0.f;
+        // four sums with nine shuffles, same butterfly order (16, 8, 4, 2, 1) as warp_sum: after the xor-16 step lanes < 16
+        // carry row 0 and lanes >= 16 row 1; after the xor-8 step lanes with bit 3 clear carry unit 0, the others unit 1
+        float v0, v1;
+        {
+          const float a0 = acc[0][0] + __shfl_xor_sync(0xffffffffu, acc[0][0], 16);
+          const float b0 = acc[0][1] + __shfl_xor_sync(0xffffffffu, acc[0][1], 16);
+          const float a1 = acc[1][0] + __shfl_xor_sync(0xffffffffu, acc[1][0], 16);
+          const float b1 = acc[1][1] + __shfl_xor_sync(0xffffffffu, acc[1][1], 16);
+          v0 = lane < 16 ? a0 : b0;
+          v1 = lane < 16 ? a1 : b1;
+        }
+        v0 += __shfl_xor_sync(0xffffffffu, v0, 8);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
+        float v = (lane & 8) ? v1 : v0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        // lane 16 r + 8 k holds row r of unit k
+        if (gate_up) {
+          const float up = __shfl_sync(0xffffffffu, v, (lane & 8) | 16);  // the up row of this lane's unit
+          if (s_live) {
+            const float sg = P.eltop == NS_ELT_GELU ? ns_gelu(v) : ns_silu(v);  // kernel_ref.h:1569-1576
+            float* aux = P.aux;
+            if (aux) aux[s_out] = sg;
+            P.dst[s_out] = sg * up;
+            st_tagged(P.dst_tag, s_out, sg * up, out_tag);
+          }
+        } else if (s_live) {
+          if (P.bias) v += ep_bias;
+          if (P.eltop == NS_ELT_GELU) v = ns_gelu(v);
+          if (residual) v += ep_res;
+          P.dst[s_out] = v;
+          st_tagged(P.dst_tag, s_out, v, out_tag);
+        }
+      }
+    } else {
+      const SmemUnitArgs ua0{0, 0, smem_base, smem_base + (uint32_t)P.meta_off, P.sc_off, P.zp_off, P.cpg, P.cpg_magic, P.act_row,
+                             P.meta_stride, P.kpad >> 5, lane};
+      for (; cur.j < my_units; unit_advance(cur, env, P)) {
+        const UnitOut uo = unit_out(P, lo + cur.j);
+        const UnitPre pre = unit_prologue<M>(P, env, cur, uo, gate_up, residual);
+        SmemUnitArgs ua = ua0;
+        ua.r0 = pre.r0;
+        ua.r1 = pre.r1;
+        float acc[2][M];
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-          for (int m = 0; m < M; ++m)
-            if (lane == 2 * m + r) v = acc[r][m];
-        if (e_live) {
-          if (bias) v += ep_bias;
-          if (eltop == NS_ELT_GELU) v = ns_gelu(v);
-          if (residual) v += ep_res;
-          dst[(size_t)e_m * ldo + e_out] = v;
-        }
+          for (int m = 0; m < M; ++m) acc[r][m] = 0.f;
+        if (P.unit_rows == 2) smem_unit<2, M, AMODE, ASYM, STYPE>(ua, acc);
+        else smem_unit<1, M, AMODE, ASYM, STYPE>(ua, acc);
+        unit_epilogue<M>(P, env, cur, uo, pre, gate_up, residual, acc);
       }
     }
-    ubase += my_units;
+    gslot0 += ng;
+    while (gslot0 >= NG) {
+      gslot0 -= NG;
+      ++glap0;
+    }
+    ucount += my_units;
     // ---- op done in this CTA: publish (release) ----
-    nsq::bar_sync<1, kConsumerThreads>();
-    if (threadIdx.x == 0) {
-      if (tl) tl[tli + 3] = clk64();
-      red_release_add(counters + oi, 1u);
-      if (tl) tl[tli + 4] = clk64();
+    if (P.publish) {
+      nsq::bar_sync<1, kConsumerThreads>();
+      if (threadIdx.x == 0) {
+        if (tl) tl[tli + 3] = clk64();
+        red_release_add(counters + oi, 1u);
+        if (tl) tl[tli + 4] = clk64();
+      }
+    } else {
+      if (tl && threadIdx.x == 0) tl[tli + 3] = tl[tli + 4] = clk64();
+      nsq::bar_sync<1, kConsumerThreads>();  // every warp is done with the activation image and the op descriptor
     }
   }
   // last op finished everywhere -> advance the epoch exactly once (block 0), so the next launch sees fresh targets
@@ -642,6 +885,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     while ((int)(ld_acquire(counters + (nops - 1)) - want) < 0) {
     }
     red_release_add(epoch_ptr, (unsigned)R.iters);
+    red_release_add(epoch_ptr + 1, (unsigned)total_ops);
   }
 }
 
@@ -761,7 +1005,7 @@ extern "C" int ns_program_add_matmul_ex(ns_program* p, const ns_weight* const* w
   op.meta_stride = ns_meta_stride(w0->kpad);
   op.meta_off = p->m * op.act_row;
   static const bool no_reg = getenv("NS_PROG_NO_REG") != nullptr;  // tuning aid
-  op.use_reg = (p->m == 1 && (w0->kpad >> 5) <= 32 * kKcReg && (w0->kpad >> 5) % 32 == 0 && !no_reg) ? 1 : 0;
+  op.use_reg = (p->m == 1 && (w0->kpad >> 5) <= 32 * kKcReg && (w0->kpad >> 5) % 32 == 0 && 32 % op.cpg == 0 && !no_reg) ? 1 : 0;
   p->ops.push_back(op);
   return NS_OK;
 }
@@ -771,6 +1015,23 @@ extern "C" int ns_program_add_matmul(ns_program* p, const ns_weight* const* weig
                                      float* aux, int barrier_before) {
   return ns_program_add_matmul_ex(p, weights, nw, mode, in, lda, dst, ldo, bias, bias_bcast, residual, aux, barrier_before,
                                   nullptr, 0.f, nullptr, 0, nullptr, 0, NS_ELT_DEFAULT);
+}
+
+// Flag-in-data hand-over for the op added last: in_tagged != 0 -> its input `in` is a [m][lda] array of 8-byte {value, tag}
+// words written by the PREVIOUS op of the program (that op's dst_tag), polled word by word instead of waiting on a grid barrier
+// (barrier_before is cleared); dst_tag != NULL -> the op also writes its outputs as such words to dst_tag [m][ldo].
+extern "C" int ns_program_tag_last(ns_program* p, int in_tagged, void* dst_tag) {
+  if (!p || p->finalized || p->ops.empty()) return NS_E_INVALID;
+  ProgOp& o = p->ops.back();
+  if (in_tagged && (p->ops.size() < 2 || o.in_index || o.kpad > 3 * kConsumerThreads * 8)) {
+    ns_set_error("ns_program_tag_last: a tagged input needs a producing op before it, no input indirection and k <= %d",
+                 3 * kConsumerThreads * 8);
+    return NS_E_INVALID;
+  }
+  o.in_tagged = in_tagged ? 1 : 0;
+  if (in_tagged) o.barrier_before = 0;
+  o.dst_tag = (unsigned long long*)dst_tag;
+  return NS_OK;
 }
 
 extern "C" size_t ns_program_algorithmic_bytes(const ns_program* p) { return p ? p->alg_bytes : 0; }
@@ -786,47 +1047,73 @@ extern "C" int ns_program_finalize(ns_program* p, void* queue) {
     act_region = std::max(act_region, ns_round_up((size_t)mt * o.act_row + (size_t)mt * o.meta_stride * 8, 128));
     unit_max = std::max(unit_max, 2 * o.pitch);
   }
-  static const int env_kb = getenv("NS_PROG_SMEM_KB") ? atoi(getenv("NS_PROG_SMEM_KB")) : 0;  // tuning aid
+  static const int env_kb = getenv("NS_PROG_SMEM_KB") ? atoi(getenv("NS_PROG_SMEM_KB")) : 0;  // tuning aids
+  static const int env_gb = getenv("NS_PROG_GROUP_KB") ? atoi(getenv("NS_PROG_GROUP_KB")) : 0;
+  static const int env_batch = getenv("NS_PROG_BATCH") ? atoi(getenv("NS_PROG_BATCH")) : 0;
   const size_t budget = (size_t)(env_kb > 0 ? env_kb : 222) * 1024;  // the static shared memory (descriptors, reductions) rides on top
-  // slot = the longest row, or a gate/up pair (both rows of such a unit feed one epilogue); ops whose row pair fits use pairs
-  int slot = 0;
-  for (const ProgOp& o : p->ops) slot = std::max(slot, o.mode == NS_GEMV_GATE_UP_SILU ? 2 * o.pitch : o.pitch);
-  static const int env_pair = getenv("NS_PROG_PAIR_SLOTS") ? atoi(getenv("NS_PROG_PAIR_SLOTS")) : 0;  // tuning aid: slots of a pair of the longest rows
-  if (env_pair) slot = unit_max;
-  slot = (int)ns_round_up((size_t)slot, 128);
-  int nslots = 0;
-  if (budget > act_region + 64) nslots = (int)((budget - act_region - 64) / ((size_t)slot + 16));
-  nslots -= nslots % kConsumers;
-  if (nslots > kMaxSlots) nslots = kMaxSlots;
-  if (nslots < kConsumers) {  // kBatch <= nslots: the units of one producer batch land in distinct slots
-    ns_set_error("ns_program: rows too long for the shared-memory ring (%d B per slot)", slot);
+  // Ring slot = one GROUP of units fetched by one bulk copy.  Sized for two pairs of the longest rows when at least six such
+  // slots fit, else one pair, else one row; shorter rows pack floor(slot / unit) units (<= kMaxGs) into a slot.
+  int max_pitch = 0;
+  for (const ProgOp& o : p->ops) max_pitch = std::max(max_pitch, o.pitch);
+  int group = 0, ngroups = 0;
+  const int cand[3] = {4 * max_pitch, 2 * max_pitch, max_pitch};
+  for (int ci = 0; ci < 3; ++ci) {
+    group = env_gb > 0 ? env_gb * 1024 : cand[ci];
+    group = (int)ns_round_up((size_t)group, 128);
+    ngroups = budget > act_region + 64 ? (int)((budget - act_region - 64) / ((size_t)group + 16)) : 0;
+    if (ngroups >= 6 || env_gb > 0) break;
+  }
+  if (ngroups > 32) ngroups = 32;
+  if (ngroups < 2 || group < max_pitch) {
+    ns_set_error("ns_program: rows too long for the shared-memory ring (%d B per row)", max_pitch);
     return NS_E_UNSUPPORTED;
   }
+  int gs_max = 1;
   for (ProgOp& o : p->ops) {
-    o.unit_rows = (o.mode == NS_GEMV_GATE_UP_SILU || 2 * o.pitch <= slot) ? 2 : 1;
+    const bool gate_up = o.mode == NS_GEMV_GATE_UP_SILU;
+    if (gate_up && 2 * o.pitch > group) {
+      ns_set_error("ns_program: a gate/up row pair (%d B) does not fit a ring slot", 2 * o.pitch);
+      return NS_E_UNSUPPORTED;
+    }
+    o.unit_rows = (gate_up || 2 * o.pitch <= group) ? 2 : 1;
     long long rows = 0;
     for (int i = 0; i < o.nw; ++i) rows += o.n[i];
     o.nunits = o.unit_rows == 2 ? o.npairs : (int)rows;
+    o.gs = std::max(1, std::min(kMaxGs, group / (o.unit_rows * o.pitch)));
+    gs_max = std::max(gs_max, o.gs);
+    o.dgi = kConsumers / o.gs;
+    o.dwi = kConsumers % o.gs;
+    o.cstep = 32 / std::max(1, std::min(32, o.cpg));
+    o.gs_magic = o.gs > 1 ? (uint32_t)((0x100000000ull + (uint64_t)o.gs - 1) / (uint64_t)o.gs) : 0u;  // 0: gs == 1, no division
   }
   p->cfg.ring_off = (int)act_region;
-  p->cfg.slot_bytes = slot;
-  p->cfg.nslots = nslots;
-  p->cfg.bar_off = (int)(act_region + (size_t)nslots * slot);
+  p->cfg.group_bytes = group;
+  p->cfg.ngroups = ngroups;
+  p->cfg.gs_max = gs_max;
+  p->cfg.bar_off = (int)(act_region + (size_t)ngroups * group);
   p->cfg.m = p->m;
   p->cfg.iters = 1;
-  static const int env_batch = getenv("NS_PROG_BATCH") ? atoi(getenv("NS_PROG_BATCH")) : 0;        // tuning aids
-  static const int env_inflight = getenv("NS_PROG_INFLIGHT") ? atoi(getenv("NS_PROG_INFLIGHT")) : 0;
-  p->cfg.batch = std::max(1, std::min(std::min(32, nslots), env_batch > 0 ? env_batch : kBatch));
-  p->cfg.inflight = std::max(p->cfg.batch, env_inflight > 0 ? env_inflight : nslots);
-  static const int env_pf = getenv("NS_PROG_PF_UNITS") ? atoi(getenv("NS_PROG_PF_UNITS")) : -1;
-  p->cfg.pf_units = env_pf >= 0 ? env_pf : 0;
-  p->smem = act_region + (size_t)nslots * slot + (size_t)nslots * 16;
+  p->cfg.batch = std::max(1, std::min(ngroups, env_batch > 0 ? env_batch : 8));
+  p->grid = ns_num_sms();
+  p->cfg.g_magic = (uint32_t)((0x100000000ull + (uint64_t)p->grid - 1) / (uint64_t)p->grid);
+  for (const ProgOp& o : p->ops)
+    if ((uint64_t)(p->grid + 1) * (uint64_t)o.nunits >= 0x100000000ull / (uint64_t)p->grid) {
+      ns_set_error("ns_program: too many rows (%d units) for the 32-bit unit split", o.nunits);
+      return NS_E_UNSUPPORTED;
+    }
+  p->smem = act_region + (size_t)ngroups * group + (size_t)ngroups * 16;
   p->grid = ns_num_sms();
   const size_t nops = p->ops.size();
+  for (size_t i = 0; i < nops; ++i)  // an arrival counter is only bumped where somebody waits on it
+    p->ops[i].publish = (i + 1 == nops || p->ops[i + 1].barrier_before) ? 1 : 0;
   NS_CUDA_TRY(cudaMalloc((void**)&p->d_ops, nops * sizeof(ProgOp)));
-  NS_CUDA_TRY(cudaMalloc((void**)&p->d_counters, (nops + 1) * sizeof(unsigned)));
+  NS_CUDA_TRY(cudaMalloc((void**)&p->d_counters, (nops + 2) * sizeof(unsigned)));
   NS_CUDA_TRY(cudaMemcpyAsync(p->d_ops, p->ops.data(), nops * sizeof(ProgOp), cudaMemcpyHostToDevice, st));
-  NS_CUDA_TRY(cudaMemsetAsync(p->d_counters, 0, (nops + 1) * sizeof(unsigned), st));
+  NS_CUDA_TRY(cudaMemsetAsync(p->d_counters, 0, (nops + 2) * sizeof(unsigned), st));
+  {
+    const unsigned one = 1;  // tags start at 1: zero-initialised tagged buffers never match
+    NS_CUDA_TRY(cudaMemcpyAsync(p->d_counters + nops + 1, &one, sizeof(one), cudaMemcpyHostToDevice, st));
+  }
   if (getenv("NS_PROG_TIMELINE")) {
     const size_t words = nops * (size_t)p->grid * kTl;
     NS_CUDA_TRY(cudaMalloc((void**)&p->d_tl, words * sizeof(unsigned long long)));
@@ -839,13 +1126,13 @@ extern "C" int ns_program_finalize(ns_program* p, void* queue) {
   return NS_OK;
 }
 
-template <int COMP, int M, bool ASYM, int STYPE>
+template <int COMP, int M, bool ASYM, int STYPE, bool TRACE>
 static int run_one(ns_program* p, int iters, cudaStream_t st) {
-  auto kern = program_kernel<COMP, M, ASYM, STYPE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
+  auto kern = program_kernel<COMP, M, ASYM, STYPE, TRACE>;
+  static size_t attr_smem = 0;
+  if (p->smem > attr_smem) {
+    NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    attr_smem = p->smem;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p->grid);
@@ -872,9 +1159,11 @@ static int run_one(ns_program* p, int iters, cudaStream_t st) {
 template <int COMP, bool ASYM, int STYPE>
 static int run_m(ns_program* p, int iters, cudaStream_t st) {
   switch (p->m) {
-    case 1: return run_one<COMP, 1, ASYM, STYPE>(p, iters, st);
-    case 2: return run_one<COMP, 2, ASYM, STYPE>(p, iters, st);
-    default: return run_one<COMP, 4, ASYM, STYPE>(p, iters, st);
+    case 1:
+      if (COMP == NS_COMP_Q8_0 && !ASYM && p->d_tl && iters == 1) return run_one<COMP, 1, ASYM, STYPE, (COMP == NS_COMP_Q8_0 && !ASYM)>(p, iters, st);
+      return run_one<COMP, 1, ASYM, STYPE, false>(p, iters, st);
+    case 2: return run_one<COMP, 2, ASYM, STYPE, false>(p, iters, st);
+    default: return run_one<COMP, 4, ASYM, STYPE, false>(p, iters, st);
   }
 }
 template <int COMP, bool ASYM>

@@ -137,7 +137,8 @@ REF_API ref_ne_llama* ref_ne_llama_create(int n_vocab, int n_embd, int n_head, i
 /* which: -1 tok_embd (f32), -2 out_norm (f32), -3 output (q4_0 rows); 0..8 = the layer's tensors in the order above */
 REF_API int ref_ne_llama_set(ref_ne_llama* m, int layer, int which, const void* data, size_t bytes) {
   struct ne_tensor* t = which == -1 ? m->tok : which == -2 ? m->out_norm : which == -3 ? m->output : m->lw[layer * 9 + which];
-  if (ne_nbytes(t) != bytes) return -1;
+  /* a BTLA tensor's size counts the tensor struct as well (ne_new_tensor_impl, ne_layers.c:1078,1095): the blob must fit */
+  if (t->type == NE_TYPE_BTLA ? bytes > ne_nbytes(t) : ne_nbytes(t) != bytes) return -1;
   memcpy(t->data, data, bytes);
   return 0;
 }

@@ -44,12 +44,33 @@ tmp = torch.zeros(1, N_FF, device="cuda")
 ffn = torch.zeros(1, N_EMBD, device="cuda")
 logits = torch.zeros(1, N_VOCAB, device="cuda")
 prog = ns.Program(1)
-for lay in layers:
-    prog.add([lay["wq"], lay["wk"], lay["wv"]], ns.Program.CONCAT, x.data_ptr(), N_EMBD, qkv.data_ptr(), 3 * N_EMBD, barrier_before=BB)
-    prog.add([lay["wo"]], ns.Program.PLAIN, attn.data_ptr(), N_EMBD, o.data_ptr(), N_EMBD, barrier_before=BB)
-    prog.add([lay["w1"], lay["w3"]], ns.Program.GATE_UP_SILU, x.data_ptr(), N_EMBD, tmp.data_ptr(), N_FF, barrier_before=BB)
-    prog.add([lay["w2"]], ns.Program.PLAIN, tmp.data_ptr(), N_FF, ffn.data_ptr(), N_EMBD, barrier_before=BB)
-prog.add([lm_head], ns.Program.PLAIN, x.data_ptr(), N_EMBD, logits.data_ptr(), N_VOCAB, barrier_before=BB)
+TAGS = int(os.environ.get("TAGS", "0"))
+CHAIN = int(os.environ.get("CHAIN", "1"))  # 1: every op reads the previous op's output (the real dependency chain of a decode step)
+if CHAIN:
+    tq = torch.zeros(3 * N_EMBD, dtype=torch.int64, device="cuda")    # tagged copies of the outputs ({value, tag} words)
+    to = torch.zeros(N_EMBD, dtype=torch.int64, device="cuda")
+    tt = torch.zeros(N_FF, dtype=torch.int64, device="cuda")
+    tf = torch.zeros(N_EMBD, dtype=torch.int64, device="cuda")
+    tg = lambda tns: tns.data_ptr() if TAGS else None
+    first = True
+    for lay in layers:
+        prog.add([lay["wq"], lay["wk"], lay["wv"]], ns.Program.CONCAT, (tf if TAGS and not first else ffn).data_ptr() if not first else x.data_ptr(), N_EMBD,
+                 qkv.data_ptr(), 3 * N_EMBD, barrier_before=0 if first else BB, in_tagged=bool(TAGS and not first), dst_tag_ptr=tg(tq))
+        first = False
+        prog.add([lay["wo"]], ns.Program.PLAIN, (tq if TAGS else qkv).data_ptr(), 3 * N_EMBD, o.data_ptr(), N_EMBD, barrier_before=BB, in_tagged=bool(TAGS),
+                 dst_tag_ptr=tg(to))
+        prog.add([lay["w1"], lay["w3"]], ns.Program.GATE_UP_SILU, (to if TAGS else o).data_ptr(), N_EMBD, tmp.data_ptr(), N_FF, barrier_before=BB,
+                 in_tagged=bool(TAGS), dst_tag_ptr=tg(tt))
+        prog.add([lay["w2"]], ns.Program.PLAIN, (tt if TAGS else tmp).data_ptr(), N_FF, ffn.data_ptr(), N_EMBD, barrier_before=BB, in_tagged=bool(TAGS),
+                 dst_tag_ptr=tg(tf))
+    prog.add([lm_head], ns.Program.PLAIN, (tf if TAGS else ffn).data_ptr(), N_EMBD, logits.data_ptr(), N_VOCAB, barrier_before=BB, in_tagged=bool(TAGS))
+else:
+    for lay in layers:
+        prog.add([lay["wq"], lay["wk"], lay["wv"]], ns.Program.CONCAT, x.data_ptr(), N_EMBD, qkv.data_ptr(), 3 * N_EMBD, barrier_before=BB)
+        prog.add([lay["wo"]], ns.Program.PLAIN, attn.data_ptr(), N_EMBD, o.data_ptr(), N_EMBD, barrier_before=BB)
+        prog.add([lay["w1"], lay["w3"]], ns.Program.GATE_UP_SILU, x.data_ptr(), N_EMBD, tmp.data_ptr(), N_FF, barrier_before=BB)
+        prog.add([lay["w2"]], ns.Program.PLAIN, tmp.data_ptr(), N_FF, ffn.data_ptr(), N_EMBD, barrier_before=BB)
+    prog.add([lm_head], ns.Program.PLAIN, x.data_ptr(), N_EMBD, logits.data_ptr(), N_VOCAB, barrier_before=BB)
 prog.finalize(queue)
 for _ in range(5):
     prog.run(queue)
@@ -67,7 +88,8 @@ buf = np.zeros(8 * 1024 * 1024, np.uint64)
 L.ns_program_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
 rc = L.ns_program_timeline(prog.h, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(nops), C.byref(grid))
 assert rc == 0, ns.last_error()
-tl = buf[: nops.value * grid.value * 8].reshape(nops.value, grid.value, 8).astype(np.int64)
+KTL = 12
+tl = buf[: nops.value * grid.value * KTL].reshape(nops.value, grid.value, KTL).astype(np.int64)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 np.savez_compressed(os.path.join(ROOT, "gpurun_out", "prog_timeline.npz"), tl=tl)
 MHZ = 1965.0
@@ -84,7 +106,9 @@ for ki, kn in enumerate(kinds + ["lm_head"]):
     gt = t[:, :, 7]
     spread = (gt.max(axis=1) - gt.min(axis=1)) / 1e3
     total = np.diff(tl[:, :, 7].astype(np.float64), axis=0)[[i - 1 for i in idx if i > 0]] / 1e3 if idx[0] > 0 else None
-    print(f"{kn:8s} wait {wait.mean():6.2f} (max-cta {wait.max(axis=1).mean():6.2f})  quant {quant.mean():5.2f}  compute {comp.mean():6.2f} "
+    setup = (t[:, :, 8] - t[:, :, 2]) / MHZ
+    regld = (t[:, :, 9] - t[:, :, 8]) / MHZ
+    print(f"{kn:8s} setup {setup.mean():5.2f} regload {regld.mean():5.2f} | wait {wait.mean():6.2f} (max-cta {wait.max(axis=1).mean():6.2f})  quant {quant.mean():5.2f}  compute {comp.mean():6.2f} "
           f"(min {comp.min(axis=1).mean():5.2f} max {comp.max(axis=1).mean():5.2f})  publish {pub.mean():5.2f}  "
           f"producer lead {prod_lead.mean():6.2f} span {prod_span.mean():6.2f}  op-start spread {spread.mean():5.2f} us")
 per_op = np.diff(tl[:, 0, 7].astype(np.float64)) / 1e3

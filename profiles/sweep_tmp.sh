@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-for v in "A=1" "NS_PROG_PF_UNITS=32" "NS_PROG_PF_UNITS=64" "NS_PROG_PF_UNITS=128" "NS_PROG_PF_UNITS=64 NS_PROG_INFLIGHT=15" "NS_PROG_INFLIGHT=15" "NS_PROG_BATCH=8 NS_PROG_INFLIGHT=8" "NS_PROG_BATCH=8 NS_PROG_INFLIGHT=8 NS_PROG_PF_UNITS=64" "NS_PROG_BATCH=30" "BARRIER=0 NS_PROG_PF_UNITS=64"; do echo "== $v"; env $v timeout 200 python profiles/prog_timeline.py 2>&1 | tail -56 | head -11; done
+timeout 300 python -m pytest tests/test_gpu_program.py -x -q 2>&1 | tail -5
+for v in "A=1" "TAGS=1" "BARRIER=0" "TAGS=1 NS_PROG_GROUP_KB=13"; do echo "== $v"; env $v timeout 200 python profiles/prog_timeline.py 2>&1 | tail -56 | head -8; done

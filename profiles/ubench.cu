@@ -168,6 +168,59 @@ __global__ void pipe_kernel(int iters, unsigned* sink, unsigned long long* out) 
   sink[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ c0 ^ c1 ^ c2 ^ c3 ^ __float_as_uint(f0 + f1 + f2 + f3);
 }
 
+// ---- T4: TMA 1-D bulk-copy streaming rate: one producer warp per CTA, `lanes` lanes each issuing copies of `bytes` bytes into a
+// ring of `slots` slots (one mbarrier each); a consumer thread waits for each slot and frees it at once (no compute).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(64, 1) tma_stream_kernel(const unsigned char* src, size_t total_bytes, int bytes, int slots, int lanes,
+                                                           unsigned long long* out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t full0 = base + (uint32_t)slots * bytes, empty0 = full0 + 8u * slots;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < slots; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full0 + 8 * s));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty0 + 8 * s));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const size_t per_cta = total_bytes / gridDim.x / bytes * bytes;
+  const int n = (int)(per_cta / bytes);
+  const unsigned char* my = src + (size_t)blockIdx.x * per_cta;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned long long t0 = clk64();
+  if (warp == 0) {
+    for (int i0 = 0; i0 < n; i0 += lanes) {
+      const int i = i0 + lane;
+      if (lane < lanes && i < n) {
+        const int s = i % slots, lap = i / slots;
+        if (lap > 0) {
+          uint32_t ok;
+          do {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(empty0 + 8 * s), "r"((uint32_t)(lap - 1) & 1u) : "memory");
+          } while (!ok);
+        }
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8 * s), "r"((uint32_t)bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(base + (uint32_t)s * bytes),
+                     "l"(my + (size_t)i * bytes), "r"((uint32_t)bytes), "r"(full0 + 8 * s)
+                     : "memory");
+      }
+      __syncwarp();
+    }
+  } else if (lane == 0) {
+    for (int i = 0; i < n; ++i) {
+      const int s = i % slots, lap = i / slots;
+      uint32_t ok;
+      do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(full0 + 8 * s), "r"((uint32_t)lap & 1u) : "memory");
+      } while (!ok);
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * s) : "memory");
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = clk64() - t0;
+}
+
 static double med(unsigned long long* v, int n) {
   double s = 0;
   unsigned long long mx = 0;
@@ -178,7 +231,8 @@ static double med(unsigned long long* v, int n) {
   return s / n;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const bool only_t4 = argc > 1 && argv[1][0] == 't';
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
@@ -195,7 +249,7 @@ int main() {
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   const int rounds = 1000;
-  for (int per = 1; per <= 2; ++per) {
+  for (int per = 1; per <= 2 && !only_t4; ++per) {
     const int G = sms * per;
     for (int mode = 0; mode < 4; ++mode) {
       for (int threads = 288; threads <= 544; threads += 256) {
@@ -221,7 +275,7 @@ int main() {
   float* src;
   CK(cudaMalloc(&src, 1 << 20));
   CK(cudaMemset(src, 0, 1 << 20));
-  for (int per = 1; per <= 2; ++per) {
+  for (int per = 1; per <= 2 && !only_t4; ++per) {
     const int G = sms * per;
     const int threads = per == 1 ? 544 : 320;
     for (int bytes = 16384; bytes <= 65536; bytes *= 2) {
@@ -237,7 +291,7 @@ int main() {
     }
   }
   // T3
-  for (int what = 0; what < 6; ++what) {
+  for (int what = 0; what < 6 && !only_t4; ++what) {
     for (int warps = 4; warps <= 16; warps *= 2) {
       int iters = 2000;
       void* args[] = {&iters, &usink, &out};
@@ -250,6 +304,37 @@ int main() {
       printf("T3 pipe what %d warps/SM %d: %.3f cycles per warp-instr per SMSP (%.2f warp-instr/clk/SM)\n", what, warps,
              cyc / (instr_per_warp * warps / 4.0), instr_per_warp * warps / cyc);
     }
+  }
+  // T4: TMA streaming
+  {
+    const size_t total = (size_t)1 << 30;  // 1 GiB >> L2
+    unsigned char* big;
+    CK(cudaMalloc(&big, total));
+    CK(cudaMemset(big, 1, total));
+    CK(cudaFuncSetAttribute(tma_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    const int sizes[] = {1152, 2304, 4608, 9216, 23040};
+    for (int per = 1; per <= 2; ++per)
+      for (int si = 0; si < 5; ++si)
+        for (int lanes = 1; lanes <= 16; lanes *= 4) {
+          const int bytes = sizes[si];
+          const int budget = (per == 1 ? 200 : 100) * 1024;
+          int slots = budget / (bytes + 16);
+          if (slots > 64) slots = 64;
+          if (slots < lanes) continue;
+          const size_t smem = (size_t)slots * bytes + 16 * slots;
+          const int G = sms * per;
+          void* args[] = {&big, (void*)&total, (void*)&bytes, &slots, &lanes, &out};
+          for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaEventRecord(e0));
+            CK(cudaLaunchKernel((const void*)tma_stream_kernel, dim3(G), dim3(64), args, smem, 0));
+            CK(cudaEventRecord(e1));
+            CK(cudaDeviceSynchronize());
+          }
+          float ms;
+          CK(cudaEventElapsedTime(&ms, e0, e1));
+          printf("T4 tma stream: %d CTA/SM, copy %5d B, %2d slots (%3zu KB), %2d issuing lanes: %.0f GB/s\n", per, bytes, slots, smem / 1024, lanes,
+                 (double)(total / G / bytes * bytes) * G / (ms * 1e-3) / 1e9);
+        }
   }
   return 0;
 }
