@@ -29,7 +29,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 os.environ.setdefault("OMP_PROC_BIND", "false")
 
 N_EMBD, N_FF, N_LAYER, N_VOCAB = 4096, 11008, 32, 32000
@@ -92,6 +91,31 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic(kernel_substr, path=None):
+    """average dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels whose name contains `kernel_substr`, from a
+    committed `ncu --csv` launch list (cold-cache, serialised launches); (None, None) when the file is missing"""
+    import csv
+    path = path or os.path.join(ROOT, "profiles", "r02_launches_bench.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+    except OSError:
+        return None, None
+    hdr = next((r for r in rows if "Kernel Name" in r), None)
+    if not hdr:
+        return None, None
+    ki, mi, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+    per = {}
+    for r in rows:
+        if len(r) > vi and kernel_substr in r[ki] and r[mi] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            try:
+                per[r[ii]] = per.get(r[ii], 0.0) + float(r[vi].replace(",", ""))
+            except ValueError:
+                pass
+    if not per:
+        return None, None
+    return sum(per.values()) / len(per), f"ncu launch list {os.path.relpath(path, ROOT)} ({len(per)} launches of {kernel_substr})"
 
 
 # ----------------------------------------------------------------------------------------------------------- reference arm
@@ -185,6 +209,95 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------- tensor parallel leg
+def run_tp(world, rank, hbm_peak, steps):
+    """BASELINE config 5: Llama-2-70B INT4 g128, tensor parallel over `world` GPUs (strong scaling: the model is fixed, every rank
+    holds 1/world of each matmul; q/k/v/gate/up N-split, o/down K-split + one sum all-reduce each, llama.cpp:121-124,592,693).
+    All 80 layers' matmul nodes + the replicated lm_head per token, one CUDA graph per token, (a) NCCL all-reduce (b) the one-shot
+    NVLink all-reduce of csrc/comm.cu (ns_comm_*).  Device time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import neural_speed_b200 as ns
+    from neural_speed_b200 import tp
+    E, FF, H, HKV, NL, V = 8192, 28672, 64, 8, 80, 32000
+    if H % world or HKV % world:
+        return {"skipped": f"n_head_kv {HKV} not divisible by {world}"}
+    ctx = tp.TPContext(init=False)
+    plan = tp.LlamaShardPlan(world, E, FF, H, HKV, 128)
+    shapes = plan.shapes()
+    kw = dict(group=128, wfmt=ns.W_S4, stype=ns.S_F32, comp=ns.COMP_INT8, asym=False)
+    layers = [{name: ns.Weight.random(n, k, seed=1000 * rank + 7 * li + i, **kw) for i, (name, (_, n, k)) in enumerate(shapes.items())}
+              for li in range(NL)]
+    head = ns.Weight.random(V, E, seed=5, **kw)  # replicated, as the reference keeps it
+    ns.lib().bestla_device_sync(None)
+    bytes_rank = sum(w.algorithmic_bytes for lay in layers for w in lay.values()) + head.algorithmic_bytes
+    eng = tp.TPLlamaMatmuls(plan, layers, ctx)
+    x0 = torch.randn(1, E, device="cuda")
+    logits = torch.zeros(1, V, device="cuda")
+    res = {}
+    for mode in ("nccl", "nvlink_oneshot"):
+        if mode == "nvlink_oneshot":
+            ctx.enable_p2p(E)
+        stream = torch.cuda.Stream()
+        xa, xb = x0.clone(), torch.empty_like(x0)
+
+        def token():
+            cur, nxt = xa, xb
+            for li in range(NL):
+                out = eng.layer(li, cur, out=nxt)
+                cur, nxt = out, cur
+            ns.mul_mat(head, cur.data_ptr(), E, logits.data_ptr(), V, 1, queue=tp.current_queue(torch))
+            return cur
+
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                token()
+            torch.cuda.synchronize()
+            dist.barrier()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                y = token()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                g.replay()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            # the exchange alone: 2 x NL all-reduces of E floats, same graph mechanics
+            t = torch.zeros(1, E, device="cuda")
+            ga = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga, stream=stream):
+                for _ in range(2 * NL):
+                    ctx.all_reduce(t)
+            ga.replay()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0.record(stream)
+            for _ in range(10):
+                ga.replay()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ar_us = e0.elapsed_time(e1) * 1e3 / (10 * 2 * NL)
+        tm = torch.tensor([ms, ar_us], device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms, ar_us = float(tm[0]), float(tm[1])
+        assert bool(torch.isfinite(y).all())
+        res[mode] = {"ms_per_token": ms, "tokens_per_s": 1000.0 / ms, "per_gpu_GBps": bytes_rank / (ms * 1e-3) / 1e9,
+                     "per_gpu_frac": bytes_rank / (ms * 1e-3) / 1e9 / hbm_peak, "allreduce_us": ar_us}
+    best = max(res, key=lambda m: res[m]["tokens_per_s"])
+    out = {"model": "llama2-70b int4 g128 (synthetic shards), batch 1, 80 layers + replicated lm_head, matmul path + 160 all-reduces of 32 KiB",
+           "tp": world, "scaling": "strong", "tokens_per_s": res[best]["tokens_per_s"], "per_gpu_frac": res[best]["per_gpu_frac"],
+           "allreduce_us": res[best]["allreduce_us"], "exchange": best, "per_rank_packed_bytes": int(bytes_rank), **res}
+    del layers, head, eng
+    torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------- our arm
@@ -359,6 +472,9 @@ def run_ours(args):
         sampler.start()
     ms_perop = timed(run_step, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    # a leg of at least one second of back-to-back steps: sustained clocks / power rather than a 20 ms burst
+    sus_steps = max(args.steps, int(1.05 / (ms_perop * 1e-3)))
+    ms_sus = timed(run_step, sus_steps, 3)
     ms_prog = timed(lambda: prog.run(queue), args.steps, args.warmup)
     ms_step = ms_perop  # headline = the fastest complete path (one fused act-quant + GEMV launch per matmul node)
     # dominant kernel alone (graph of GEMV launches on pre-quantised activations)
@@ -462,6 +578,95 @@ def run_ours(args):
         del eng
         torch.cuda.empty_cache()
 
+    # ---- the other BASELINE.json configs, same protocol (one CUDA graph of a token's matmul nodes, CUDA events on the launching
+    # stream, weights >> L2): synthetic weight images of the right geometry (ns_weight_random: values do not matter to a
+    # bandwidth-bound path; parity of every format is covered by the tests).  Rank 0 only.
+    configs = []
+    if rank == 0 and not args.skip_configs and n_layers == N_LAYER:
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+
+        def build(shape_layer, lm_shape, **kw):
+            lays = [{nm: ns.Weight.random(n, k, seed=17 + 131 * li + i, queue=queue, **kw) for i, (nm, n, k) in enumerate(shape_layer)}
+                    for li in range(N_LAYER)]
+            head = ns.Weight.random(lm_shape[1], lm_shape[2], seed=7, queue=queue, **kw)
+            L.bestla_device_sync(queue)
+            return lays, head
+
+        def token_calls(lays, head, M, E, FF, kvd, xb, ab, qb, ob, tb, fb, lb, wsb):
+            cp = lambda t: C.c_void_p(t.data_ptr())
+            for lay in lays:
+                if kvd == E:
+                    rc = L.ns_mul_qkv(lay["wq"].h, lay["wk"].h, lay["wv"].h, cp(xb), E, cp(qb), E, M, wsb, queue)
+                else:  # grouped-query attention: k and v are narrower, three nodes (llama.cpp:223-231)
+                    rc = L.ns_mul_mat(lay["wq"].h, cp(xb), E, cp(qb), E, M, None, None, 0, wsb, queue)
+                    rc |= L.ns_mul_mat(lay["wk"].h, cp(xb), E, cp(ob), kvd, M, None, None, 0, wsb, queue)
+                    rc |= L.ns_mul_mat(lay["wv"].h, cp(xb), E, cp(ob), kvd, M, None, None, 0, wsb, queue)
+                rc |= L.ns_mul_mat(lay["wo"].h, cp(ab), E, cp(ob), E, M, None, None, 0, wsb, queue)
+                rc |= L.ns_ffn_silu(lay["w1"].h, lay["w2"].h, lay["w3"].h, cp(xb), E, cp(tb), cp(fb), E, M, wsb, queue)
+                assert rc == 0, ns.last_error()
+            if head is not None:
+                assert L.ns_mul_mat(head.h, cp(xb), E, cp(lb), N_VOCAB, M, None, None, 0, wsb, queue) == 0, ns.last_error()
+
+        def leg(name, lays, head, M, E, FF, kvd, steps, with_head=True, graph=True):
+            xb, ab = torch.randn(M, E, device="cuda"), torch.randn(M, E, device="cuda")
+            qb, ob = torch.zeros(3, M, E, device="cuda"), torch.zeros(M, E, device="cuda")
+            tb, fb = torch.zeros(2, M, FF, device="cuda"), torch.zeros(M, E, device="cuda")
+            lb = torch.zeros(M, N_VOCAB, device="cuda")
+            wsz = L.ns_device_workspace_bytes(M, FF)
+            wst = torch.zeros(wsz, dtype=torch.uint8, device="cuda")
+            wsb = C.c_void_p(wst.data_ptr())
+            torch.cuda.synchronize()
+            fn = lambda: token_calls(lays, head if with_head else None, M, E, FF, kvd, xb, ab, qb, ob, tb, fb, lb, wsb)
+            lc = L.ns_launch_count()
+            fn()
+            L.bestla_device_sync(queue)
+            nl = int(L.ns_launch_count() - lc)
+            if graph:
+                g = capture(fn)
+                run = lambda: L.ns_graph_launch(g, queue)
+            else:
+                run = fn
+            ms = timed(run, steps, 3, collective=False)
+            nbytes = sum(w.algorithmic_bytes for lay in lays for w in lay.values()) + (head.algorithmic_bytes if with_head else 0)
+            nweights = sum(w.n * w.k for lay in lays for w in lay.values()) + (head.n * head.k if with_head else 0)
+            out = {"name": name, "batch": M, "ms_per_step": ms, "tokens_per_s": M * 1000.0 / ms, "launches_per_step": nl}
+            if M <= 32:   # weight streaming bound: the packed weights are read once per step whatever the batch
+                gbs = nbytes / (ms * 1e-3) / 1e9
+                out["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                   "algorithmic_bytes_per_step": int(nbytes)}
+            else:
+                tf = 2.0 * M * nweights / (ms * 1e-3) / 1e12
+                out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak}
+            del xb, ab, qb, ob, tb, fb, lb, wst
+            return out
+
+        csteps = max(5, min(20, args.steps))
+        per7b = per_layer
+        lm7b = lm
+        # config 2: Llama-2-7B INT4 group 128 symmetric (RTN geometry: f32 scales, int8 compute), decode + 2048-token prefill
+        lays, head = build(per7b, lm7b, group=128, wfmt=ns.W_S4, stype=ns.S_F32, comp=ns.COMP_INT8, asym=False)
+        configs.append(dict(leg("llama2-7b int4 g128 sym (RTN), decode", lays, head, 1, N_EMBD, N_FF, N_EMBD, csteps), config=2))
+        configs.append(dict(leg("llama2-7b int4 g128 sym (RTN), prefill 2048", lays, head, args.prefill_tokens, N_EMBD, N_FF, N_EMBD, 3,
+                                with_head=False, graph=False), config=2))
+        del lays, head
+        torch.cuda.empty_cache()
+        # config 3: GPTQ / AWQ INT4 g128 (asymmetric zero points, bf16 scales as the reference's qpack emits), batch 1 / 8 / 32
+        lays, head = build(per7b, lm7b, group=128, wfmt=ns.W_S4, stype=ns.S_BF16, comp=ns.COMP_INT8, asym=True)
+        for M in (1, 8, 32):
+            configs.append(dict(leg(f"llama2-7b GPTQ/AWQ int4 g128 asym, batch {M}", lays, head, M, N_EMBD, N_FF, N_EMBD, csteps), config=3))
+        del lays, head
+        torch.cuda.empty_cache()
+        # config 4: Mistral-7B shapes (n_ff 14336, 8 KV heads), NF4 and INT8 weights, bf16 compute
+        MFF, MKV = 14336, 1024
+        mis = [("wq", N_EMBD, N_EMBD), ("wk", MKV, N_EMBD), ("wv", MKV, N_EMBD), ("wo", N_EMBD, N_EMBD), ("w1", MFF, N_EMBD),
+               ("w3", MFF, N_EMBD), ("w2", N_EMBD, MFF)]
+        for nm, kw in (("nf4 g32", dict(group=32, wfmt=ns.W_NF4, stype=ns.S_F32, comp=ns.COMP_BF16, asym=False)),
+                       ("int8 g32", dict(group=32, wfmt=ns.W_S8, stype=ns.S_F32, comp=ns.COMP_BF16, asym=False))):
+            lays, head = build(mis, lm7b, **kw)
+            configs.append(dict(leg(f"mistral-7b {nm}, bf16 compute, decode", lays, head, 1, N_EMBD, MFF, MKV, csteps), config=4))
+            del lays, head
+            torch.cuda.empty_cache()
+
     # ---- e2e (headline): the token through the device-backend C-ABI of INTEGRATION.md B -- what ne_device_sync does in the
     # reference's NS_SYCL slot: the token's fp32 hidden state comes from pinned HOST memory (bestla_device_memcpy H2D), the
     # matmul nodes run device-resident (one ns_graph_launch), the fp32 logits go back to pinned HOST memory (D2H), then
@@ -551,8 +756,16 @@ def run_ours(args):
         cpu = {"value": tps, "unit": "tokens/s", "cores": ref.threads, "kind": ref.kind,
                "sample": f"2 full tokens (32 layers x 7 matmuls + lm_head) after 1 warm-up, {ref.threads} OpenMP threads"}
 
+    tp_res = None
+    if world > 1 and not args.skip_tp:
+        # free the 7B replicas first: the TP leg builds its own shards
+        try:
+            tp_res = run_tp(world, rank, hbm_peak, max(5, min(20, args.steps)))
+        except Exception as e:  # the replica numbers stay valid
+            tp_res = {"error": repr(e)[:300]}
     if rank == 0:
         scale = n_layers / N_LAYER
+        traffic, traffic_src = (ncu_traffic("gemv_ring_kernel") if (args.fmt == "q4_0" and n_layers == N_LAYER) else (None, None))
         line = {
             "metric": METRIC if args.fmt == "q4_0" else METRIC.replace("Q4_0", "int4 g128 sym"),
             "value_is": "decode tokens/s (first component of the metric); prefill tok/s is prefill.tokens_per_s",
@@ -567,11 +780,11 @@ def run_ours(args):
                        "l2_policy": "inputs (3.7 GB of weights per step) exceed the 126 MB L2; no flush needed",
                        "parallelism": "replicas" if world > 1 else "single"},
             "roofline": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, averaged over the 903 launches of
-                         # the committed ncu list profiles/r01_launches_bench_final.csv (same command, same synthetic weights; the
-                         # weights are read exactly once: 28.89 MB against 28.81 MB algorithmic); null for other formats / sizes
-                         "traffic": 28891941 if (args.fmt == "q4_0" and n_layers == N_LAYER) else None,
-                         "traffic_source": "ncu launch list, profiles/r01_launches_bench_final.csv", "kernel": "gemv_ring_kernel<S8,M=1,sym,f16> (fused Q8_0 activation quantisation)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, parsed at run time from the
+                         # committed ncu launch list of this same command (profiles/r02_launches_bench.csv); null when that
+                         # file is absent or the workload differs (other formats / layer counts)
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "gemv_ring_kernel<S8,M=1,sym,f16> (fused Q8_0 activation quantisation)",
                          "launches_per_step": launches_per_step, "avg_launch_us": ms_step * 1e3 / max(1, launches_per_step),
                          "peak_source": peak_kind, "algorithmic_bytes_per_launch": int(alg_bytes // max(1, launches_per_step)),
                          "note": "the timed region contains only this kernel (129 launches per token, one CUDA graph, PDL)",
@@ -580,7 +793,9 @@ def run_ours(args):
                                               "launches": n_gemv}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step, "clocks": clocks, "setup_s": setup_s,
-            "prefill": prefill, "decode_engine": engine,
+            "sustained": {"steps": sus_steps, "ms_per_step": ms_sus, "tokens_per_s": world * 1000.0 / ms_sus,
+                          "frac": (alg_bytes / (ms_sus * 1e-3) / 1e9) / hbm_peak, "note": "the same step repeated for >= 1 s"},
+            "prefill": prefill, "decode_engine": engine, "configs": configs, "tp": tp_res,
             "persistent_program": {"tokens_per_s": world * 1000.0 / ms_prog, "ms_per_step": ms_prog, "launches_per_step": 1,
                                    "frac": prog_gbs / hbm_peak,
                                    "note": "same matmuls as ONE cooperative launch (ns_program, grid barrier between nodes)"},
@@ -610,6 +825,8 @@ def main():
     ap.add_argument("--gen-tokens", type=int, default=128)
     ap.add_argument("--prefill-tokens", type=int, default=2048)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="skip the BASELINE configs 2-4 legs")
+    ap.add_argument("--skip-tp", action="store_true", help="N > 1: skip the Llama-2-70B tensor-parallel leg (config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 20:

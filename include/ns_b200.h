@@ -311,6 +311,9 @@ NS_API unsigned long long ns_llama_kv_bytes(const ns_llama* ctx);
  * the hosts exchange the ns_comm_get_handle blobs (e.g. torch.distributed all_gather) and call ns_comm_open_peers.
  * Every rank gets bit-identical sums (fixed rank order).  max_elems bounds n of later calls. */
 typedef struct ns_comm ns_comm;
+/* several ranks' communicators inside ONE process (loopback on one device, or one host process driving peer-enabled GPUs): wire
+ * them by plain device pointers instead of cudaIpc handles; comms[r] is rank r */
+NS_API int ns_comm_link_local(ns_comm* const* comms, int world);
 NS_API size_t ns_comm_handle_bytes(void);
 NS_API ns_comm* ns_comm_create(int rank, int world, size_t max_elems, void* queue);
 NS_API int ns_comm_get_handle(ns_comm* c, void* handle_out);

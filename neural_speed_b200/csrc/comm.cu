@@ -166,6 +166,30 @@ extern "C" int ns_comm_open_peers(ns_comm* c, const void* all_handles) {
   return NS_OK;
 }
 
+// Same-process wiring (several ranks' communicators living in one process, e.g. a loopback test of the exchange kernel with all
+// ranks on ONE device, or a single-process multi-GPU host with peer access enabled): the ranks' buffers are plain device
+// pointers, no cudaIpc handles.  comms[r] must be rank r of the same world, all with the same max_elems.
+extern "C" int ns_comm_link_local(ns_comm* const* comms, int world) {
+  if (!comms || world < 1 || world > kMaxWorld) return NS_E_INVALID;
+  for (int r = 0; r < world; ++r)
+    if (!comms[r] || comms[r]->rank != r || comms[r]->world != world || comms[r]->max_elems != comms[0]->max_elems) {
+      ns_set_error("ns_comm_link_local: communicator %d does not match (rank / world / max_elems)", r);
+      return NS_E_INVALID;
+    }
+  const size_t slot_bytes = ns_round_up((size_t)2 * world * comms[0]->max_elems * sizeof(float), 256);
+  for (int me = 0; me < world; ++me) {
+    ns_comm* c = comms[me];
+    for (int r = 0; r < world; ++r) {
+      c->peer_base[r] = comms[r]->local;
+      c->peers.slots[r] = (float*)comms[r]->local;
+      c->peers.flags[r] = (unsigned int*)((char*)comms[r]->local + slot_bytes);
+    }
+    c->ctl = c->peers.flags[me] + 2 * world + 1;
+    c->ready = true;
+  }
+  return NS_OK;
+}
+
 // in-place: data[0..n) = sum over ranks (+ residual).  Every rank must call it with the same n, in the same order.
 extern "C" int ns_comm_all_reduce_f32(ns_comm* c, float* data, size_t n, const float* residual, void* queue) {
   if (!c || !c->ready || !data || n == 0 || n > c->max_elems || (n & 3) || ((uintptr_t)data & 15) || ((uintptr_t)residual & 15)) {

@@ -151,3 +151,62 @@ def test_two_gpu_tensor_parallel_layer():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_one_gpu_loopback_of_the_exchange_and_the_k_split(world):
+    """The tensor-parallel exchange on ONE device: `world` ranks' communicators live in this process (ns_comm_link_local wires
+    their buffers by pointer instead of cudaIpc), every rank runs its all-reduce kernel on its own stream, so the kernels are
+    co-resident and really wait on each other's flags.  The partials come from a K-split o-projection (ns_split_weight shards,
+    model_files.h:1650-1672): the reduced result must equal the unsplit matmul within the fp32-compute tolerance, every rank must
+    hold bit-identical sums, and the step counters must survive many back-to-back steps (both parities, CUDA-graph-style replay)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes as C
+    import neural_speed_b200 as ns
+    import oracle
+    from neural_speed_b200 import tp
+    L = ns.lib()
+    L.bestla_init()
+    L.ns_comm_link_local.argtypes = [C.c_void_p, C.c_int]
+    n, k, g = 1024, 2048, 128
+    rng = np.random.default_rng(77)
+    w = rng.uniform(-0.05, 0.05, (n, k)).astype(np.float32)
+    blob = ns.np_bestla_quantize(w, "int4", g, "sym", "fp32", "fp32")
+    x = rng.uniform(-0.5, 0.5, (1, k)).astype(np.float32)
+    res = rng.normal(0, 1, (1, n)).astype(np.float32)
+    kl = k // world
+    shards = [ns.Weight.from_blob(tp.split_blob(blob, n, k, world, r, tp.SPLIT_K)) for r in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    comms = [C.c_void_p(L.ns_comm_create(r, world, n, None)) for r in range(world)]
+    assert all(c.value for c in comms), ns.last_error()
+    arr = (C.c_void_p * world)(*[c.value for c in comms])
+    assert L.ns_comm_link_local(arr, world) == 0, ns.last_error()
+    xs = [torch.from_numpy(np.ascontiguousarray(x[:, r * kl:(r + 1) * kl])).cuda() for r in range(world)]
+    resid = torch.from_numpy(res).cuda()
+    parts = [torch.zeros(1, n, device="cuda") for _ in range(world)]
+    torch.cuda.synchronize()
+    want = None
+    for step in range(5):  # both parities of the slot buffers, several wraps of the arrival counters
+        for r in range(world):
+            q = C.c_void_p(streams[r].cuda_stream)
+            ns.mul_mat(shards[r], xs[r].data_ptr(), kl, parts[r].data_ptr(), n, 1, queue=q)
+            rc = L.ns_comm_all_reduce_f32(comms[r], C.c_void_p(parts[r].data_ptr()), n, C.c_void_p(resid.data_ptr()), q)
+            assert rc == 0, ns.last_error()
+        torch.cuda.synchronize()
+        got = [p.cpu().numpy().copy() for p in parts]
+        for r in range(1, world):
+            assert np.array_equal(got[0], got[r]), f"rank {r} differs from rank 0 at step {step}"
+        if want is None:
+            wdq = ns.unpack_blob(blob, n, k)  # [K, N]
+            want = oracle.gemm_f64acc(x, wdq) + res
+            # shards are re-quantised slices (bestla_split_weight): compare against THEIR dequantised sum as well
+            sh = sum(oracle.gemm_f64acc(np.ascontiguousarray(x[:, r * kl:(r + 1) * kl]),
+                                        ns.unpack_blob(tp.split_blob(blob, n, k, world, r, tp.SPLIT_K), n, kl)).astype(np.float64)
+                     for r in range(world)) + res
+            assert np.abs(got[0] - sh).max() <= 1e-3
+            assert np.abs(got[0] - want).max() <= 0.2  # re-quantising the int4 slices moves the weights a little (outputs are O(1))
+        for r in range(world):
+            assert L.ns_comm_status(comms[r]) == 0
+    for c in comms:
+        L.ns_comm_free(c)
