@@ -563,7 +563,9 @@ extern "C" size_t ns_device_workspace_bytes(int m, int k) {
   const int kpad = (int)ns_round_up((size_t)k, 32);
   const size_t gemv = ns_act_workspace_bytes(4, kpad);  // GEMV path: activations are prepared in tiles of <= 4 rows
   const size_t tc = m > 4 ? ns_gemm_tc_workspace_bytes(m, kpad) : 0;  // tensor-core path: bf16 [m][kpad]
-  return gemv > tc ? gemv : tc;
+  const size_t im = (m > 4 && m <= 32) ? ns_gemm_imma_workspace_bound(m, kpad) : 0;  // integer tensor-core path
+  const size_t a = gemv > tc ? gemv : tc;
+  return a > im ? a : im;
 }
 
 static void* pick_ws(void* workspace, cudaStream_t st, size_t bytes) { return workspace ? workspace : scratch_get(st, bytes); }
@@ -574,6 +576,11 @@ static bool use_tc(const ns_weight* w, int m, int flags) {
   // Measured on 4096x4096 Q4_0 (profiles/r01_summary.md): the tensor-core GEMM costs ~30 us at small M (pipeline fill, split-K
   // epilogue) while a 4-row GEMV tile costs ~7 us and keeps the exact-integer numerics: GEMV tiles win up to 16 rows.
   return m > 16 || (flags & NS_MM_FORCE_TC);
+}
+// 5..32 rows of an int4 weight with an integer compute type: integer tensor cores, exact block sums, weights read once
+static bool use_imma(const ns_weight* const* ws, int nw, int m, int flags) {
+  if (flags & (NS_MM_FORCE_GEMV | NS_MM_FORCE_TC)) return false;
+  return ns_gemm_imma_supported(ws, nw, m);
 }
 static size_t ws_need(const ns_weight* w, int m, bool tc) {
   return tc ? ns_gemm_tc_workspace_bytes(m, w->kpad) : ns_act_workspace_bytes(4, w->kpad);
@@ -599,6 +606,11 @@ extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* 
         return rc;
     }
     return NS_OK;
+  }
+  if (use_imma(&w, 1, m, flags)) {
+    void* wsi = pick_ws(workspace, st, ns_gemm_imma_workspace_bound(m, w->kpad));
+    if (!wsi) return NS_E_CUDA;
+    return ns_launch_gemm_imma(&w, 1, NS_GEMV_PLAIN, act, lda, dst, ldo, m, bias, bcast, residual, NS_ELT_DEFAULT, wsi, st);
   }
   const bool tc = use_tc(w, m, flags);
   void* ws = pick_ws(workspace, st, ws_need(w, m, tc));
@@ -628,11 +640,16 @@ extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_wei
   if (int rc = ns_ensure_device()) return rc;
   if (!wq || !wk || !wv || !act || !dst || m <= 0) return NS_E_INVALID;
   cudaStream_t st = stream_of(queue);
+  const ns_weight* wl[3] = {wq, wk, wv};
+  if (use_imma(wl, 3, m, 0) && !(wq->n % 2) && !(wk->n % 2)) {
+    void* wsi = pick_ws(workspace, st, ns_gemm_imma_workspace_bound(m, wq->kpad));
+    if (!wsi) return NS_E_CUDA;
+    return ns_launch_gemm_imma(wl, 3, NS_GEMV_CONCAT, act, lda, dst, ldo, m, nullptr, 0, nullptr, NS_ELT_DEFAULT, wsi, st);
+  }
   const bool tc = use_tc(wq, m, 0) && ns_gemm_tc_supported(wk) && ns_gemm_tc_supported(wv) && wk->k == wq->k &&
                   wv->k == wq->k && !wq->shuffle && !wk->shuffle && !wv->shuffle;
   void* ws = pick_ws(workspace, st, ws_need(wq, m, tc));
   if (!ws) return NS_E_CUDA;
-  const ns_weight* wl[3] = {wq, wk, wv};
   if (tc) {
     if (int rc = ns_launch_act_bf16(wq, act, lda, m, ws, st)) return rc;
     for (int i = 0; i < 3; ++i)
@@ -670,6 +687,19 @@ static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w
   const bool tc = use_tc(w1, m, 0) && ns_gemm_tc_supported(w2) && (!w3 || ns_gemm_tc_supported(w3)) && !w1->shuffle &&
                   !(w3 && w3->shuffle);
   const int kmax = w1->kpad > w2->kpad ? w1->kpad : w2->kpad;
+  {
+    const ns_weight* gu2[2] = {w1, w3};
+    if (use_imma(gu2, w3 ? 2 : 1, m, 0) && use_imma(&w2, 1, m, 0)) {
+      void* wsi = pick_ws(workspace, st, ns_gemm_imma_workspace_bound(m, kmax));
+      if (!wsi) return NS_E_CUDA;
+      if (w3) {
+        if (int rc = ns_launch_gemm_imma(gu2, 2, NS_GEMV_GATE_UP_SILU, act, lda, tmp, fmid, m, nullptr, 0, nullptr, eltop, wsi, st)) return rc;
+      } else {
+        if (int rc = ns_launch_gemm_imma(gu2, 1, NS_GEMV_PLAIN, act, lda, tmp, fmid, m, b1, bcast, nullptr, NS_ELT_GELU, wsi, st)) return rc;
+      }
+      return ns_launch_gemm_imma(&w2, 1, NS_GEMV_PLAIN, tmp, fmid, dst, ldo, m, b2, bcast, residual, NS_ELT_DEFAULT, wsi, st);
+    }
+  }
   void* ws = pick_ws(workspace, st, tc ? ns_gemm_tc_workspace_bytes(m, kmax) : ns_act_workspace_bytes(4, kmax));
   if (!ws) return NS_E_CUDA;
   if (tc) {

@@ -597,8 +597,10 @@ static int ensure_buffers(ns_llama* c, int m) {
   size_t wsb = ns_act_workspace_bytes(4, (int)ns_round_up((size_t)kmax, 32));
   const size_t tcb = ns_gemm_tc_workspace_bytes(m, (int)ns_round_up((size_t)kmax, 32));
   const size_t q6 = ns_q6k_workspace_bytes(4, kmax);
+  const size_t imb = ns_gemm_imma_workspace_bound(m > 32 ? 32 : (m < 5 ? 5 : m), (int)ns_round_up((size_t)kmax, 32));
   wsb = wsb > tcb ? wsb : tcb;
   wsb = wsb > q6 ? wsb : q6;
+  wsb = wsb > imb ? wsb : imb;
   c->ws = dev_alloc(c, wsb);
   c->ws_bytes = wsb;
   if (!c->x || !c->xn || !c->qkv || !c->attn || !c->tmp || !c->ws) return NS_E_CUDA;

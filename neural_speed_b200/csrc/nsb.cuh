@@ -106,6 +106,12 @@ int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, i
 int ns_launch_silu_mul(const float* g, const float* u, float* out, float* aux, size_t total, cudaStream_t st, int eltop = 0);
 int ns_launch_gelu(float* x, size_t total, cudaStream_t st);
 
+// integer tensor-core path for 5..32 activation rows (gemm_imma.cu); modes and epilogue arguments as ns_launch_gemv
+bool ns_gemm_imma_supported(const ns_weight* const* ws, int nw, int m);
+size_t ns_gemm_imma_workspace_bound(int m, int kpad);  // enough for any weight shape the launcher accepts
+int ns_launch_gemm_imma(const ns_weight* const* ws, int nw, int mode, const float* act, int lda, float* dst, int ldo, int m,
+                        const float* bias, int bias_bcast, const float* residual, int eltop, void* workspace, cudaStream_t st);
+
 enum { NS_GEMV_PLAIN = 0, NS_GEMV_CONCAT = 1, NS_GEMV_GATE_UP_SILU = 2 };
 // element-wise epilogue op (bestla.h:89 BTLA_ELTWISEOP): DEFAULT = Swish(alpha=-1) in gate/up mode, nothing otherwise
 enum { NS_ELT_DEFAULT = 0, NS_ELT_GELU = 1 };

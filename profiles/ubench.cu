@@ -112,6 +112,7 @@ template <int WHAT>
 __global__ void pipe_kernel(int iters, unsigned* sink, unsigned long long* out) {
   unsigned a0 = threadIdx.x, a1 = threadIdx.x * 3, a2 = 7, a3 = 11, b0 = blockIdx.x | 0x01010101u, b1 = 0x0f0f0f0fu ^ threadIdx.x;
   int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  int d0 = 0, d1 = 0, d2 = 0, d3 = 0, e0 = 0, e1 = 0, e2 = 0, e3 = 0, g0 = 0, g1 = 0, g2 = 0, g3 = 0;
   float f0 = 1.f, f1 = 2.f, f2 = 0.5f, f3 = 0.25f;
   __syncthreads();
   const unsigned long long t0 = clk64();
@@ -144,6 +145,16 @@ __global__ void pipe_kernel(int iters, unsigned* sink, unsigned long long* out) 
         asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(f1) : "f"(f2), "f"(f3));
         asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(f2) : "f"(f0), "f"(f3));
         asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(f3) : "f"(f1), "f"(f0));
+      } else if (WHAT == 6) {
+        // integer tensor-core MMA as sm_100a still offers it to mma.sync: m16n8k32 u8 x s8 -> s32, four independent accumulators
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+r"(d0), "+r"(d1), "+r"(d2), "+r"(d3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b1), "r"(b0));
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3) : "r"(a1), "r"(a0), "r"(a3), "r"(a2), "r"(b0), "r"(b1));
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+r"(g0), "+r"(g1), "+r"(g2), "+r"(g3) : "r"(a1), "r"(a0), "r"(a3), "r"(a2), "r"(b1), "r"(b0));
       } else {
         // one row-chunk: 4 words -> 8 lop, 8 dp4a (two chains), lea.hi-like add, i2f, fmul, ffma
         unsigned w[4] = {a0 + u, a1 + u, a2 + u, a3 + u};
@@ -165,7 +176,8 @@ __global__ void pipe_kernel(int iters, unsigned* sink, unsigned long long* out) 
   }
   const unsigned long long t1 = clk64();
   if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
-  sink[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ c0 ^ c1 ^ c2 ^ c3 ^ __float_as_uint(f0 + f1 + f2 + f3);
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ c0 ^ c1 ^ c2 ^ c3 ^ d0 ^ d1 ^ d2 ^ d3 ^ e0 ^ e1 ^ e2 ^ e3 ^ g0 ^ g1 ^ g2 ^ g3 ^
+                                                   __float_as_uint(f0 + f1 + f2 + f3);
 }
 
 // ---- T4: TMA 1-D bulk-copy streaming rate: one producer warp per CTA, `lanes` lanes each issuing copies of `bytes` bytes into a
@@ -232,6 +244,7 @@ static double med(unsigned long long* v, int n) {
 }
 
 int main(int argc, char** argv) {
+  const bool only_t3b = argc > 1 && argv[1][0] == 'm';  // only the integer-MMA rate
   const bool only_t4 = argc > 1 && argv[1][0] == 't';
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -249,7 +262,7 @@ int main(int argc, char** argv) {
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   const int rounds = 1000;
-  for (int per = 1; per <= 2 && !only_t4; ++per) {
+  for (int per = 1; per <= 2 && !only_t4 && !only_t3b; ++per) {
     const int G = sms * per;
     for (int mode = 0; mode < 4; ++mode) {
       for (int threads = 288; threads <= 544; threads += 256) {
@@ -275,7 +288,7 @@ int main(int argc, char** argv) {
   float* src;
   CK(cudaMalloc(&src, 1 << 20));
   CK(cudaMemset(src, 0, 1 << 20));
-  for (int per = 1; per <= 2 && !only_t4; ++per) {
+  for (int per = 1; per <= 2 && !only_t4 && !only_t3b; ++per) {
     const int G = sms * per;
     const int threads = per == 1 ? 544 : 320;
     for (int bytes = 16384; bytes <= 65536; bytes *= 2) {
@@ -291,11 +304,11 @@ int main(int argc, char** argv) {
     }
   }
   // T3
-  for (int what = 0; what < 6 && !only_t4; ++what) {
+  for (int what = (only_t3b ? 6 : 0); what < 7 && !only_t4; ++what) {
     for (int warps = 4; warps <= 16; warps *= 2) {
       int iters = 2000;
       void* args[] = {&iters, &usink, &out};
-      const void* k = what == 0 ? (const void*)pipe_kernel<0> : what == 1 ? (const void*)pipe_kernel<1> : what == 2 ? (const void*)pipe_kernel<2> : what == 3 ? (const void*)pipe_kernel<3> : what == 4 ? (const void*)pipe_kernel<4> : (const void*)pipe_kernel<5>;
+      const void* k = what == 0 ? (const void*)pipe_kernel<0> : what == 1 ? (const void*)pipe_kernel<1> : what == 2 ? (const void*)pipe_kernel<2> : what == 3 ? (const void*)pipe_kernel<3> : what == 4 ? (const void*)pipe_kernel<4> : what == 5 ? (const void*)pipe_kernel<5> : (const void*)pipe_kernel<6>;
       CK(cudaLaunchKernel(k, dim3(sms), dim3(warps * 32), args, 0, 0));
       CK(cudaDeviceSynchronize());
       CK(cudaMemcpy(hout, out, sms * 8, cudaMemcpyDeviceToHost));
@@ -306,7 +319,7 @@ int main(int argc, char** argv) {
     }
   }
   // T4: TMA streaming
-  {
+  if (!only_t3b) {
     const size_t total = (size_t)1 << 30;  // 1 GiB >> L2
     unsigned char* big;
     CK(cudaMalloc(&big, total));
