@@ -563,7 +563,7 @@ extern "C" size_t ns_device_workspace_bytes(int m, int k) {
   const int kpad = (int)ns_round_up((size_t)k, 32);
   const size_t gemv = ns_act_workspace_bytes(4, kpad);  // GEMV path: activations are prepared in tiles of <= 4 rows
   const size_t tc = m > 4 ? ns_gemm_tc_workspace_bytes(m, kpad) : 0;  // tensor-core path: bf16 [m][kpad]
-  const size_t im = (m > 4 && m <= 32) ? ns_gemm_imma_workspace_bound(m, kpad) : 0;  // integer tensor-core path
+  const size_t im = (m > 1 && m <= 32) ? ns_gemm_imma_workspace_bound(m, kpad) : 0;  // integer tensor-core path
   const size_t a = gemv > tc ? gemv : tc;
   return a > im ? a : im;
 }

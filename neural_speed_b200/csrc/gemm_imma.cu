@@ -55,6 +55,7 @@ struct ImmaParams {
   float* partial;     // [ksplit][tiles][MT][BN]
   unsigned* tickets;  // [tiles], zero on entry (act_quant_imma_kernel clears them), zero again on exit
   int sc_row;         // bytes per row of the staged scales (+ zero points)
+  int sc_zp;          // offset of the zero points inside a staged row
   int stages;
 };
 
@@ -116,6 +117,21 @@ __device__ __forceinline__ void imma(int (&c)[4], const uint32_t (&a)[4], uint32
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+
+// the same with a zero accumulator input: d = a x b (block size 32: every chunk is flushed, nothing to carry)
+template <bool ACT_U8>
+__device__ __forceinline__ void imma0(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (ACT_U8)
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(0));
+  else
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(0));
+}
+// exact int -> float for |i| < 2^22 without the quarter-rate I2F: (float)(i + 0x4B400000 as float bits) - 12582912
+__device__ __forceinline__ float i2f_small(int i) { return __int_as_float(i + 0x4B400000) - 12582912.f; }
 
 // ---- activation image ------------------------------------------------------------------------------------------------
 // One warp per (token, activation block).  Same arithmetic as act_quant_kernel<COMP> (act_prep.cu) -- bit-exact codes, scales,
@@ -230,8 +246,8 @@ __device__ __forceinline__ float lds_scale_b(uint32_t a) {  // a: byte address o
   return __uint_as_float((uint32_t)h << 16);
 }
 
-template <bool ACT_U8, int MT, bool ASYM, int STYPE>
-__global__ void __launch_bounds__(kThr, 1)
+template <bool ACT_U8, int MT, bool ASYM, int STYPE, bool P1>  // P1: activation blocks of one chunk (32): flush every chunk
+__global__ void __launch_bounds__(kThr, 2)
     gemm_imma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                      const __grid_constant__ CUtensorMap map2, const ImmaParams P) {
   constexpr int NTB = MT / 8;
@@ -310,48 +326,63 @@ __global__ void __launch_bounds__(kThr, 1)
   }
 
   // ===================== consumers =====================
-  // stage the scales (+ zero points) of this CTA's rows and K range: constant data, read before the dependency wait
+  // stage the scales (+ zero points) of this CTA's rows and K range: constant data, read before the dependency wait.
+  // 16-byte segments (the range starts wherever group g0 falls: keep its misalignment inside the staged row), all loads of a
+  // thread issued before the first store -- a scalar loop here cost more than the whole matmul.
   const int g0 = (sl0 * 8) >> P.cpg_shift;                          // first weight group of the range
   const int ng = ((sl1 * 8 + P.cpg - 1) >> P.cpg_shift) - g0;       // groups in the range
+  const int dsc = (SS * g0) & 15, dzp = g0 & 15;                    // sc_off and zp_off are 16-byte multiples
+  const int nsc = (dsc + SS * ng + 15) >> 4, nzp = ASYM ? (dzp + ng + 15) >> 4 : 0;
+  const int scb = P.sc_zp;                                          // byte offset of the zero-point area in a staged row
   {
-    const int total_groups = (P.k + P.group - 1) / P.group;
-    const int per_row = ng;
-    for (int idx = threadIdx.x; idx < BN * per_row; idx += kCons * 32) {
-      const int r = idx / per_row, gi = idx - r * per_row;
-      int row, w = wi;
-      if (gate_up) {
-        w = r >= BN / 2 ? 1 : 0;
-        row = r0 + (r & (BN / 2 - 1));
-      } else {
-        row = r0 + r;
+    const int nseg = nsc + nzp;
+    constexpr int U = 4;
+    for (int i0 = threadIdx.x; i0 < BN * nseg; i0 += U * kCons * 32) {
+      uint4 v[U];
+      uint32_t d[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = i0 + u * kCons * 32;
+        d[u] = 0u;
+        if (idx < BN * nseg) {
+          const int r = idx / nseg, sg = idx - r * nseg;
+          int row, w = wi;
+          if (gate_up) {
+            w = r >= BN / 2 ? 1 : 0;
+            row = r0 + (r & (BN / 2 - 1));
+          } else {
+            row = r0 + r;
+          }
+          if (row >= P.n[w]) row = 0;  // overhang rows: any valid data, the epilogue masks them
+          const uint8_t* src = P.rows[w] + (size_t)row * P.pitch;
+          if (sg < nsc) {
+            src += ((P.sc_off + SS * g0) & ~15) + 16 * sg;
+            d[u] = sc_s + (uint32_t)r * P.sc_row + 16u * sg;
+          } else {
+            src += ((P.zp_off + g0) & ~15) + 16 * (sg - nsc);
+            d[u] = sc_s + (uint32_t)r * P.sc_row + scb + 16u * (sg - nsc);
+          }
+          v[u] = __ldg(reinterpret_cast<const uint4*>(src));
+        }
       }
-      const bool ok = row < P.n[w] && g0 + gi < total_groups;
-      const uint8_t* src = P.rows[w] + (size_t)(ok ? row : 0) * P.pitch;
-      const uint32_t d = sc_s + (uint32_t)r * P.sc_row;
-      if (SS == 4) {
-        const uint32_t v = ok ? *reinterpret_cast<const uint32_t*>(src + P.sc_off + 4 * (g0 + gi)) : 0u;
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(d + 4 * gi), "r"(v) : "memory");
-      } else {
-        const unsigned short v = ok ? *reinterpret_cast<const unsigned short*>(src + P.sc_off + 2 * (g0 + gi)) : (unsigned short)0;
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(d + 2 * gi), "h"(v) : "memory");
-      }
-      if (ASYM) {
-        const unsigned short z = ok ? (unsigned short)src[P.zp_off + g0 + gi] : (unsigned short)0;
-        asm volatile("st.shared.u8 [%0], %1;" ::"r"(d + (uint32_t)SS * per_row + gi), "h"(z) : "memory");
-      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (d[u]) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(d[u]), "r"(v[u].x), "r"(v[u].y), "r"(v[u].z), "r"(v[u].w) : "memory");
     }
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kCons * 32) : "memory");
 
   const int g = lane >> 2, t = lane & 3;
   const int rA = warp * 16 + g, rB = rA + 8;  // rows of this thread inside the tile
-  const uint32_t scA = sc_s + (uint32_t)rA * P.sc_row, scB = sc_s + (uint32_t)rB * P.sc_row;
-  const uint32_t zpo = (uint32_t)SS * ng;
+  const uint32_t scA = sc_s + (uint32_t)rA * P.sc_row + dsc, scB = sc_s + (uint32_t)rB * P.sc_row + dsc;
+  const uint32_t zpo = (uint32_t)(scb + dzp - dsc);
+  const int nchunks = (P.k + 31) >> 5;
   // ldmatrix row address of this lane: matrices 0/1 = rows +0..7 / +8..15 of chunk j, matrices 2/3 = the same rows of chunk j+1
   const int lrow = warp * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
   const int lsel = lane >> 4;  // 0: chunk j, 1: chunk j + 1
-  const uint32_t lrow_off = (uint32_t)lrow * 128u;
-  const int lx = lrow & 7;
+  // 128B swizzle: 16-byte unit index ^ (row & 7).  chunk j2 + lsel with j2 even = j2 ^ lsel, so the per-thread part of the
+  // address is fixed and the chunk pair enters as one XOR
+  const uint32_t lthread = (uint32_t)lrow * 128u + ((uint32_t)(lsel ^ (lrow & 7)) << 4);
 
   float acc[NTB][4];
   int ci[NTB][4];
@@ -375,7 +406,7 @@ __global__ void __launch_bounds__(kThr, 1)
 #pragma unroll
     for (int j2 = 0; j2 < 8; j2 += 2) {
       uint32_t w0, w1, w2, w3;
-      ldmatrix_x4(qs + lrow_off + ((uint32_t)((j2 + lsel) ^ lx) << 4), w0, w1, w2, w3);
+      ldmatrix_x4(qs + (lthread ^ ((uint32_t)j2 << 4)), w0, w1, w2, w3);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int j = j2 + h;
@@ -384,11 +415,15 @@ __global__ void __launch_bounds__(kThr, 1)
 #pragma unroll
         for (int tb = 0; tb < NTB; ++tb) {
           const uint2 b = lds64(as + (uint32_t)j * (MT * 32) + (uint32_t)(tb * 8 + g) * 32u + 8u * t);
-          imma<ACT_U8>(ci[tb], a, b.x, b.y);
+          if (P1) imma0<ACT_U8>(ci[tb], a, b.x, b.y);
+          else imma<ACT_U8>(ci[tb], a, b.x, b.y);
         }
-        if (ACT_U8) imma<true>(cs, a, 0x01010101u, 0x01010101u);  // row sums of the weight codes (zero-point term)
+        if (ACT_U8) {  // row sums of the weight codes (zero-point term)
+          if (P1) imma0<true>(cs, a, 0x01010101u, 0x01010101u);
+          else imma<true>(cs, a, 0x01010101u, 0x01010101u);
+        }
         const int ch = (sl0 + i) * 8 + j;                         // global chunk
-        if (((ch + 1) & (period - 1)) == 0) {
+        if ((P1 || ((ch + 1) & (period - 1)) == 0) && ch < nchunks) {
           // end of an activation block: exact integer block sums -> fp32
           const int gi = (ch >> P.cpg_shift) - g0;
           const float wsA = lds_scale_b<STYPE>(scA + SS * gi), wsB = lds_scale_b<STYPE>(scB + SS * gi);
@@ -417,13 +452,13 @@ __global__ void __launch_bounds__(kThr, 1)
               i2 -= za0 * uB;
               i3 -= za1 * uB;
             }
-            acc[tb][0] = fmaf((float)i0, as0 * wsA, acc[tb][0]);
-            acc[tb][1] = fmaf((float)i1, as1 * wsA, acc[tb][1]);
-            acc[tb][2] = fmaf((float)i2, as0 * wsB, acc[tb][2]);
-            acc[tb][3] = fmaf((float)i3, as1 * wsB, acc[tb][3]);
-            ci[tb][0] = ci[tb][1] = ci[tb][2] = ci[tb][3] = 0;
+            acc[tb][0] = fmaf(i2f_small(i0), as0 * wsA, acc[tb][0]);  // |block sum| < 2^22: 256 x 255 x 15 < 1e6
+            acc[tb][1] = fmaf(i2f_small(i1), as1 * wsA, acc[tb][1]);
+            acc[tb][2] = fmaf(i2f_small(i2), as0 * wsB, acc[tb][2]);
+            acc[tb][3] = fmaf(i2f_small(i3), as1 * wsB, acc[tb][3]);
+            if (!P1) ci[tb][0] = ci[tb][1] = ci[tb][2] = ci[tb][3] = 0;
           }
-          cs[0] = cs[1] = cs[2] = cs[3] = 0;
+          if (!P1) cs[0] = cs[1] = cs[2] = cs[3] = 0;
         }
       }
     }
@@ -522,7 +557,7 @@ constexpr int kMaxPartialTiles = 640;  // tiles x ksplit when K is split
 constexpr int kMaxTiles = 16384;
 
 struct Plan {
-  int mt, tiles, ksplit, nslices, stages, sc_row;
+  int mt, tiles, ksplit, nslices, stages, sc_row, sc_zp;
   size_t smem, img_bytes, partial_bytes, ticket_bytes;
 };
 
@@ -544,23 +579,28 @@ bool make_plan(const ns_weight* const* ws, int nw, int mode, int m, Plan* pl) {
   const int cpg = w0->group / 32;
   const int kact = pl->mt * 320;
   const int kstage = kQStage + (kact + 1023) / 1024 * 1024;
-  // split K: CTAs run one per SM in waves; cost of a choice = waves x (slices per CTA + pipeline ramp).  The staged scales must
-  // also fit beside a ring of >= 4 stages.
+  // split K.  Two CTAs share an SM (16 consumer warps hide the MMA / shared-memory latencies; one CTA's prologue overlaps the
+  // other's main loop), so a wave has 2 x SMs slots and a CTA gets half an SM's bandwidth: cost of a choice = waves x (2 x slices
+  // per CTA + ramp).  The staged scales must fit beside a ring of >= 3 stages in half an SM's shared memory.
   static const int env_split = getenv("NS_IMMA_KSPLIT") ? atoi(getenv("NS_IMMA_KSPLIT")) : 0;
+  static const int env_budget = getenv("NS_IMMA_SMEM_KB") ? atoi(getenv("NS_IMMA_SMEM_KB")) : 0;
   const int sms = ns_num_sms();
-  const size_t budget = 221 * 1024;
+  const size_t budget = (size_t)(env_budget > 0 ? env_budget : 111) * 1024;
+  const int per_sm = budget > 112 * 1024 ? 1 : 2;
   int ksplit = 0;
   long best = -1;
   for (int ks = 1; ks <= 16 && ks <= pl->nslices; ++ks) {
     if (env_split > 0 && ks != env_split && env_split <= pl->nslices) continue;
+    if (ks > 1 && tiles * ks > kMaxPartialTiles) continue;
     const int max_sl = (pl->nslices + ks - 1) / ks;
     const int ng = ((max_sl + 1) * 8 + cpg - 1) / cpg + 1;
-    const int sc_row = (int)ns_round_up((size_t)ng * (ss + (w0->asym ? 1 : 0)), 8);
-    const size_t fixed = (size_t)BN * sc_row + 16 * 16 + 64;
-    if (fixed + (size_t)(max_sl < 4 ? max_sl : 4) * kstage > budget) continue;
-    if (ks > 1 && tiles * ks > kMaxPartialTiles) continue;
-    const long waves = ((long)tiles * ks + sms - 1) / sms;
-    const long cost = waves * (max_sl + 2) * 16 + ks;  // ties: fewer splits
+    const int sc_zp = (int)ns_round_up((size_t)15 + (size_t)ss * ng, 16);
+    const int sc_row = sc_zp + (w0->asym ? (int)ns_round_up((size_t)15 + ng, 16) : 0);
+    const size_t fixed = (size_t)BN * sc_row + 16 * 16 + 64 + 1024;
+    const int need = max_sl < 3 ? max_sl : 3;
+    if (fixed + (size_t)need * kstage > budget) continue;
+    const long waves = ((long)tiles * ks + per_sm * sms - 1) / (per_sm * sms);
+    const long cost = waves * (per_sm * max_sl + 2) * 16 + ks;  // ties: fewer splits
     if (best < 0 || cost < best) {
       best = cost;
       ksplit = ks;
@@ -569,6 +609,7 @@ bool make_plan(const ns_weight* const* ws, int nw, int mode, int m, Plan* pl) {
       if (stages > max_sl) stages = max_sl;
       pl->stages = stages;
       pl->sc_row = sc_row;
+      pl->sc_zp = sc_zp;
       pl->smem = (size_t)stages * kstage + (size_t)BN * sc_row + 16 * (size_t)stages + 64 + 1024;
     }
   }
@@ -580,9 +621,9 @@ bool make_plan(const ns_weight* const* ws, int nw, int mode, int m, Plan* pl) {
   return true;
 }
 
-template <bool ACT_U8, int MT, bool ASYM, int STYPE>
-int launch_k(const CUtensorMap* maps, const ImmaParams& P, const Plan& pl, cudaStream_t st) {
-  auto kern = gemm_imma_kernel<ACT_U8, MT, ASYM, STYPE>;
+template <bool ACT_U8, int MT, bool ASYM, int STYPE, bool P1>
+int launch_p(const CUtensorMap* maps, const ImmaParams& P, const Plan& pl, cudaStream_t st) {
+  auto kern = gemm_imma_kernel<ACT_U8, MT, ASYM, STYPE, P1>;
   static bool attr = false;
   if (!attr) {
     NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -591,6 +632,10 @@ int launch_k(const CUtensorMap* maps, const ImmaParams& P, const Plan& pl, cudaS
   NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)(pl.tiles * pl.ksplit)), dim3(kThr), pl.smem, st, maps[0], maps[1], maps[2], P));
   ns_count_launch();
   return NS_OK;
+}
+template <bool ACT_U8, int MT, bool ASYM, int STYPE>
+int launch_k(const CUtensorMap* maps, const ImmaParams& P, const Plan& pl, cudaStream_t st) {
+  return P.acpg == 1 ? launch_p<ACT_U8, MT, ASYM, STYPE, true>(maps, P, pl, st) : launch_p<ACT_U8, MT, ASYM, STYPE, false>(maps, P, pl, st);
 }
 template <bool ACT_U8, int MT, bool ASYM>
 int launch_s(const CUtensorMap* maps, const ImmaParams& P, const Plan& pl, int stype, cudaStream_t st) {
@@ -614,7 +659,8 @@ int launch_m(const CUtensorMap* maps, const ImmaParams& P, const Plan& pl, int s
 // Can this (fused) matmul of m activation rows run on the integer tensor cores?
 bool ns_gemm_imma_supported(const ns_weight* const* ws, int nw, int m) {
   static const bool off = getenv("NS_NO_IMMA") != nullptr;
-  if (off || m < 5 || m > 32 || nw < 1 || nw > 3) return false;
+  static const int min_m = getenv("NS_IMMA_MIN_M") ? atoi(getenv("NS_IMMA_MIN_M")) : 3;  // measured: the 4-row GEMV tile is slower already
+  if (off || m < min_m || m > 32 || nw < 1 || nw > 3) return false;
   const ns_weight* w0 = ws[0];
   for (int i = 0; i < nw; ++i) {
     const ns_weight* w = ws[i];
@@ -729,6 +775,7 @@ int ns_launch_gemm_imma(const ns_weight* const* ws, int nw, int mode, const floa
   P.partial = partial;
   P.tickets = tickets;
   P.sc_row = pl.sc_row;
+  P.sc_zp = pl.sc_zp;
   P.stages = pl.stages;
   static const bool dbg = getenv("NS_IMMA_DEBUG") != nullptr;
   if (dbg)

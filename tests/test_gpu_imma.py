@@ -1,4 +1,4 @@
-"""Batched decode (5..32 activation rows) on the integer tensor cores (csrc/gemm_imma.cu) against the CPU oracle.
+"""Batched decode (3..32 activation rows) on the integer tensor cores (csrc/gemm_imma.cu) against the CPU oracle.
 
 The reference runs M > 4 through its int8 GEMM cores (bestla_wrapper.h:214-350): activations quantised per K-block
 (kernel_ref.h:1825 / :1886, quantize_row_q8_0 for ggml weights), exact integer block dots, fp32 accumulation of the scaled
@@ -51,7 +51,7 @@ def close(got, want, rtol=1e-4):
 
 
 @pytest.mark.parametrize("n,k,m", [(128, 512, 8), (4096, 4096, 8), (4096, 4096, 32), (1000, 11008, 16), (257, 1024, 5), (96, 4096, 13),
-                                   (4096, 11008, 27), (300, 14336, 32), (32000, 4096, 8)])
+                                   (4096, 11008, 27), (300, 14336, 32), (32000, 4096, 8), (4096, 4096, 3), (640, 11008, 4)])
 def test_q4_0_batch_vs_oracle(n, k, m):
     """ggml Q4_0 x Q8_0: row counts off the 8/16/32 tiles, n off the 128-row tile, K = 11008 (43 slices: uneven K splits)"""
     rng = np.random.default_rng(300 + n + m)
@@ -97,7 +97,7 @@ def test_q4_0_block_sums_exact_and_deterministic():
 
 @pytest.mark.parametrize("asym", [False, True])
 @pytest.mark.parametrize("g,k", [(32, 1024), (128, 4096), (128, 11008), (64, 2048), (256, 4096)])
-@pytest.mark.parametrize("m", [8, 20, 32])
+@pytest.mark.parametrize("m", [4, 8, 20, 32])
 def test_btla_s4_int8_compute_batch(asym, g, k, m):
     """BesTLA int4 blobs, int8 compute: u8 activations with zero points per K-block (kernel_ref.h:1825), weight zero points"""
     n = 320
