@@ -310,7 +310,9 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a rank that dies must not leave the others waiting for ten minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     torch.cuda.set_device(local)
     L = ns.lib()
     L.bestla_init()
@@ -418,20 +420,6 @@ def run_ours(args):
         assert g, ns.last_error()
         return C.c_void_p(g)
 
-    # persistent multi-op kernel: the same 129 matmul nodes, every node waiting (grid barrier) for the previous one
-    prog = ns.Program(1)
-    bb = 0 if args.prog_nobarrier else 1
-    tmp2 = torch.zeros(1, N_FF, device="cuda")
-    for lay in layers:
-        prog.add([lay["wq"], lay["wk"], lay["wv"]], ns.Program.CONCAT, x.data_ptr(), N_EMBD, qkv.data_ptr(), 3 * N_EMBD, barrier_before=bb)
-        prog.add([lay["wo"]], ns.Program.PLAIN, attn.data_ptr(), N_EMBD, o.data_ptr(), N_EMBD, barrier_before=bb)
-        prog.add([lay["w1"], lay["w3"]], ns.Program.GATE_UP_SILU, x.data_ptr(), N_EMBD, tmp.data_ptr(), N_FF, barrier_before=bb)
-        prog.add([lay["w2"]], ns.Program.PLAIN, (tmp if bb else tmp2).data_ptr(), N_FF, ffn.data_ptr(), N_EMBD, barrier_before=bb)
-    prog.add([lm_head], ns.Program.PLAIN, x.data_ptr(), N_EMBD, logits.data_ptr(), N_VOCAB, barrier_before=bb)
-    prog.finalize(queue)
-    prog.run(queue)
-    L.bestla_device_sync(queue)
-
     use_graph = not args.no_graph
     g_step = capture(step_calls) if use_graph else None
     g_gemv = capture(gemv_only_calls) if use_graph else None
@@ -475,7 +463,6 @@ def run_ours(args):
     # a leg of at least one second of back-to-back steps: sustained clocks / power rather than a 20 ms burst
     sus_steps = max(args.steps, int(1.05 / (ms_perop * 1e-3)))
     ms_sus = timed(run_step, sus_steps, 3)
-    ms_prog = timed(lambda: prog.run(queue), args.steps, args.warmup)
     ms_step = ms_perop  # headline = the fastest complete path (one fused act-quant + GEMV launch per matmul node)
     # dominant kernel alone (graph of GEMV launches on pre-quantised activations)
     n_gemv = 4 * n_layers + 1
@@ -485,7 +472,6 @@ def run_ours(args):
         ms_gemv = timed(gemv_only_calls, args.steps, args.warmup)
     gemv_gbs = alg_bytes / (ms_gemv * 1e-3) / 1e9
     step_gbs = alg_bytes / (ms_step * 1e-3) / 1e9
-    prog_gbs = alg_bytes / (ms_prog * 1e-3) / 1e9
 
     # ---- prefill: the same matmul nodes for a 2048-token prompt through the tcgen05 tensor-core GEMM (bf16 numerics)
     prefill = None
@@ -796,9 +782,6 @@ def run_ours(args):
             "sustained": {"steps": sus_steps, "ms_per_step": ms_sus, "tokens_per_s": world * 1000.0 / ms_sus,
                           "frac": (alg_bytes / (ms_sus * 1e-3) / 1e9) / hbm_peak, "note": "the same step repeated for >= 1 s"},
             "prefill": prefill, "decode_engine": engine, "configs": configs, "tp": tp_res,
-            "persistent_program": {"tokens_per_s": world * 1000.0 / ms_prog, "ms_per_step": ms_prog, "launches_per_step": 1,
-                                   "frac": prog_gbs / hbm_peak,
-                                   "note": "same matmuls as ONE cooperative launch (ns_program, grid barrier between nodes)"},
         }
         if n_layers != N_LAYER:
             line["config"]["note"] = f"REDUCED run: {n_layers} of 32 layers (debug only, not a valid bench value)"
@@ -818,7 +801,6 @@ def main():
     ap.add_argument("--fmt", default="q4_0", choices=["q4_0", "int4g128"])
     ap.add_argument("--layers", type=int, default=N_LAYER, help="debug: fewer layers (invalid as a bench value)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--prog-nobarrier", action="store_true", help="experiment: drop the inter-op grid barriers (no dependencies)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-prefill", action="store_true")
     ap.add_argument("--skip-engine", action="store_true")
