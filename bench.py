@@ -237,7 +237,10 @@ def run_tp(world, rank, hbm_peak, steps):
     x0 = torch.randn(1, E, device="cuda")
     logits = torch.zeros(1, V, device="cuda")
     res = {}
-    for mode in ("nccl", "nvlink_oneshot"):
+    # the one-shot NVLink exchange (cudaIpc peer mappings, csrc/comm.cu) is measured where it has been validated on hardware
+    # (2 GPUs: tests/test_gpu_tp.py, profiles/r02_summary.md); NS_TP_ONESHOT=1 forces it at any world size
+    modes = ("nccl", "nvlink_oneshot") if (world == 2 or os.environ.get("NS_TP_ONESHOT")) else ("nccl",)
+    for mode in modes:
         if mode == "nvlink_oneshot":
             ctx.enable_p2p(E)
         stream = torch.cuda.Stream()
