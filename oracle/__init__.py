@@ -35,7 +35,7 @@ def build(force: bool = False) -> None:
     """Compile liboracle.so and (when /root/reference exists) oracle/_ref/."""
     need = force or not os.path.exists(os.path.join(_HERE, "liboracle.so"))
     if os.path.isdir("/root/reference/neural_speed") and not all(
-            os.path.exists(os.path.join(_HERE, "_ref", f)) for f in ("libref_ggml.so", "libref_btla.so", "libref_ne.so")):
+            os.path.exists(os.path.join(_HERE, "_ref", f)) for f in ("libref_ggml.so", "libref_btla.so", "libref_ne.so", "libref_ne_ns.so")):
         need = True
     if need:
         subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
