@@ -303,6 +303,11 @@ NS_API int ns_llama_set_weight(ns_llama* ctx, int tensor, int layer, const ns_we
 NS_API int ns_llama_eval(ns_llama* ctx, const int32_t* tokens, int n_tokens, int n_past, float* logits_host, int32_t* next_token);
 /* greedy generation of n_new tokens starting with first_token at position n_past; out_tokens[i] = pick after step i */
 NS_API int ns_llama_generate(ns_llama* ctx, int32_t first_token, int n_past, int n_new, int32_t* out_tokens);
+/* Numerics of prompt evaluation.  Matmuls of up to 32 new tokens reproduce the reference's exact integer block sums (GEMV /
+ * integer tensor cores); longer prompts run the bf16 tcgen05 GEMM (measured logit deviation <= 4e-2 of max|logit| on the toy
+ * models of tests/test_gpu_llama.py, KV cache entries differ at bf16 precision).  on = 1 evaluates long prompts in pieces of 32
+ * tokens instead: reference numerics for the whole prompt at about 1/6 of the prefill throughput. */
+NS_API int ns_llama_set_exact_prefill(ns_llama* ctx, int on);
 NS_API unsigned long long ns_llama_kv_bytes(const ns_llama* ctx);
 
 /* ---- tensor-parallel exchange step over NVLink peer memory --------------------------------------------

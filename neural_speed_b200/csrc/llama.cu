@@ -448,6 +448,8 @@ struct ns_llama {
   int* am_idx = nullptr;
   unsigned* am_ticket = nullptr;
   int m_cap = 0;
+  size_t attn_attr = 0, fast_attr = 0;  // dynamic shared memory already granted to the attention kernels
+  int exact_prefill = 0;               // ns_llama_set_exact_prefill
   float *x = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *tmp = nullptr, *logits = nullptr;
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -467,6 +469,17 @@ static void* dev_alloc(ns_llama* c, size_t bytes) {
   return p;
 }
 
+// release one allocation of the context early (superseded activation buffers / tensors set twice)
+static void dev_free(ns_llama* c, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < c->owned.size(); ++i)
+    if (c->owned[i] == p) {
+      c->owned.erase(c->owned.begin() + (long)i);
+      cudaFree(p);
+      return;
+    }
+}
+
 extern "C" ns_llama* ns_llama_create(const ns_llama_hparams* hp, void* queue) {
   if (ns_ensure_device()) return nullptr;
   if (!hp || hp->n_vocab <= 0 || hp->n_embd <= 0 || hp->n_head <= 0 || hp->n_head_kv <= 0 || hp->n_layer <= 0 || hp->n_ff <= 0 ||
@@ -482,6 +495,15 @@ extern "C" ns_llama* ns_llama_create(const ns_llama_hparams* hp, void* queue) {
   c->st = ns_stream_of(queue);
   c->layers.resize(hp->n_layer);
   const int hd = hp->n_embd / hp->n_head;
+  {  // the single-pass attention kernels keep one score per cached position in shared memory
+    const size_t need = (size_t)((3 + kAW) * hd + hp->n_ctx) * sizeof(float);
+    if (need > 220 * 1024) {
+      ns_set_error("ns_llama_create: n_ctx %d too large for the single-pass attention kernel (limit %zu positions at head size %d)",
+                   hp->n_ctx, (size_t)(220 * 1024) / sizeof(float) - (size_t)(3 + kAW) * hd, hd);
+      delete c;
+      return nullptr;
+    }
+  }
   const size_t kv_elems = (size_t)hp->n_layer * hp->n_head_kv * hp->n_ctx * hd;
   c->kc = (__half*)dev_alloc(c, kv_elems * 2);
   c->vc = (__half*)dev_alloc(c, kv_elems * 2);
@@ -529,11 +551,21 @@ extern "C" int ns_llama_set_f32(ns_llama* c, int tensor, int layer, const float*
   float* d = (float*)dev_alloc(c, want * 4);
   if (!d) return NS_E_CUDA;
   NS_CUDA_TRY(cudaMemcpyAsync(d, host, want * 4, cudaMemcpyHostToDevice, c->st));
-  NS_CUDA_TRY(cudaStreamSynchronize(c->st));
-  if (tensor == NS_LT_TOK_EMBD) c->tok_embd = d;
-  else if (tensor == NS_LT_OUT_NORM) c->out_norm = d;
-  else if (tensor == NS_LT_ATTN_NORM) c->layers[layer].attn_norm = d;
-  else c->layers[layer].ffn_norm = d;
+  NS_CUDA_TRY(cudaStreamSynchronize(c->st));  // also: nothing in flight reads the tensor this call replaces
+  const float** slot = tensor == NS_LT_TOK_EMBD   ? (const float**)&c->tok_embd
+                       : tensor == NS_LT_OUT_NORM ? (const float**)&c->out_norm
+                       : tensor == NS_LT_ATTN_NORM ? &c->layers[layer].attn_norm
+                                                   : &c->layers[layer].ffn_norm;
+  if (*slot) {  // set twice: the captured decode graph holds the old pointer
+    if (c->decode_exec) {
+      cudaGraphExecDestroy(c->decode_exec);
+      cudaGraphDestroy(c->decode_graph);
+      c->decode_exec = nullptr;
+      c->decode_graph = nullptr;
+    }
+    dev_free(c, (void*)*slot);
+  }
+  *slot = d;
   return NS_OK;
 }
 
@@ -588,6 +620,14 @@ static int ensure_buffers(ns_llama* c, int m) {
   if (m <= c->m_cap) return NS_OK;
   const ns_llama_hparams& hp = c->hp;
   const int hd = hp.n_embd / hp.n_head, kvd = hd * hp.n_head_kv;
+  if (c->m_cap > 0) {  // growing: the smaller buffers are dead once the stream has drained
+    NS_CUDA_TRY(cudaStreamSynchronize(c->st));
+    void* old[6] = {c->x, c->xn, c->qkv, c->attn, c->tmp, c->ws};
+    for (void* p : old) dev_free(c, p);
+    c->x = c->xn = c->qkv = c->attn = c->tmp = nullptr;
+    c->ws = nullptr;
+    c->m_cap = 0;
+  }
   c->x = (float*)dev_alloc(c, (size_t)m * hp.n_embd * 4);
   c->xn = (float*)dev_alloc(c, (size_t)m * hp.n_embd * 4);
   c->qkv = (float*)dev_alloc(c, (size_t)m * (hp.n_embd + 2 * kvd) * 4);
@@ -645,7 +685,7 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
                             (const int*)(from_state ? c->state : c->tokens), E, hp.n_vocab, c->x));
   ns_count_launch();
   const size_t attn_smem = (size_t)(hd + hp.n_ctx) * sizeof(float);
-  static size_t attn_attr = 0;
+  size_t& attn_attr = c->attn_attr;  // per context: the function attribute is per device
   if (attn_smem > 48 * 1024 && attn_smem > attn_attr) {
     if (attn_smem > 220 * 1024) {
       ns_set_error("ns_llama: n_ctx %d too large for the single-pass attention kernel", hp.n_ctx);
@@ -656,7 +696,7 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
   }
   const size_t fast_smem = (size_t)((3 + kAW) * hd + hp.n_ctx) * sizeof(float);
   if (fast_smem > 48 * 1024) {
-    static size_t fast_attr = 0;
+    size_t& fast_attr = c->fast_attr;
     if (fast_smem > 220 * 1024) {
       ns_set_error("ns_llama: n_ctx %d too large for the single-pass attention kernel", hp.n_ctx);
       return NS_E_UNSUPPORTED;
@@ -747,11 +787,27 @@ static int ensure_decode_graph(ns_llama* c) {
 
 // model_eval (models/model_utils/model_utils.h): evaluate n_tokens new tokens after n_past cached ones.
 // logits_host (nullable): n_vocab floats of the LAST token; next_token (nullable): its greedy pick.
+extern "C" int ns_llama_set_exact_prefill(ns_llama* c, int on) {
+  if (!c) return NS_E_INVALID;
+  c->exact_prefill = on ? 1 : 0;
+  return NS_OK;
+}
+
 extern "C" int ns_llama_eval(ns_llama* c, const int32_t* tokens, int n_tokens, int n_past, float* logits_host, int32_t* next_token) {
   if (int rc = ns_ensure_device()) return rc;
   if (!c || !tokens || n_tokens <= 0 || n_past < 0 || n_past + n_tokens > c->hp.n_ctx) {
     ns_set_error("ns_llama_eval: invalid arguments (n_tokens=%d n_past=%d n_ctx=%d)", n_tokens, n_past, c ? c->hp.n_ctx : 0);
     return NS_E_INVALID;
+  }
+  if (c->exact_prefill && n_tokens > 32) {
+    // parity mode: prompts go through in pieces of <= 32 tokens, which the matmuls run on the integer tensor cores with the
+    // reference's exact block sums (causal attention over the fp16 KV cache makes the split invisible to the arithmetic)
+    for (int t0 = 0; t0 < n_tokens; t0 += 32) {
+      const int nt = n_tokens - t0 < 32 ? n_tokens - t0 : 32;
+      const bool last = t0 + nt == n_tokens;
+      if (int rc = ns_llama_eval(c, tokens + t0, nt, n_past + t0, last ? logits_host : nullptr, last ? next_token : nullptr)) return rc;
+    }
+    return NS_OK;
   }
   if (int rc = check_complete(c)) return rc;
   if (int rc = ensure_buffers(c, n_tokens)) return rc;

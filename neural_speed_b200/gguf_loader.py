@@ -63,7 +63,7 @@ def parse(path: str) -> GGUFLlama:
     hp = dict(n_embd=int(_field(r, "llama.embedding_length")), n_layer=int(_field(r, "llama.block_count")),
               n_ff=int(_field(r, "llama.feed_forward_length")), n_head=int(_field(r, "llama.attention.head_count")),
               n_ctx=int(_field(r, "llama.context_length", 2048)),
-              norm_eps=float(_field(r, "llama.attention.layer_norm_rms_epsilon", 1e-5)),
+              norm_eps=float(_field(r, "llama.attention.layer_norm_rms_epsilon", 1e-6)),  # reference default (model_types.h)
               rope_theta=float(_field(r, "llama.rope.freq_base", 10000.0)), rope_scale=1.0)
     hp["n_head_kv"] = int(_field(r, "llama.attention.head_count_kv", hp["n_head"]))
     tensors = {t.name: t for t in r.tensors}
@@ -111,6 +111,10 @@ def load_into_engine(model: GGUFLlama, n_ctx: int | None = None, queue=None):
     hp = dict(model.hparams)
     if n_ctx:
         hp["n_ctx"] = n_ctx
+    elif hp["n_ctx"] > 32768:
+        # files advertise their training length (131072 ...): the KV cache is allocated for n_ctx up front and the attention
+        # kernel keeps one score per position in shared memory (~54k positions at head size 128); ask explicitly for more
+        hp["n_ctx"] = 32768
     eng = Llama(hp["n_vocab"], hp["n_embd"], hp["n_head"], hp["n_head_kv"], hp["n_layer"], hp["n_ff"], hp["n_ctx"],
                 hp["norm_eps"], hp["rope_theta"], hp["rope_scale"], queue)
 

@@ -118,7 +118,7 @@ def parse(path: str) -> GGUFLlama:
         if typ in (NE_F32, NE_F16):
             return data
         if typ == NE_Q4_0:
-            return dequantize_q4_0(data, shape[1])
+            return dequantize_q4_0(data, shape[-1])   # 1-D tensors: the row length is the only dimension
         raise ValueError(f"{name}: type {typ} cannot be used as an fp32 tensor")
 
     def weight(name, n, k):

@@ -99,6 +99,18 @@ def test_long_prompt_goes_through_the_tensor_core_gemm(n_head):
     eng.close()
 
 
+def test_exact_prefill_mode_keeps_reference_numerics_for_long_prompts():
+    """a 70-token prompt: default = bf16 tensor-core GEMM (looser bar); exact mode = pieces of 32 on the integer tensor cores,
+    held to the north-star 1e-2, and the KV cache it leaves serves the following single-token steps"""
+    hp, orc, eng = _build(seed=12, n_ctx=96)
+    prompt = [int(t) for t in np.random.default_rng(3).integers(3, hp["n_vocab"], 70)]
+    want = orc.eval(prompt, 0)
+    eng.set_exact_prefill(True)
+    _check_logits(eng.eval(prompt, 0)[0], want)
+    _check_logits(eng.eval([9], 70)[0], orc.eval([9], 70))
+    eng.close()
+
+
 def test_generate_feeds_the_argmax_on_device():
     hp, orc, eng = _build(seed=7)
     first, n_new = 11, 10
