@@ -246,7 +246,9 @@ __device__ __forceinline__ float lds_scale_b(uint32_t a) {  // a: byte address o
   return __uint_as_float((uint32_t)h << 16);
 }
 
-template <bool ACT_U8, int MT, bool ASYM, int STYPE, bool P1>  // P1: activation blocks of one chunk (32): flush every chunk
+// PER: 32-chunks per activation block, compile-time for the common cases (1: ggml Q8_0 / group 32, 4: group 128) so that the
+// eight chunks of a stage are one straight-line schedule; 0: read from the parameters (groups 64 / 256)
+template <bool ACT_U8, int MT, bool ASYM, int STYPE, int PER>
 __global__ void __launch_bounds__(kThr, 2)
     gemm_imma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                      const __grid_constant__ CUtensorMap map2, const ImmaParams P) {
@@ -376,7 +378,6 @@ __global__ void __launch_bounds__(kThr, 2)
   const int rA = warp * 16 + g, rB = rA + 8;  // rows of this thread inside the tile
   const uint32_t scA = sc_s + (uint32_t)rA * P.sc_row + dsc, scB = sc_s + (uint32_t)rB * P.sc_row + dsc;
   const uint32_t zpo = (uint32_t)(scb + dzp - dsc);
-  const int nchunks = (P.k + 31) >> 5;
   // ldmatrix row address of this lane: matrices 0/1 = rows +0..7 / +8..15 of chunk j, matrices 2/3 = the same rows of chunk j+1
   const int lrow = warp * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
   const int lsel = lane >> 4;  // 0: chunk j, 1: chunk j + 1
@@ -397,8 +398,10 @@ __global__ void __launch_bounds__(kThr, 2)
 
   int s = 0;
   uint32_t phase = 0;
-  const int period = P.acpg;
+  constexpr bool P1 = PER == 1;
+  const int period = PER ? PER : P.acpg;
   for (int i = 0; i < nsl; ++i) {
+    const int gstage = (((sl0 + i) * 8) >> P.cpg_shift) - g0;  // first weight group of the stage (a stage holds whole groups)
     mbar_wait(full0 + 8 * s, phase);
     const uint32_t qs = base + (uint32_t)s * kStage;
     const uint32_t as = qs + kQStage;
@@ -422,10 +425,9 @@ __global__ void __launch_bounds__(kThr, 2)
           if (P1) imma0<true>(cs, a, 0x01010101u, 0x01010101u);
           else imma<true>(cs, a, 0x01010101u, 0x01010101u);
         }
-        const int ch = (sl0 + i) * 8 + j;                         // global chunk
-        if ((P1 || ((ch + 1) & (period - 1)) == 0) && ch < nchunks) {
+        if (PER ? ((j + 1) % (PER ? PER : 1) == 0) : (((j + 1) & (period - 1)) == 0)) {
           // end of an activation block: exact integer block sums -> fp32
-          const int gi = (ch >> P.cpg_shift) - g0;
+          const int gi = gstage + (PER == 1 ? j : (PER ? j / (PER ? PER : 1) : (j >> P.cpg_shift)));
           const float wsA = lds_scale_b<STYPE>(scA + SS * gi), wsB = lds_scale_b<STYPE>(scB + SS * gi);
           int offA = 8, offB = 8;
           if (ASYM) {
@@ -621,9 +623,9 @@ bool make_plan(const ns_weight* const* ws, int nw, int mode, int m, Plan* pl) {
   return true;
 }
 
-template <bool ACT_U8, int MT, bool ASYM, int STYPE, bool P1>
+template <bool ACT_U8, int MT, bool ASYM, int STYPE, int PER>
 int launch_p(const CUtensorMap* maps, const ImmaParams& P, const Plan& pl, cudaStream_t st) {
-  auto kern = gemm_imma_kernel<ACT_U8, MT, ASYM, STYPE, P1>;
+  auto kern = gemm_imma_kernel<ACT_U8, MT, ASYM, STYPE, PER>;
   static bool attr = false;
   if (!attr) {
     NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -635,7 +637,9 @@ int launch_p(const CUtensorMap* maps, const ImmaParams& P, const Plan& pl, cudaS
 }
 template <bool ACT_U8, int MT, bool ASYM, int STYPE>
 int launch_k(const CUtensorMap* maps, const ImmaParams& P, const Plan& pl, cudaStream_t st) {
-  return P.acpg == 1 ? launch_p<ACT_U8, MT, ASYM, STYPE, true>(maps, P, pl, st) : launch_p<ACT_U8, MT, ASYM, STYPE, false>(maps, P, pl, st);
+  if (P.acpg == 1 && P.cpg == 1) return launch_p<ACT_U8, MT, ASYM, STYPE, 1>(maps, P, pl, st);
+  if (P.acpg == 4 && P.cpg == 4) return launch_p<ACT_U8, MT, ASYM, STYPE, 4>(maps, P, pl, st);
+  return launch_p<ACT_U8, MT, ASYM, STYPE, 0>(maps, P, pl, st);
 }
 template <bool ACT_U8, int MT, bool ASYM>
 int launch_s(const CUtensorMap* maps, const ImmaParams& P, const Plan& pl, int stype, cudaStream_t st) {
@@ -669,6 +673,7 @@ bool ns_gemm_imma_supported(const ns_weight* const* ws, int nw, int m) {
   }
   if (!(w0->comp == NS_COMP_Q8_0 || w0->comp == NS_COMP_INT8 || w0->comp == NS_COMP_INT8_S8)) return false;
   if (!(w0->group == 32 || w0->group == 64 || w0->group == 128 || w0->group == 256) || w0->k % w0->group) return false;
+  if (w0->k % KS) return false;  // whole 256-k stages only (every model width is): no per-chunk tail checks in the loop
   if (w0->pitch % 16) return false;
   return true;
 }

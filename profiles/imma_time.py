@@ -30,11 +30,14 @@ only = sys.argv[1:] or list(modes)
 NW = 16
 for mode in only:
     kw = modes[mode]
-    for (n, k) in [(4096, 4096), (12288, 4096), (4096, 11008), (22016, 4096), (32000, 4096)]:
+    shapes = [(4096, 4096), (12288, 4096), (4096, 11008), (22016, 4096), (32000, 4096)]
+    if os.environ.get("IMMA_SHAPES"):
+        shapes = [tuple(int(v) for v in t.split("x")) for t in os.environ["IMMA_SHAPES"].split(",")]
+    for (n, k) in shapes:
         ws = [ns.Weight.random(n, k, seed=3 + i, queue=queue, **kw) for i in range(NW)]
         L.bestla_device_sync(queue)
         bytes_node = ws[0].algorithmic_bytes
-        for M in (1, 4, 8, 16, 32):
+        for M in [int(v) for v in os.environ.get("IMMA_MS", "1,4,8,16,32").split(",")]:
             x = torch.randn(M, k, device="cuda"); y = torch.zeros(M, n, device="cuda")
             wsb = torch.zeros(L.ns_device_workspace_bytes(M, k), dtype=torch.uint8, device="cuda")
             def calls():
