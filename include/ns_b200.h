@@ -202,6 +202,23 @@ NS_API int ns_ffn_gelu(const ns_weight* w1, const ns_weight* w2, const ns_weight
 NS_API int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda, float* tmp,
                        float* dst, int ldo, int m, void* workspace, void* queue);
 
+/* The RMSNorm in front of a matmul node folded into the node's launch: ne_rms_norm + ne_mul(norm weight) + ne_mul_mat /
+ * ne_mul_qkv / ne_ffn_silu (models/llama/llama.cpp:205-215, :601-612, :703-712) as ONE kernel -- every CTA of the decode GEMV
+ * reads the whole activation row for the fused NE_TASK_INIT quantiser anyway, so the sum of squares costs a block reduction
+ * instead of a one-CTA kernel and a launch boundary.  Decode rows only (m <= 2, int4 weights with an integer compute type):
+ * ns_rmsnorm_fusable says whether a set of 1..3 weights qualifies; the calls return NS_E_UNSUPPORTED otherwise.
+ *   ns_rmsnorm_mul_mat   dst = W (rms_norm(act) * norm_w) [+ residual]
+ *   ns_rmsnorm_mul_qkv   dst[3][m][ldo] as ns_mul_qkv
+ *   ns_rmsnorm_ffn_silu  dst = W2 (silu(W1 xn) * (W3 xn)) [+ residual],  xn = rms_norm(act) * norm_w */
+NS_API int ns_rmsnorm_fusable(const ns_weight* const* weights, int nw, int m);
+NS_API int ns_rmsnorm_mul_mat(const ns_weight* w, const float* act, int lda, const float* norm_w, float norm_eps, float* dst, int ldo,
+                              int m, const float* residual, void* workspace, void* queue);
+NS_API int ns_rmsnorm_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_weight* wv, const float* act, int lda,
+                              const float* norm_w, float norm_eps, float* dst, int ldo, int m, void* workspace, void* queue);
+NS_API int ns_rmsnorm_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda,
+                               const float* norm_w, float norm_eps, float* tmp, float* dst, int ldo, int m, const float* residual,
+                               void* workspace, void* queue);
+
 /* The two phases of a reference matmul node, separately (ne_compute_forward_mul_mat_q_f32: NE_TASK_INIT quantises src1
  * into wdata, NE_TASK_COMPUTE runs the dots; core/ne_layers.c:7143-7203):
  *   ns_prepare_activation  act[m][k] (device fp32) -> activation image in `workspace` (m <= 4 rows per image)

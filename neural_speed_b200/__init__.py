@@ -51,7 +51,8 @@ EXPORTS = [
     "bestla_device_f32f32_forward",
     "ns_weight_from_q4_0", "ns_weight_from_q6_K", "ns_weight_from_btla_blob", "ns_weight_from_btla_blob_n", "ns_weight_random", "ns_weight_from_unpacked", "ns_weight_free", "ns_weight_info",
     "ns_weight_set_comp", "ns_weight_algorithmic_bytes", "ns_weight_dequant_f32",
-    "ns_mul_mat", "ns_mul_qkv", "ns_ffn_silu", "ns_ffn_gelu", "ns_mul_mat_q4_0_f32_host", "ns_mul_mat_q6_K_f32_host",
+    "ns_mul_mat", "ns_mul_qkv", "ns_ffn_silu", "ns_ffn_gelu",
+    "ns_rmsnorm_fusable", "ns_rmsnorm_mul_mat", "ns_rmsnorm_mul_qkv", "ns_rmsnorm_ffn_silu", "ns_mul_mat_q4_0_f32_host", "ns_mul_mat_q6_K_f32_host",
     "ns_program_create", "ns_program_add_matmul", "ns_program_add_matmul_ex", "ns_program_tag_last", "ns_program_finalize", "ns_program_run",
     "ns_program_run_n", "ns_program_algorithmic_bytes", "ns_program_free", "ns_program_timeline", "ns_program_unit_trace",
     "ns_prepare_activation", "ns_matmul_prepared", "ns_graph_begin", "ns_graph_end", "ns_graph_launch", "ns_graph_free",
@@ -138,6 +139,10 @@ def lib() -> C.CDLL:
     L.ns_mul_qkv.argtypes = [vp, vp, vp, vp, i, vp, i, i, vp, vp]
     L.ns_ffn_silu.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp, vp]
     L.ns_ffn_gelu.argtypes = [vp, vp, vp, vp, vp, i, vp, i, vp, vp, i, i, vp, vp]
+    L.ns_rmsnorm_fusable.argtypes = [vp, i, i]
+    L.ns_rmsnorm_mul_mat.argtypes = [vp, vp, i, vp, C.c_float, vp, i, i, vp, vp, vp]
+    L.ns_rmsnorm_mul_qkv.argtypes = [vp, vp, vp, vp, i, vp, C.c_float, vp, i, i, vp, vp]
+    L.ns_rmsnorm_ffn_silu.argtypes = [vp, vp, vp, vp, i, vp, C.c_float, vp, vp, i, i, vp, vp, vp]
     L.bestla_fusion_FFN_Gelu_Mul_f32f32_support.restype = C.c_bool
     L.bestla_fusion_FFN_Gelu_Mul_f32f32_support.argtypes = [vp, vp, vp, i, i, i, i]
     L.bestla_fusion_FFN_Gelu_Mul_f32f32_forward.restype = None
@@ -384,6 +389,31 @@ def ffn_silu(w1: Weight, w2: Weight, w3: Weight, act_ptr: int, lda: int, tmp_ptr
              queue=None):
     _check(lib().ns_ffn_silu(w1.h, w2.h, w3.h, C.c_void_p(act_ptr), lda, C.c_void_p(tmp_ptr), C.c_void_p(dst_ptr), ldo, m,
                              None, queue), "ns_ffn_silu")
+
+
+def rmsnorm_fusable(weights, m: int) -> bool:
+    """Can RMSNorm(x) * norm_w be folded into the launch of these 1..3 weights for m activation rows?"""
+    arr = (C.c_void_p * len(weights))(*[w.h for w in weights])
+    return bool(lib().ns_rmsnorm_fusable(arr, len(weights), m))
+
+
+def rmsnorm_mul_mat(w: Weight, act_ptr: int, lda: int, norm_ptr: int, eps: float, dst_ptr: int, ldo: int, m: int, residual_ptr=None,
+                    queue=None):
+    _check(lib().ns_rmsnorm_mul_mat(w.h, C.c_void_p(act_ptr), lda, C.c_void_p(norm_ptr), eps, C.c_void_p(dst_ptr), ldo, m,
+                                    C.c_void_p(residual_ptr) if residual_ptr else None, None, queue), "ns_rmsnorm_mul_mat")
+
+
+def rmsnorm_mul_qkv(wq: Weight, wk: Weight, wv: Weight, act_ptr: int, lda: int, norm_ptr: int, eps: float, dst_ptr: int, ldo: int,
+                    m: int, queue=None):
+    _check(lib().ns_rmsnorm_mul_qkv(wq.h, wk.h, wv.h, C.c_void_p(act_ptr), lda, C.c_void_p(norm_ptr), eps, C.c_void_p(dst_ptr), ldo,
+                                    m, None, queue), "ns_rmsnorm_mul_qkv")
+
+
+def rmsnorm_ffn_silu(w1: Weight, w2: Weight, w3: Weight, act_ptr: int, lda: int, norm_ptr: int, eps: float, tmp_ptr: int, dst_ptr: int,
+                     ldo: int, m: int, residual_ptr=None, queue=None):
+    _check(lib().ns_rmsnorm_ffn_silu(w1.h, w2.h, w3.h, C.c_void_p(act_ptr), lda, C.c_void_p(norm_ptr), eps, C.c_void_p(tmp_ptr),
+                                     C.c_void_p(dst_ptr), ldo, m, C.c_void_p(residual_ptr) if residual_ptr else None, None, queue),
+           "ns_rmsnorm_ffn_silu")
 
 
 def ffn_gelu(w1: Weight, w2: Weight, w3, b1_ptr, b2_ptr, bias_bcast: int, act_ptr: int, lda: int, tmp_ptr: int, dst_ptr: int,

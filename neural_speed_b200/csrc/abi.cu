@@ -586,8 +586,13 @@ static size_t ws_need(const ns_weight* w, int m, bool tc) {
   return tc ? ns_gemm_tc_workspace_bytes(m, w->kpad) : ns_act_workspace_bytes(4, w->kpad);
 }
 
-extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* bias,
-                          const float* residual, int flags, void* workspace, void* queue) {
+static int norm_unsupported(const char* who) {
+  ns_set_error("%s: the RMSNorm can only be folded into the ring GEMV (int4 weights, integer compute type, <= 2 rows)", who);
+  return NS_E_UNSUPPORTED;
+}
+
+static int mul_mat_impl(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* bias,
+                        const float* residual, int flags, void* workspace, void* queue, const float* norm_w, float norm_eps) {
   if (int rc = ns_ensure_device()) return rc;
   if (!w || !act || !dst || m <= 0 || lda < w->k || ldo < w->n) {
     ns_set_error("ns_mul_mat: invalid arguments (m=%d lda=%d ldo=%d)", m, lda, ldo);
@@ -595,6 +600,7 @@ extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* 
   }
   cudaStream_t st = stream_of(queue);
   const int bcast = (flags & NS_MM_BIAS_BCAST) ? 1 : 0;
+  if (norm_w && ((flags & NS_MM_FORCE_TC) || !ns_gemv_fused_norm_ok(&w, 1, m))) return norm_unsupported("ns_rmsnorm_mul_mat");
   if (w->wfmt == NS_W_Q6K) {  // ggml Q6_K x Q8_K, tiles of <= 4 activation rows
     void* ws6 = pick_ws(workspace, st, ns_q6k_workspace_bytes(4, w->k));
     if (!ws6) return NS_E_CUDA;
@@ -629,18 +635,30 @@ extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* 
       if (int rc = ns_launch_act_prep(a, lda, mt, w, ws, st)) return rc;
     if (int rc = ns_launch_gemv(&w, 1, NS_GEMV_PLAIN, fused ? nullptr : ws, dst + (size_t)m0 * ldo, ldo, mt, m,
                                 bias ? (bcast ? bias : bias + (size_t)m0 * ldo) : nullptr, bcast,
-                                residual ? residual + (size_t)m0 * ldo : nullptr, nullptr, st, fused ? a : nullptr, lda))
+                                residual ? residual + (size_t)m0 * ldo : nullptr, nullptr, st, fused ? a : nullptr, lda,
+                                NS_ELT_DEFAULT, norm_w, norm_eps))
       return rc;
   }
   return NS_OK;
 }
+extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* bias,
+                          const float* residual, int flags, void* workspace, void* queue) {
+  return mul_mat_impl(w, act, lda, dst, ldo, m, bias, residual, flags, workspace, queue, nullptr, 0.f);
+}
+// dst = W * (rms_norm(act) * norm_w) [+ residual]: ne_rms_norm + ne_mul + ne_mul_mat (llama.cpp:205-215, :703-712) as ONE launch
+extern "C" int ns_rmsnorm_mul_mat(const ns_weight* w, const float* act, int lda, const float* norm_w, float norm_eps, float* dst,
+                                  int ldo, int m, const float* residual, void* workspace, void* queue) {
+  if (!norm_w) return NS_E_INVALID;
+  return mul_mat_impl(w, act, lda, dst, ldo, m, nullptr, residual, 0, workspace, queue, norm_w, norm_eps);
+}
 
-extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_weight* wv, const float* act, int lda,
-                          float* dst, int ldo, int m, void* workspace, void* queue) {
+int ns_mul_qkv_norm(const ns_weight* wq, const ns_weight* wk, const ns_weight* wv, const float* act, int lda, float* dst, int ldo,
+                    int m, void* workspace, void* queue, const float* norm_w, float norm_eps) {
   if (int rc = ns_ensure_device()) return rc;
   if (!wq || !wk || !wv || !act || !dst || m <= 0) return NS_E_INVALID;
   cudaStream_t st = stream_of(queue);
   const ns_weight* wl[3] = {wq, wk, wv};
+  if (norm_w && !ns_gemv_fused_norm_ok(wl, 3, m)) return norm_unsupported("ns_rmsnorm_mul_qkv");
   if (use_imma(wl, 3, m, 0) && !(wq->n % 2) && !(wk->n % 2)) {
     void* wsi = pick_ws(workspace, st, ns_gemm_imma_workspace_bound(m, wq->kpad));
     if (!wsi) return NS_E_CUDA;
@@ -664,10 +682,19 @@ extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_wei
     if (!fused)
       if (int rc = ns_launch_act_prep(a, lda, mt, wq, ws, st)) return rc;
     if (int rc = ns_launch_gemv(wl, 3, NS_GEMV_CONCAT, fused ? nullptr : ws, dst + (size_t)m0 * ldo, ldo, mt, m, nullptr, 0,
-                                nullptr, nullptr, st, fused ? a : nullptr, lda))
+                                nullptr, nullptr, st, fused ? a : nullptr, lda, NS_ELT_DEFAULT, norm_w, norm_eps))
       return rc;
   }
   return NS_OK;
+}
+extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_weight* wv, const float* act, int lda,
+                          float* dst, int ldo, int m, void* workspace, void* queue) {
+  return ns_mul_qkv_norm(wq, wk, wv, act, lda, dst, ldo, m, workspace, queue, nullptr, 0.f);
+}
+extern "C" int ns_rmsnorm_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_weight* wv, const float* act, int lda,
+                                  const float* norm_w, float norm_eps, float* dst, int ldo, int m, void* workspace, void* queue) {
+  if (!norm_w) return NS_E_INVALID;
+  return ns_mul_qkv_norm(wq, wk, wv, act, lda, dst, ldo, m, workspace, queue, norm_w, norm_eps);
 }
 
 // Fused feed-forward.  w3 != NULL: tmp = elt(x W1^T) * (x W3^T), dst = tmp W2^T (SiLu / Gelu_Mul, ip_fusion_ffn.cpp:734-753).
@@ -675,7 +702,7 @@ extern "C" int ns_mul_qkv(const ns_weight* wq, const ns_weight* wk, const ns_wei
 // tmp: [2][m][fmid] floats when m > 4 and w3 is given (gate and up GEMM outputs; the product lands in the first half), else [m][fmid]
 static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, int eltop, const float* b1, const float* b2,
                     int bcast, const float* act, int lda, float* tmp, float* dst, int ldo, int m, void* workspace, void* queue,
-                    const float* residual = nullptr) {
+                    const float* residual = nullptr, const float* norm_w = nullptr, float norm_eps = 0.f) {
   if (int rc = ns_ensure_device()) return rc;
   if (!w1 || !w2 || !act || !tmp || !dst || m <= 0 || w2->k != w1->n || (w3 && (w3->n != w1->n || w3->k != w1->k)) ||
       (w3 && (b1 || b2)) || (!w3 && eltop != NS_ELT_GELU)) {
@@ -689,6 +716,7 @@ static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w
   const int kmax = w1->kpad > w2->kpad ? w1->kpad : w2->kpad;
   {
     const ns_weight* gu2[2] = {w1, w3};
+    if (norm_w && !ns_gemv_fused_norm_ok(gu2, w3 ? 2 : 1, m)) return norm_unsupported("fused FFN");
     if (use_imma(gu2, w3 ? 2 : 1, m, 0) && use_imma(&w2, 1, m, 0)) {
       void* wsi = pick_ws(workspace, st, ns_gemm_imma_workspace_bound(m, kmax));
       if (!wsi) return NS_E_CUDA;
@@ -726,12 +754,12 @@ static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w
       if (int rc = ns_launch_act_prep(a, lda, mt, w1, ws, st)) return rc;
     if (w3) {
       if (int rc = ns_launch_gemv(gu, 2, NS_GEMV_GATE_UP_SILU, fused1 ? nullptr : ws, tmp + (size_t)m0 * fmid, fmid, mt, m, nullptr,
-                                  0, nullptr, nullptr, st, fused1 ? a : nullptr, lda, eltop))
+                                  0, nullptr, nullptr, st, fused1 ? a : nullptr, lda, eltop, norm_w, norm_eps))
         return rc;
     } else {
       if (int rc = ns_launch_gemv(gu, 1, NS_GEMV_PLAIN, fused1 ? nullptr : ws, tmp + (size_t)m0 * fmid, fmid, mt, m,
                                   b1 ? (bcast ? b1 : b1 + (size_t)m0 * fmid) : nullptr, bcast, nullptr, nullptr, st,
-                                  fused1 ? a : nullptr, lda, NS_ELT_GELU))
+                                  fused1 ? a : nullptr, lda, NS_ELT_GELU, norm_w, norm_eps))
         return rc;
     }
   }
@@ -750,9 +778,22 @@ static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w
 }
 // dst = residual + FFN_SiLU(act): the decode engine's "cur = ne_add(ffn, inpFF)" (llama.cpp:698) folded into the down GEMV
 int ns_ffn_silu_residual(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda, float* tmp,
-                         float* dst, int ldo, int m, const float* residual, void* workspace, cudaStream_t st) {
+                         float* dst, int ldo, int m, const float* residual, void* workspace, cudaStream_t st, const float* norm_w,
+                         float norm_eps) {
   if (!w3) return NS_E_INVALID;
-  return ffn_impl(w1, w2, w3, NS_ELT_DEFAULT, nullptr, nullptr, 0, act, lda, tmp, dst, ldo, m, workspace, (void*)st, residual);
+  return ffn_impl(w1, w2, w3, NS_ELT_DEFAULT, nullptr, nullptr, 0, act, lda, tmp, dst, ldo, m, workspace, (void*)st, residual, norm_w,
+                  norm_eps);
+}
+// dst = residual + FFN_SiLU(rms_norm(act) * norm_w): llama.cpp:601-698 with the norm folded into the gate/up launch
+extern "C" int ns_rmsnorm_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda,
+                                   const float* norm_w, float norm_eps, float* tmp, float* dst, int ldo, int m, const float* residual,
+                                   void* workspace, void* queue) {
+  if (!w3 || !norm_w) return NS_E_INVALID;
+  return ffn_impl(w1, w2, w3, NS_ELT_DEFAULT, nullptr, nullptr, 0, act, lda, tmp, dst, ldo, m, workspace, queue, residual, norm_w,
+                  norm_eps);
+}
+extern "C" int ns_rmsnorm_fusable(const ns_weight* const* weights, int nw, int m) {
+  return (weights && nw >= 1 && nw <= 3 && ns_gemv_fused_norm_ok(weights, nw, m)) ? 1 : 0;
 }
 extern "C" int ns_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda,
                            float* tmp, float* dst, int ldo, int m, void* workspace, void* queue) {

@@ -368,9 +368,17 @@ bool ns_gemv_fused_quant_ok(const ns_weight* w) {
   return (qg == 32 || qg == 64 || qg == 128 || qg == 256) && w->k % qg == 0;
 }
 
+bool ns_gemv_fused_norm_ok(const ns_weight* const* ws, int nw, int m) {
+  static const bool off = getenv("NS_NO_FUSED_NORM") != nullptr;  // debugging aid: separate rmsnorm launches
+  if (off || m < 1 || m > 2 || nw < 1) return false;
+  for (int i = 0; i < nw; ++i)
+    if (!ws[i] || !ns_gemv_fused_quant_ok(ws[i]) || ws[i]->k % 8) return false;
+  return !ns_gemm_imma_supported(ws, nw, m);  // (NS_IMMA_MIN_M may hand 2 rows to the integer tensor cores)
+}
+
 int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* act_ws, float* dst, int ldo, int m,
                    int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st,
-                   const float* act_f32, int lda, int eltop) {
+                   const float* act_f32, int lda, int eltop, const float* norm_w, float norm_eps) {
   const ns_weight* w0 = ws_[0];
   for (int i = 1; i < nw; ++i) {
     const ns_weight* wi = ws_[i];
@@ -443,6 +451,12 @@ int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* ac
   P.lda = lda;
   P.eltop = eltop;
   P.comp = w0->comp;
+  P.norm_w = norm_w;
+  P.norm_eps = norm_eps;
+  if (norm_w && !(act_f32 && ns_gemv_fused_quant_ok(w0))) {
+    ns_set_error("internal: fused RMSNorm needs the fused activation quantiser");
+    return NS_E_INVALID;
+  }
   if (act_f32 && !(ns_gemv_fused_quant_ok(w0))) {
     ns_set_error("internal: fused activation quantisation not available for this weight");
     return NS_E_INVALID;

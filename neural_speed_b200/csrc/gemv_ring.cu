@@ -17,6 +17,7 @@
 // Roofline: HBM.  Algorithmic bytes per launch = sum over weights of N*K/2 + N*ceil(K/g)*(scale_bytes [+1 if asym]).
 #include "nsb.cuh"
 #include "quant_smem.cuh"
+#include "norm_quant.cuh"
 
 namespace {
 
@@ -125,6 +126,7 @@ struct RingCfg {
   int units;        // row pairs (ROWS == 2) or rows (ROWS == 1) of this launch
   int active;       // consumer warps that own ring stages (<= kConsumers; `stages` is a multiple of it)
   int act_row;      // bytes per activation row in the staged image
+  int red_off;      // byte offset of the RMSNorm reduction scratch (8 floats) inside the activation region, fused-norm launches only
   uint32_t cpg_magic;  // ceil(2^32 / cpg): gi = umulhi(c, magic)
 };
 
@@ -194,7 +196,16 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
 
   // ===================== consumers =====================
   pdl_wait();  // activations (and residual) come from earlier kernels
-  if (P.act_f32) {
+  if (P.act_f32 && P.norm_w) {
+    // fused ne_rms_norm + ne_mul + NE_TASK_INIT: every CTA already reads the whole fp32 row, the sum of squares costs one more
+    // block reduction instead of a kernel boundary (llama.cpp:205-210; arithmetic of rmsnorm_kernel, llama.cu)
+    const nsq::NormQuantIn ni{P.act_f32, 0u, P.norm_w, P.norm_eps, P.lda, P.k, P.kpad, P.comp == NS_COMP_Q8_0 ? 32 : P.group,
+                              R.act_row, P.meta_off, P.meta_stride};
+    float* red = reinterpret_cast<float*>(smem + R.red_off);
+    if (AMODE == A_U8) nsq::norm_quantise_to_smem<NS_COMP_INT8, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x);
+    else if (P.comp == NS_COMP_Q8_0) nsq::norm_quantise_to_smem<NS_COMP_Q8_0, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x);
+    else nsq::norm_quantise_to_smem<NS_COMP_INT8_S8, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x);
+  } else if (P.act_f32) {
     // fused NE_TASK_INIT: quantise the fp32 rows straight into the shared-memory image (no separate kernel, no round trip)
     const QuantIn qi{P.act_f32, P.lda, P.k, P.kpad, P.comp == NS_COMP_Q8_0 ? 32 : P.group, R.act_row, P.meta_off, P.meta_stride};
     if (P.comp == NS_COMP_Q8_0) nsq::quantise_to_smem<NS_COMP_Q8_0, kConsumers * 32>(qi, P.m, smem_base);
@@ -380,7 +391,7 @@ static RingPlan plan_ring(const GemvParams& P, size_t act_region) {
 }
 
 template <int AMODE, int M, bool ASYM, int STYPE, int ROWS>
-int launch_rows(const GemvParams& P, const RingPlan& plan, size_t act_region, int act_row, cudaStream_t st) {
+int launch_rows(const GemvParams& P, const RingPlan& plan, size_t act_region, int act_row, int red_off, cudaStream_t st) {
   auto kern = gemv_ring_kernel<AMODE, M, ASYM, STYPE, ROWS>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -396,6 +407,7 @@ int launch_rows(const GemvParams& P, const RingPlan& plan, size_t act_region, in
   R.stages = plan.stages;
   R.active = plan.active;
   R.act_row = act_row;
+  R.red_off = red_off;
   if (ROWS == 2) {
     R.units = P.npairs;
   } else {
@@ -419,14 +431,16 @@ int launch_rows(const GemvParams& P, const RingPlan& plan, size_t act_region, in
 template <int AMODE, int M, bool ASYM, int STYPE>
 int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
   const int act_row = (int)ns_round_up((size_t)P.kpad, 1024);
-  const size_t act_region = ns_round_up((size_t)mt * act_row + (size_t)mt * P.meta_stride * 8, 128);
+  const size_t img_end = (size_t)mt * act_row + (size_t)mt * P.meta_stride * 8;
+  const int red_off = (int)ns_round_up(img_end, 16);  // 8 floats of reduction scratch behind the image when a norm is fused
+  const size_t act_region = ns_round_up(P.norm_w ? (size_t)red_off + 32 : img_end, 128);
   const RingPlan plan = plan_ring(P, act_region);
   if (plan.stages < 1) {
     ns_set_error("gemv_ring: row pitch %d too large for shared memory", P.pitch);
     return NS_E_UNSUPPORTED;
   }
-  if (plan.rows == 2) return launch_rows<AMODE, M, ASYM, STYPE, 2>(P, plan, act_region, act_row, st);
-  return launch_rows<AMODE, M, ASYM, STYPE, 1>(P, plan, act_region, act_row, st);
+  if (plan.rows == 2) return launch_rows<AMODE, M, ASYM, STYPE, 2>(P, plan, act_region, act_row, red_off, st);
+  return launch_rows<AMODE, M, ASYM, STYPE, 1>(P, plan, act_region, act_row, red_off, st);
 }
 
 template <int AMODE, bool ASYM, int STYPE>

@@ -713,15 +713,29 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
     const Layer& L = c->layers[il];
     __half* kc = c->kc + (size_t)il * hp.n_head_kv * hp.n_ctx * hd;
     __half* vc = c->vc + (size_t)il * hp.n_head_kv * hp.n_ctx * hd;
-    if (int rc = launch_rmsnorm(c->x, L.attn_norm, c->xn, m, E, hp.norm_eps, st)) return rc;
+    // Decode rows: the attention RMSNorm (llama.cpp:205-210) rides in the activation quantiser of the Q/K/V launch(es) -- every
+    // CTA reads the whole row anyway -- instead of a one-CTA kernel and a launch boundary of its own.
+    const ns_weight* qkvw[3] = {L.wq, L.wk, L.wv};
     bool fused = false;
-    if (hp.n_head == hp.n_head_kv) {  // fused QKV node (llama.cpp:212-215); dst = [3][m][E] = q | k | v
-      fused = ns_mul_qkv(L.wq, L.wk, L.wv, c->xn, E, q, E, m, c->ws, (void*)st) == NS_OK;
+    if (hp.n_head == hp.n_head_kv && ns_gemv_fused_norm_ok(qkvw, 3, m))
+      fused = ns_mul_qkv_norm(L.wq, L.wk, L.wv, c->x, E, q, E, m, c->ws, (void*)st, L.attn_norm, hp.norm_eps) == NS_OK;
+    if (!fused && hp.n_head != hp.n_head_kv && ns_gemv_fused_norm_ok(&qkvw[0], 1, m) && ns_gemv_fused_norm_ok(&qkvw[1], 1, m) &&
+        ns_gemv_fused_norm_ok(&qkvw[2], 1, m)) {
+      if (int rc = ns_rmsnorm_mul_mat(L.wq, c->x, E, L.attn_norm, hp.norm_eps, q, E, m, nullptr, c->ws, (void*)st)) return rc;
+      if (int rc = ns_rmsnorm_mul_mat(L.wk, c->x, E, L.attn_norm, hp.norm_eps, k, kvd, m, nullptr, c->ws, (void*)st)) return rc;
+      if (int rc = ns_rmsnorm_mul_mat(L.wv, c->x, E, L.attn_norm, hp.norm_eps, v, kvd, m, nullptr, c->ws, (void*)st)) return rc;
+      fused = true;
     }
     if (!fused) {
-      if (int rc = ns_mul_mat(L.wq, c->xn, E, q, E, m, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
-      if (int rc = ns_mul_mat(L.wk, c->xn, E, k, kvd, m, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
-      if (int rc = ns_mul_mat(L.wv, c->xn, E, v, kvd, m, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
+      if (int rc = launch_rmsnorm(c->x, L.attn_norm, c->xn, m, E, hp.norm_eps, st)) return rc;
+      if (hp.n_head == hp.n_head_kv) {  // fused QKV node (llama.cpp:212-215); dst = [3][m][E] = q | k | v
+        fused = ns_mul_qkv(L.wq, L.wk, L.wv, c->xn, E, q, E, m, c->ws, (void*)st) == NS_OK;
+      }
+      if (!fused) {
+        if (int rc = ns_mul_mat(L.wq, c->xn, E, q, E, m, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
+        if (int rc = ns_mul_mat(L.wk, c->xn, E, k, kvd, m, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
+        if (int rc = ns_mul_mat(L.wv, c->xn, E, v, kvd, m, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
+      }
     }
     const bool fast = (hd == 128 || hd == 64);
     if (fast && m == 1) {  // rope + KV append + attention in one launch
@@ -749,13 +763,26 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
     }
     // inpFF = wo * attn + inpSA, written over x (every row is read by its own output only after the matmul finished)
     if (int rc = ns_mul_mat(L.wo, c->attn, E, c->xn, E, m, nullptr, c->x, 0, c->ws, (void*)st)) return rc;
-    // xn now holds inpFF; normalise it into attn (free again), FFN + residual back into x
-    if (int rc = launch_rmsnorm(c->xn, L.ffn_norm, c->attn, m, E, hp.norm_eps, st)) return rc;
-    if (int rc = ns_ffn_silu_residual(L.w1, L.w2, L.w3, c->attn, E, c->tmp, c->x, E, m, c->xn, c->ws, st)) return rc;
+    // xn now holds inpFF; FFN + residual back into x, the FFN RMSNorm folded into the gate/up launch where that is a ring GEMV,
+    // else normalised into attn (free again) first
+    const ns_weight* guw[2] = {L.w1, L.w3};
+    if (ns_gemv_fused_norm_ok(guw, 2, m)) {
+      if (int rc = ns_ffn_silu_residual(L.w1, L.w2, L.w3, c->xn, E, c->tmp, c->x, E, m, c->xn, c->ws, st, L.ffn_norm, hp.norm_eps)) return rc;
+    } else {
+      if (int rc = launch_rmsnorm(c->xn, L.ffn_norm, c->attn, m, E, hp.norm_eps, st)) return rc;
+      if (int rc = ns_ffn_silu_residual(L.w1, L.w2, L.w3, c->attn, E, c->tmp, c->x, E, m, c->xn, c->ws, st)) return rc;
+    }
   }
   // logits of the last token only (model_eval keeps the last row unless logits_all)
-  if (int rc = launch_rmsnorm(c->x + (size_t)(m - 1) * E, c->out_norm, c->xn, 1, E, hp.norm_eps, st)) return rc;
-  if (int rc = ns_mul_mat(c->output, c->xn, E, c->logits, hp.n_vocab, 1, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
+  const ns_weight* outw[1] = {c->output};
+  if (ns_gemv_fused_norm_ok(outw, 1, 1)) {
+    if (int rc = ns_rmsnorm_mul_mat(c->output, c->x + (size_t)(m - 1) * E, E, c->out_norm, hp.norm_eps, c->logits, hp.n_vocab, 1, nullptr,
+                                    c->ws, (void*)st))
+      return rc;
+  } else {
+    if (int rc = launch_rmsnorm(c->x + (size_t)(m - 1) * E, c->out_norm, c->xn, 1, E, hp.norm_eps, st)) return rc;
+    if (int rc = ns_mul_mat(c->output, c->xn, E, c->logits, hp.n_vocab, 1, nullptr, nullptr, 0, c->ws, (void*)st)) return rc;
+  }
   NS_CUDA_TRY(ns_launch_pdl(argmax_kernel, dim3((unsigned)kArgmaxBlocks), dim3(256), 0, st, (const float*)c->logits, hp.n_vocab, c->state, m,
                             advance, record, c->am_val, c->am_idx, c->am_ticket));
   ns_count_launch();
