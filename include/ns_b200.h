@@ -219,6 +219,24 @@ NS_API int ns_rmsnorm_ffn_silu(const ns_weight* w1, const ns_weight* w2, const n
                                const float* norm_w, float norm_eps, float* tmp, float* dst, int ldo, int m, const float* residual,
                                void* workspace, void* queue);
 
+/* Expert-indexed nodes of mixture-of-experts models: ne_mul_mat_id and ne_mul_id_ffn_silu / _gelu
+ * (core/ne_layers.c:2384-2460; ne_compute_forward_mul_mat_id_q_f32 :7345-7498, _q_f32_bestla :7783-7916, dispatch :7918-7943,
+ * ne_compute_forward_ffn_id_silu / _gelu :8053-8111).  dst[t] = W[e_t] . act[t] with e_t = ids[t * ids_stride + id]
+ * (ids = the int32 top-k selection [n_tokens][n_used], id = which of the n_used slots this node serves, ids_stride >= n_used).
+ * The reference walks the tokens of every expert one by one; here tokens are grouped by expert and every expert's weights are
+ * read once per node.  ids may live on the host (ids_on_device = 0, what ne_graph_compute has) or on the device (one small
+ * D2H + stream sync per node: the host sizes the per-expert launches).  Expert ids outside [0, n_as) -> NS_E_INVALID.
+ * flags: NS_MM_* of ns_mul_mat (e.g. NS_MM_FORCE_GEMV keeps the exact-integer path whatever the group size).
+ * ns_ffn_id: gelu = 0 SiLU(gate) * up (Mixtral), 1 GELU(gate) * up; tmp [2][m][fmid] floats.
+ * ns_mul_mat_id_q4_0_f32_host: the ggml-type host-buffer drop-in (expert_rows[e] = dst->opt[e]->data, ids = ids->data). */
+NS_API int ns_mul_mat_id(const ns_weight* const* experts, int n_as, const int32_t* ids, int ids_stride, int id, int ids_on_device,
+                         const float* act, int lda, float* dst, int ldo, int m, int flags, void* queue);
+NS_API int ns_ffn_id(const ns_weight* const* gate, const ns_weight* const* down, const ns_weight* const* up, int n_as, int gelu,
+                     const int32_t* ids, int ids_stride, int id, int ids_on_device, const float* act, int lda, float* tmp, float* dst,
+                     int ldo, int m, void* queue);
+NS_API int ns_mul_mat_id_q4_0_f32_host(const void* const* expert_rows, int n_as, size_t nb01, const int32_t* ids, int ids_stride,
+                                       int id, const float* src1, float* dst, int ne00, int ne01, int ne11);
+
 /* The two phases of a reference matmul node, separately (ne_compute_forward_mul_mat_q_f32: NE_TASK_INIT quantises src1
  * into wdata, NE_TASK_COMPUTE runs the dots; core/ne_layers.c:7143-7203):
  *   ns_prepare_activation  act[m][k] (device fp32) -> activation image in `workspace` (m <= 4 rows per image)

@@ -52,6 +52,7 @@ EXPORTS = [
     "ns_weight_from_q4_0", "ns_weight_from_q6_K", "ns_weight_from_btla_blob", "ns_weight_from_btla_blob_n", "ns_weight_random", "ns_weight_from_unpacked", "ns_weight_free", "ns_weight_info",
     "ns_weight_set_comp", "ns_weight_algorithmic_bytes", "ns_weight_dequant_f32",
     "ns_mul_mat", "ns_mul_qkv", "ns_ffn_silu", "ns_ffn_gelu",
+    "ns_mul_mat_id", "ns_ffn_id", "ns_mul_mat_id_q4_0_f32_host",
     "ns_rmsnorm_fusable", "ns_rmsnorm_mul_mat", "ns_rmsnorm_mul_qkv", "ns_rmsnorm_ffn_silu", "ns_mul_mat_q4_0_f32_host", "ns_mul_mat_q6_K_f32_host",
     "ns_program_create", "ns_program_add_matmul", "ns_program_add_matmul_ex", "ns_program_tag_last", "ns_program_finalize", "ns_program_run",
     "ns_program_run_n", "ns_program_algorithmic_bytes", "ns_program_free", "ns_program_timeline", "ns_program_unit_trace",
@@ -140,6 +141,9 @@ def lib() -> C.CDLL:
     L.ns_ffn_silu.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp, vp]
     L.ns_ffn_gelu.argtypes = [vp, vp, vp, vp, vp, i, vp, i, vp, vp, i, i, vp, vp]
     L.ns_rmsnorm_fusable.argtypes = [vp, i, i]
+    L.ns_mul_mat_id.argtypes = [vp, i, vp, i, i, i, vp, i, vp, i, i, i, vp]
+    L.ns_ffn_id.argtypes = [vp, vp, vp, i, i, vp, i, i, i, vp, i, vp, vp, i, i, vp]
+    L.ns_mul_mat_id_q4_0_f32_host.argtypes = [vp, i, sz, vp, i, i, vp, vp, i, i, i]
     L.ns_rmsnorm_mul_mat.argtypes = [vp, vp, i, vp, C.c_float, vp, i, i, vp, vp, vp]
     L.ns_rmsnorm_mul_qkv.argtypes = [vp, vp, vp, vp, i, vp, C.c_float, vp, i, i, vp, vp]
     L.ns_rmsnorm_ffn_silu.argtypes = [vp, vp, vp, vp, i, vp, C.c_float, vp, vp, i, i, vp, vp, vp]
@@ -391,10 +395,35 @@ def ffn_silu(w1: Weight, w2: Weight, w3: Weight, act_ptr: int, lda: int, tmp_ptr
                              None, queue), "ns_ffn_silu")
 
 
+def _handles(ws):
+    return (C.c_void_p * len(ws))(*[w.h for w in ws])
+
+
+def mul_mat_id(experts, ids, id: int, act_ptr: int, lda: int, dst_ptr: int, ldo: int, m: int, flags=0, queue=None):
+    """ne_mul_mat_id: dst[t] = experts[ids[t, id]] . act[t].  ids: int32 numpy [m][n_used] (host) or a (device_ptr, stride) tuple."""
+    if isinstance(ids, tuple):
+        ptr, stride, on_dev = C.c_void_p(ids[0]), int(ids[1]), 1
+    else:
+        ids = np.ascontiguousarray(ids, np.int32)
+        ptr, stride, on_dev = ids.ctypes.data_as(C.c_void_p), ids.shape[1], 0
+    _check(lib().ns_mul_mat_id(_handles(experts), len(experts), ptr, stride, id, on_dev, C.c_void_p(act_ptr), lda, C.c_void_p(dst_ptr),
+                               ldo, m, flags, queue), "ns_mul_mat_id")
+
+
+def ffn_id(gate, down, up, ids, id: int, act_ptr: int, lda: int, tmp_ptr: int, dst_ptr: int, ldo: int, m: int, gelu=False, queue=None):
+    """ne_mul_id_ffn_silu / _gelu with per-token expert selection (ids as in mul_mat_id)."""
+    if isinstance(ids, tuple):
+        ptr, stride, on_dev = C.c_void_p(ids[0]), int(ids[1]), 1
+    else:
+        ids = np.ascontiguousarray(ids, np.int32)
+        ptr, stride, on_dev = ids.ctypes.data_as(C.c_void_p), ids.shape[1], 0
+    _check(lib().ns_ffn_id(_handles(gate), _handles(down), _handles(up), len(gate), 1 if gelu else 0, ptr, stride, id, on_dev,
+                           C.c_void_p(act_ptr), lda, C.c_void_p(tmp_ptr), C.c_void_p(dst_ptr), ldo, m, queue), "ns_ffn_id")
+
+
 def rmsnorm_fusable(weights, m: int) -> bool:
     """Can RMSNorm(x) * norm_w be folded into the launch of these 1..3 weights for m activation rows?"""
-    arr = (C.c_void_p * len(weights))(*[w.h for w in weights])
-    return bool(lib().ns_rmsnorm_fusable(arr, len(weights), m))
+    return bool(lib().ns_rmsnorm_fusable(_handles(weights), len(weights), m))
 
 
 def rmsnorm_mul_mat(w: Weight, act_ptr: int, lda: int, norm_ptr: int, eps: float, dst_ptr: int, ldo: int, m: int, residual_ptr=None,

@@ -806,6 +806,149 @@ extern "C" int ns_ffn_gelu(const ns_weight* w1, const ns_weight* w2, const ns_we
   return ffn_impl(w1, w2, w3, NS_ELT_GELU, b1, b2, bias_bcast, act, lda, tmp, dst, ldo, m, workspace, queue);
 }
 
+// ---------------------------------------------------------------------------------------------------- expert-indexed nodes
+// ne_mul_mat_id / ne_mul_id_ffn_silu (core/ne_layers.c:2384-2460; compute :7345-7498 ggml types, :7783-7916 BesTLA blobs,
+// :8053-8071 fused FFN): dst[t] = W[ids[t * ids_stride + id]] . act[t].  See moe.cu for the grouping scheme.
+struct ExpertPlan {
+  std::vector<int> order;                 // token indices sorted (stably) by expert
+  std::vector<std::pair<int, int>> span;  // per expert: [begin, end) inside `order`
+  bool identity;                          // order == 0..m-1: the rows already lie grouped, no gather / scatter
+};
+static int plan_experts(const int32_t* ids, int ids_stride, int id, int ids_on_device, int m, int n_as, cudaStream_t st, ExpertPlan* pl) {
+  if (!ids || ids_stride < 1 || id < 0 || id >= ids_stride || n_as < 1 || n_as > 256 || m < 1) {
+    ns_set_error("ns_mul_mat_id: invalid ids (stride=%d id=%d n_as=%d m=%d)", ids_stride, id, n_as, m);
+    return NS_E_INVALID;
+  }
+  std::vector<int32_t> host;
+  const int32_t* h = ids;
+  if (ids_on_device) {  // the routing decision is needed on the host to size the per-expert launches: one small D2H + sync
+    host.resize((size_t)m * ids_stride);
+    NS_CUDA_TRY(cudaMemcpyAsync(host.data(), ids, host.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    NS_CUDA_TRY(cudaStreamSynchronize(st));
+    h = host.data();
+  }
+  std::vector<int> count((size_t)n_as, 0);
+  for (int t = 0; t < m; ++t) {
+    const int e = h[(size_t)t * ids_stride + id];
+    if (e < 0 || e >= n_as) {  // NE_ASSERT(row_id >= 0 && row_id < n_as), ne_layers.c:7445
+      ns_set_error("ns_mul_mat_id: expert id %d of token %d outside [0, %d)", e, t, n_as);
+      return NS_E_INVALID;
+    }
+    ++count[(size_t)e];
+  }
+  pl->span.assign((size_t)n_as, {0, 0});
+  int at = 0;
+  for (int e = 0; e < n_as; ++e) {
+    pl->span[(size_t)e] = {at, at};
+    at += count[(size_t)e];
+  }
+  pl->order.assign((size_t)m, 0);
+  for (int t = 0; t < m; ++t) pl->order[(size_t)pl->span[(size_t)h[(size_t)t * ids_stride + id]].second++] = t;
+  pl->identity = true;
+  for (int t = 0; t < m; ++t) pl->identity = pl->identity && pl->order[(size_t)t] == t;
+  return NS_OK;
+}
+
+// scratch of a grouped node: [order: m int][xg: m x k][yg: m x n][workspace of the matmuls]
+struct ExpertScratch {
+  int* order;
+  float *xg, *yg;
+  void* ws;
+};
+static int expert_scratch(const ExpertPlan& pl, int m, int k, int n, size_t mm_ws, cudaStream_t st, ExpertScratch* sc) {
+  const size_t ob = ns_round_up((size_t)m * 4, 256), xb = ns_round_up((size_t)m * k * 4, 256), yb = ns_round_up((size_t)m * n * 4, 256);
+  char* base = (char*)scratch_get(st, ob + xb + yb + mm_ws + 256);
+  if (!base) return NS_E_CUDA;
+  sc->order = (int*)base;
+  sc->xg = (float*)(base + ob);
+  sc->yg = (float*)(base + ob + xb);
+  sc->ws = base + ob + xb + yb;
+  if (!pl.identity) NS_CUDA_TRY(cudaMemcpyAsync(sc->order, pl.order.data(), (size_t)m * 4, cudaMemcpyHostToDevice, st));
+  return NS_OK;
+}
+
+// a slice of c <= m rows may take any of the matmul paths: the workspace must cover the largest of them
+static size_t expert_ws_bytes(int m, int k) {
+  size_t b = ns_device_workspace_bytes(m, k);
+  const size_t small = ns_device_workspace_bytes(m < 32 ? m : 32, k), q6 = ns_q6k_workspace_bytes(4, k);
+  b = b > small ? b : small;
+  return b > q6 ? b : q6;
+}
+
+extern "C" int ns_mul_mat_id(const ns_weight* const* experts, int n_as, const int32_t* ids, int ids_stride, int id, int ids_on_device,
+                             const float* act, int lda, float* dst, int ldo, int m, int flags, void* queue) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!experts || !act || !dst || n_as < 1 || m < 1) return NS_E_INVALID;
+  for (int e = 0; e < n_as; ++e)
+    if (!experts[e] || experts[e]->n != experts[0]->n || experts[e]->k != experts[0]->k) {  // ne_are_same_shape(as[0], a), ne_layers.c:2409
+      ns_set_error("ns_mul_mat_id: expert %d missing or of another shape", e);
+      return NS_E_INVALID;
+    }
+  const int n = experts[0]->n, k = experts[0]->k;
+  if (lda < k || ldo < n) return NS_E_INVALID;
+  cudaStream_t st = stream_of(queue);
+  ExpertPlan pl;
+  if (int rc = plan_experts(ids, ids_stride, id, ids_on_device, m, n_as, st, &pl)) return rc;
+  ExpertScratch sc;
+  if (int rc = expert_scratch(pl, m, k, n, expert_ws_bytes(m, k), st, &sc)) return rc;
+  const float* x = act;
+  float* y = dst;
+  int ldx = lda, ldy = ldo;
+  if (!pl.identity) {
+    if (int rc = ns_launch_move_rows(true, act, lda, sc.order, sc.xg, k, m, k, st)) return rc;
+    x = sc.xg, y = sc.yg, ldx = k, ldy = n;
+  }
+  for (int e = 0; e < n_as; ++e) {
+    const int b = pl.span[(size_t)e].first, c = pl.span[(size_t)e].second - b;
+    if (c == 0) continue;
+    if (int rc = mul_mat_impl(experts[e], x + (size_t)b * ldx, ldx, y + (size_t)b * ldy, ldy, c, nullptr, nullptr, flags, sc.ws, (void*)st,
+                              nullptr, 0.f))
+      return rc;
+  }
+  if (!pl.identity) return ns_launch_move_rows(false, sc.yg, n, sc.order, dst, ldo, m, n, st);
+  return NS_OK;
+}
+
+// ne_mul_id_ffn_silu / _gelu: dst[t] = W2[e] (act(W1[e] x_t) * (W3[e] x_t)), e = ids[t * ids_stride + id].  The reference's
+// compute (ne_layers.c:8053-8071, :8093-8111) reads ONE id (token 0) and applies that expert to every row -- exact for the
+// decode step it is used in; here every token follows its own id.  tmp: [2][m][fmid] floats.
+extern "C" int ns_ffn_id(const ns_weight* const* gate, const ns_weight* const* down, const ns_weight* const* up, int n_as, int gelu,
+                         const int32_t* ids, int ids_stride, int id, int ids_on_device, const float* act, int lda, float* tmp,
+                         float* dst, int ldo, int m, void* queue) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!gate || !down || !up || !act || !tmp || !dst || n_as < 1 || m < 1) return NS_E_INVALID;
+  for (int e = 0; e < n_as; ++e)
+    if (!gate[e] || !down[e] || !up[e] || gate[e]->n != gate[0]->n || gate[e]->k != gate[0]->k || down[e]->n != down[0]->n ||
+        down[e]->k != gate[0]->n || up[e]->n != gate[0]->n || up[e]->k != gate[0]->k) {
+      ns_set_error("ns_ffn_id: expert %d missing or of another shape", e);
+      return NS_E_INVALID;
+    }
+  const int k = gate[0]->k, fmid = gate[0]->n, n = down[0]->n;
+  if (lda < k || ldo < n) return NS_E_INVALID;
+  cudaStream_t st = stream_of(queue);
+  ExpertPlan pl;
+  if (int rc = plan_experts(ids, ids_stride, id, ids_on_device, m, n_as, st, &pl)) return rc;
+  ExpertScratch sc;
+  const size_t w1 = expert_ws_bytes(m, k), w2 = expert_ws_bytes(m, fmid);
+  if (int rc = expert_scratch(pl, m, k, n, w1 > w2 ? w1 : w2, st, &sc)) return rc;
+  const float* x = act;
+  float* y = dst;
+  int ldx = lda, ldy = ldo;
+  if (!pl.identity) {
+    if (int rc = ns_launch_move_rows(true, act, lda, sc.order, sc.xg, k, m, k, st)) return rc;
+    x = sc.xg, y = sc.yg, ldx = k, ldy = n;
+  }
+  for (int e = 0; e < n_as; ++e) {
+    const int b = pl.span[(size_t)e].first, c = pl.span[(size_t)e].second - b;
+    if (c == 0) continue;
+    if (int rc = ffn_impl(gate[e], down[e], up[e], gelu ? NS_ELT_GELU : NS_ELT_DEFAULT, nullptr, nullptr, 0, x + (size_t)b * ldx, ldx,
+                          tmp + (size_t)2 * b * fmid, y + (size_t)b * ldy, ldy, c, sc.ws, (void*)st))
+      return rc;
+  }
+  if (!pl.identity) return ns_launch_move_rows(false, sc.yg, n, sc.order, dst, ldo, m, n, st);
+  return NS_OK;
+}
+
 extern "C" int ns_prepare_activation(const ns_weight* w, const float* act, int lda, int m, void* workspace, void* queue) {
   if (int rc = ns_ensure_device()) return rc;
   if (!w || !act || !workspace || m < 1 || m > ns_gemv_tile_rows(w) || lda < w->k) {
@@ -1239,32 +1382,29 @@ extern "C" size_t ns_host_cache_entries(void) {
 }
 
 // ggml host drop-in
+static const ns_weight* ggml_cached_weight(int q6k, const void* src0_rows, size_t nb01, int ne00, int ne01) {
+  const size_t tag = blob_tag(src0_rows, (size_t)(ne01 - 1) * nb01 + (size_t)(ne00 / (q6k ? 256 : 32)) * (q6k ? 210 : 18)) ^
+                     ((size_t)ne00 << 32) ^ (size_t)ne01 ^ ((size_t)q6k << 63);
+  std::unique_lock<std::mutex> lk(g_mu);
+  auto it = g_cache.find(src0_rows);
+  if (it != g_cache.end() && it->second.tag == tag) return it->second.w;
+  lk.unlock();
+  ns_weight* nw = q6k ? ns_weight_from_q6_K(src0_rows, ne01, ne00, nb01, 0, nullptr) : ns_weight_from_q4_0(src0_rows, ne01, ne00, nb01, 0, nullptr);
+  if (!nw) return nullptr;
+  lk.lock();
+  auto it2 = g_cache.find(src0_rows);
+  if (it2 != g_cache.end()) ns_weight_free(it2->second.w);
+  g_cache[src0_rows] = CacheEntry{nw, tag};
+  return nw;
+}
 static int ggml_mul_mat_host(int q6k, const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01, int ne11) {
   if (int rc = ns_ensure_device()) return rc;
   if (!src0_rows || !src1 || !dst || ne00 % (q6k ? 256 : 32) != 0 || ne01 <= 0 || ne11 <= 0) {
     ns_set_error("ggml host matmul: invalid arguments");
     return NS_E_INVALID;
   }
-  const ns_weight* w = nullptr;
-  {
-    const size_t tag = blob_tag(src0_rows, (size_t)(ne01 - 1) * nb01 + (size_t)(ne00 / (q6k ? 256 : 32)) * (q6k ? 210 : 18)) ^
-                       ((size_t)ne00 << 32) ^ (size_t)ne01 ^ ((size_t)q6k << 63);
-    std::unique_lock<std::mutex> lk(g_mu);
-    auto it = g_cache.find(src0_rows);
-    if (it != g_cache.end() && it->second.tag == tag) {
-      w = it->second.w;
-    } else {
-      lk.unlock();
-      ns_weight* nw = q6k ? ns_weight_from_q6_K(src0_rows, ne01, ne00, nb01, 0, nullptr)
-                          : ns_weight_from_q4_0(src0_rows, ne01, ne00, nb01, 0, nullptr);
-      if (!nw) return NS_E_CUDA;
-      lk.lock();
-      auto it2 = g_cache.find(src0_rows);
-      if (it2 != g_cache.end()) ns_weight_free(it2->second.w);
-      g_cache[src0_rows] = CacheEntry{nw, tag};
-      w = nw;
-    }
-  }
+  const ns_weight* w = ggml_cached_weight(q6k, src0_rows, nb01, ne00, ne01);
+  if (!w) return NS_E_CUDA;
   cudaStream_t st = default_stream();
   if (!io_reserve(&g_io.act, &g_io.act_elems, (size_t)ne11 * ne00) || !io_reserve(&g_io.out, &g_io.out_elems, (size_t)ne11 * ne01)) {
     ns_set_error("device staging allocation failed");
@@ -1283,4 +1423,30 @@ extern "C" int ns_mul_mat_q4_0_f32_host(const void* src0_rows, size_t nb01, cons
 extern "C" int ns_mul_mat_q6_K_f32_host(const void* src0_rows, size_t nb01, const float* src1, float* dst, int ne00, int ne01,
                                         int ne11) {
   return ggml_mul_mat_host(1, src0_rows, nb01, src1, dst, ne00, ne01, ne11);
+}
+// ne_compute_forward_mul_mat_id_q_f32 (ne_layers.c:7345-7498) on host buffers: expert_rows[e] = dst->opt[e]->data (Q4_0 rows of
+// pitch nb01), ids = ids->data with ids_stride = ids->nb[1] / 4 int32 per token, id = dst->op_params[0]
+extern "C" int ns_mul_mat_id_q4_0_f32_host(const void* const* expert_rows, int n_as, size_t nb01, const int32_t* ids, int ids_stride,
+                                           int id, const float* src1, float* dst, int ne00, int ne01, int ne11) {
+  if (int rc = ns_ensure_device()) return rc;
+  if (!expert_rows || !ids || !src1 || !dst || n_as < 1 || n_as > 256 || ne00 % 32 != 0 || ne01 <= 0 || ne11 <= 0) {
+    ns_set_error("ggml host mul_mat_id: invalid arguments");
+    return NS_E_INVALID;
+  }
+  std::vector<const ns_weight*> ws((size_t)n_as, nullptr);
+  for (int e = 0; e < n_as; ++e) {
+    if (!expert_rows[e]) return NS_E_INVALID;
+    ws[(size_t)e] = ggml_cached_weight(0, expert_rows[e], nb01, ne00, ne01);
+    if (!ws[(size_t)e]) return NS_E_CUDA;
+  }
+  cudaStream_t st = default_stream();
+  if (!io_reserve(&g_io.act, &g_io.act_elems, (size_t)ne11 * ne00) || !io_reserve(&g_io.out, &g_io.out_elems, (size_t)ne11 * ne01)) {
+    ns_set_error("device staging allocation failed");
+    return NS_E_CUDA;
+  }
+  NS_CUDA_TRY(cudaMemcpyAsync(g_io.act, src1, (size_t)ne11 * ne00 * 4, cudaMemcpyHostToDevice, st));
+  if (int rc = ns_mul_mat_id(ws.data(), n_as, ids, ids_stride, id, 0, g_io.act, ne00, g_io.out, ne01, ne11, 0, st)) return rc;
+  NS_CUDA_TRY(cudaMemcpyAsync(dst, g_io.out, (size_t)ne11 * ne01 * 4, cudaMemcpyDeviceToHost, st));
+  NS_CUDA_TRY(cudaStreamSynchronize(st));
+  return NS_OK;
 }

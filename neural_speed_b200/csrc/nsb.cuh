@@ -103,6 +103,10 @@ int ns_ffn_silu_residual(const ns_weight* w1, const ns_weight* w2, const ns_weig
 int ns_mul_qkv_norm(const ns_weight* wq, const ns_weight* wk, const ns_weight* wv, const float* act, int lda, float* dst, int ldo,
                     int m, void* workspace, void* queue, const float* norm_w, float norm_eps);
 
+// moe.cu: dst[i] = src[idx[i]] (gather) or dst[idx[i]] = src[i] (scatter), rows of `cols` floats
+int ns_launch_move_rows(bool gather, const float* src, int ld_src, const int* idx_dev, float* dst, int ld_dst, int rows, int cols,
+                        cudaStream_t st);
+
 // tensor-core path (gemm_tc.cu)
 size_t ns_gemm_tc_workspace_bytes(int m, int kpad);
 bool ns_gemm_tc_supported(const ns_weight* w);

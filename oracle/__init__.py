@@ -75,6 +75,12 @@ _ref_ne_ns = None
 
 
 def _bind_llama(L):
+    L.ref_ne_mul_mat_id.restype = None
+    L.ref_ne_mul_mat_id.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_int, C.c_void_p, C.c_int]
+    L.ref_ne_ffn_id_silu.restype = None
+    L.ref_ne_ffn_id_silu.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_int, C.c_void_p, C.c_int]
     L.ref_ne_llama_create.restype = C.c_void_p
     L.ref_ne_llama_create.argtypes = [C.c_int] * 7 + [C.c_float] * 3
     L.ref_ne_llama_create_ex.restype = C.c_void_p
@@ -327,6 +333,51 @@ def mul_mat_q6_K_f32(wq, a, impl="oracle", nth=0):
     fn.restype = C.c_int
     fn(_p(wq), _p(a), _p(dst), C.c_int(n), C.c_int(k), C.c_int(m), _p(wdata), C.c_int(nth))
     return dst
+
+
+NE_TYPE_Q4_0, NE_TYPE_BTLA = 2, 19  # enum ne_type (core/data_types.h:32-55)
+
+
+def _blob_table(blobs):
+    blobs = [np.ascontiguousarray(b) for b in blobs]
+    ptrs = (C.c_void_p * len(blobs))(*[b.ctypes.data for b in blobs])
+    sizes = (C.c_size_t * len(blobs))(*[b.nbytes for b in blobs])
+    return blobs, ptrs, sizes
+
+
+def ref_mul_mat_id(L, experts, wtype, n, k, ids, id, b, n_threads=1):
+    """ne_mul_mat_id through the REFERENCE's engine L (ref_ne() on the CPU, ref_ne_ns() on the CUDA drop-ins).
+    experts: list of Q4_0 row arrays / BesTLA blobs; ids int32 [n_tok][n_used]; b fp32 [n_tok][k] -> [n_tok][n]."""
+    keep, ptrs, sizes = _blob_table(experts)
+    ids = np.ascontiguousarray(ids, np.int32)
+    b = np.ascontiguousarray(b, np.float32)
+    out = np.zeros((b.shape[0], n), np.float32)
+    L.ref_ne_mul_mat_id(ptrs, sizes, wtype, len(keep), n, k, _p(ids), ids.shape[1], id, _p(b), b.shape[0], _p(out), n_threads)
+    return out
+
+
+def ref_ffn_id_silu(L, gate, down, up, k, fmid, n_out, ids, id, src, n_threads=1):
+    """ne_mul_id_ffn_silu (BesTLA blobs) through the reference's engine L."""
+    keep, ptrs, sizes = _blob_table(list(gate) + list(down) + list(up))
+    ids = np.ascontiguousarray(ids, np.int32)
+    src = np.ascontiguousarray(src, np.float32)
+    out = np.zeros((src.shape[0], n_out), np.float32)
+    L.ref_ne_ffn_id_silu(ptrs, sizes, len(gate), k, fmid, n_out, _p(ids), ids.shape[1], id, _p(src), src.shape[0], _p(out), n_threads)
+    return out
+
+
+def mul_mat_id_q4_0_f32(expert_rows, ids, id, a):
+    """Restatement of ne_compute_forward_mul_mat_id_q_f32 (core/ne_layers.c:7345-7498) for Q4_0 experts: token t takes expert
+    ids[t][id]; its row is quantised to Q8_0 (NE_TASK_INIT, :7418-7431) and dotted with every weight row of that expert."""
+    ids = np.asarray(ids, np.int32)
+    a = np.ascontiguousarray(a, np.float32)
+    n = expert_rows[0].shape[0]
+    out = np.zeros((a.shape[0], n), np.float32)
+    for t in range(a.shape[0]):
+        e = int(ids[t, id])
+        assert 0 <= e < len(expert_rows)  # NE_ASSERT(row_id >= 0 && row_id < n_as), :7445
+        out[t] = mul_mat_q4_0_f32(expert_rows[e], a[t:t + 1])[0]
+    return out
 
 
 def argmax(x):
