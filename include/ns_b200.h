@@ -56,6 +56,13 @@ enum ns_ne_comp_type { NS_NE_COMP_UNDEF = 0, NS_NE_COMP_F32 = 1, NS_NE_COMP_BF16
 #define NS_BTLA_S8 (8u | (1u << 8))
 #define NS_BTLA_S4_CLIP (4u | (1u << 8))
 #define NS_BTLA_F4_NF4 (4u | (2u << 16))
+/* bit-plane integer types (bestla.h:75-81, storage bestla_storage.h:724-745): held on the device in the 4-bit (2, 3 bits) or
+ * 8-bit (5, 6, 7 bits) container, same integers, same scales and zero points */
+#define NS_BTLA_S2_CLIP (2u | (1u << 8))
+#define NS_BTLA_S3_CLIP (3u | (1u << 8))
+#define NS_BTLA_S5_CLIP (5u | (1u << 8))
+#define NS_BTLA_S6_CLIP (6u | (1u << 8))
+#define NS_BTLA_S7_CLIP (7u | (1u << 8))
 
 #define NS_OK 0
 #define NS_E_INVALID (-1)

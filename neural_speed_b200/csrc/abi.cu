@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "nsb.cuh"
+#include "btla_planes.h"
 
 // ---------------------------------------------------------------------------------------------------- errors / context
 static thread_local char g_err[512] = "";
@@ -446,11 +447,14 @@ static int blob_to_weight_meta(const BlobView& v, ns_weight* w) {
   w->n = v.n;
   w->k = v.k;
   w->group = v.blocksize;
-  if (v.dtype == NS_BTLA_S4_CLIP) w->wfmt = NS_W_S4;
-  else if (v.dtype == NS_BTLA_S8) w->wfmt = NS_W_S8;
+  const int qbits = (int)(v.dtype & 0xff);
+  const bool planes = v.dtype == NS_BTLA_S2_CLIP || v.dtype == NS_BTLA_S3_CLIP || v.dtype == NS_BTLA_S5_CLIP ||
+                      v.dtype == NS_BTLA_S6_CLIP || v.dtype == NS_BTLA_S7_CLIP;
+  if (v.dtype == NS_BTLA_S4_CLIP || (planes && qbits < 4)) w->wfmt = NS_W_S4;  // 2- / 3-bit codes ride in the 4-bit container
+  else if (v.dtype == NS_BTLA_S8 || planes) w->wfmt = NS_W_S8;                 // 5- / 6- / 7-bit codes in the 8-bit one
   else if (v.dtype == NS_BTLA_F4_NF4) w->wfmt = NS_W_NF4;
   else {
-    ns_set_error("blob: weight dtype 0x%x not supported (int4 / int8 / nf4 are)", v.dtype);
+    ns_set_error("blob: weight dtype 0x%x not supported (int2..int8 / nf4 are)", v.dtype);
     return NS_E_UNSUPPORTED;
   }
   if (v.sca_t == NS_BTLA_F32) w->stype = NS_S_F32;
@@ -476,7 +480,12 @@ static int blob_to_weight_meta(const BlobView& v, ns_weight* w) {
     ns_set_error("blob: block size %d is not a multiple of 32", w->group);
     return NS_E_UNSUPPORTED;
   }
-  const size_t need_q = (size_t)v.npad * v.kpad * (w->wfmt == NS_W_S8 ? 2 : 1) / 2;
+  size_t need_q = (size_t)v.npad * v.kpad * (w->wfmt == NS_W_S8 ? 2 : 1) / 2;
+  if (planes) {
+    ns_planes::Layout pl;
+    ns_planes::layout(qbits, (size_t)v.npad * v.kpad, &pl);
+    need_q = pl.bytes;
+  }
   const int ngroups_src = (v.kpad + v.blocksize - 1) / v.blocksize;
   if (v.qbytes < need_q || v.scale_bytes < (size_t)ngroups_src * v.cstep * stype_size(w->stype) || v.cstep < v.n ||
       (v.zp && v.zp_bytes < (size_t)ngroups_src * v.cstep) || (v.shuffle && v.shuffle_bytes < (size_t)v.k * 4)) {
@@ -488,10 +497,36 @@ static int blob_to_weight_meta(const BlobView& v, ns_weight* w) {
 
 // upload the pieces of a blob and repack into w (whose device pointers are already carved)
 static int blob_upload_repack(const BlobView& v, ns_weight* w, cudaStream_t st) {
-  const size_t qb = ns_round_up(v.qbytes, 256), sb = ns_round_up(v.scale_bytes, 256), zb = ns_round_up(v.zp_bytes, 256);
+  // bit-plane codes (2, 3, 5, 6, 7 bits): transcoded on the host, element by element in the blob's own tile order, into the nibble
+  // (q + 8) or byte (q) form of the 4- / 8-bit container the repack kernel reads -- the integers, scales and zero points are
+  // unchanged, so every matmul path sees exactly the weight the reference would dequantise
+  std::vector<uint8_t> trans;
+  const uint8_t* qsrc = v.qbuf;
+  size_t qbytes = v.qbytes;
+  const int qbits = (int)(v.dtype & 0xff);
+  if (v.prologue == 1 && qbits != 4 && qbits != 8) {
+    const size_t E = (size_t)v.npad * v.kpad;
+    ns_planes::Layout pl;
+    if (!ns_planes::layout(qbits, E, &pl) || v.qbytes < pl.bytes) return NS_E_INVALID;
+    const int full = 1 << (qbits - 1);
+    if (w->wfmt == NS_W_S4) {
+      trans.assign(E / 2 + 1, 0);
+      for (size_t e = 0; e < E; ++e) {
+        const unsigned u = (unsigned)(ns_planes::get(v.qbuf, pl, e) - full + 8) & 0xfu;
+        trans[e >> 1] = (uint8_t)((e & 1) ? (trans[e >> 1] | (u << 4)) : u);
+      }
+      qbytes = E / 2;
+    } else {
+      trans.resize(E);
+      for (size_t e = 0; e < E; ++e) trans[e] = (uint8_t)(int8_t)(ns_planes::get(v.qbuf, pl, e) - full);
+      qbytes = E;
+    }
+    qsrc = trans.data();
+  }
+  const size_t qb = ns_round_up(qbytes, 256), sb = ns_round_up(v.scale_bytes, 256), zb = ns_round_up(v.zp_bytes, 256);
   char* tmp = nullptr;
   NS_CUDA_TRY(cudaMalloc((void**)&tmp, qb + sb + zb + 256));
-  bool ok = ns_cuda_ok(cudaMemcpyAsync(tmp, v.qbuf, v.qbytes, cudaMemcpyHostToDevice, st), "H2D qbuf");
+  bool ok = ns_cuda_ok(cudaMemcpyAsync(tmp, qsrc, qbytes, cudaMemcpyHostToDevice, st), "H2D qbuf");
   ok = ok && ns_cuda_ok(cudaMemcpyAsync(tmp + qb, v.scale, v.scale_bytes, cudaMemcpyHostToDevice, st), "H2D scales");
   if (v.zp) ok = ok && ns_cuda_ok(cudaMemcpyAsync(tmp + qb + sb, v.zp, v.zp_bytes, cudaMemcpyHostToDevice, st), "H2D zp");
   if (v.shuffle && w->shuffle)

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/ns_b200.h"
+#include "btla_planes.h"
 
 namespace {
 
@@ -196,6 +197,9 @@ BlobDims blob_dims(const BlobLayoutIn& L) {
   d.kpad = (int)pad_to(L.K, L.core->ktile);
   d.nk_scale = (int)((d.kpad + L.blk - 1) / L.blk);
   d.qbytes = ((size_t)d.npad * d.kpad * dtype_bits(L.qtype) + 7) / 8;
+  ns_planes::Layout pl;  // 2/3/5/6/7-bit codes: a sum of power-of-two planes (bestla_storage.h:724-745)
+  if (dtype_bits(L.qtype) != 4 && dtype_bits(L.qtype) != 8 && ns_planes::layout(dtype_bits(L.qtype), (size_t)d.npad * d.kpad, &pl))
+    d.qbytes = pl.bytes;
   const size_t csize = (size_t)d.nk_scale * d.npad;
   d.sbytes = csize * dtype_size(L.stype);
   d.zbytes = L.asym ? csize : 0;
@@ -278,6 +282,9 @@ void pack_q(const int8_t* q, int N, int K, const BlobLayoutIn& L, const BlobDims
   const int nt = L.core->ntile, pr = L.core->packrow;
   const int bits = dtype_bits(L.qtype);
   const int bias = L.is_float ? 0 : 8;
+  ns_planes::Layout pl{};
+  const bool planes = bits != 4 && bits != 8 && ns_planes::layout(bits, (size_t)d.npad * d.kpad, &pl);
+  // (a tile block is kpad * 48 consecutive elements: a multiple of 8, so no plane byte is shared between two threads)
 #pragma omp parallel for schedule(static)
   for (int nb = 0; nb < d.npad / nt; ++nb) {
     for (int k = 0; k < d.kpad; ++k) {
@@ -287,6 +294,8 @@ void pack_q(const int8_t* q, int N, int K, const BlobLayoutIn& L, const BlobDims
         const size_t e = (size_t)nb * d.kpad * nt + (size_t)(k / pr) * pr * nt + (size_t)j * pr + (k % pr);
         if (bits == 8) {
           out[e] = (uint8_t)v;
+        } else if (planes) {
+          ns_planes::put(out, pl, e, v + (1 << (bits - 1)));
         } else {
           const uint8_t u = (uint8_t)((v + bias) & 0xf);
           if (e & 1) out[e >> 1] = (uint8_t)((out[e >> 1] & 0x0f) | (u << 4));
@@ -346,7 +355,9 @@ bool make_layout(size_t N, size_t K, size_t blk, uint32_t qtype, uint32_t stype,
   if (!N || !K) return false;
   if (blk == 0 || blk > K) blk = K;
   const bool is_int = dtype_is_int(qtype);
-  if (!(qtype == NS_BTLA_S4_CLIP || qtype == NS_BTLA_S8 || qtype == NS_BTLA_F4_NF4)) return false;
+  if (!(qtype == NS_BTLA_S4_CLIP || qtype == NS_BTLA_S8 || qtype == NS_BTLA_F4_NF4 || qtype == NS_BTLA_S2_CLIP ||
+        qtype == NS_BTLA_S3_CLIP || qtype == NS_BTLA_S5_CLIP || qtype == NS_BTLA_S6_CLIP || qtype == NS_BTLA_S7_CLIP))
+    return false;
   if (!(stype == NS_BTLA_F32 || stype == NS_BTLA_BF16 || stype == NS_BTLA_F16)) return false;
   const Core* c = pick_core(qtype, blk, asym, comp);
   if (!c) return false;
@@ -468,7 +479,9 @@ extern "C" bool BTLAGemmUnPackB(float* FpData, const void* PackedBuf, size_t N, 
   const int nt = (int)(core & 0xff), pr = (int)((core >> 8) & 0xff);
   const bool is_float = prologue == 2;
   const int bits = dtype_bits(qtype);
-  if (!(bits == 4 || bits == 8) || nt <= 0 || pr <= 0) return false;
+  ns_planes::Layout pl{};
+  const bool planes = bits != 4 && bits != 8;
+  if (nt <= 0 || pr <= 0 || (planes && (is_float || !ns_planes::layout(bits, (size_t)npad * kpad, &pl) || qb < pl.bytes))) return false;
 #pragma omp parallel for schedule(static)
   for (long long kk = 0; kk < (long long)K; ++kk)
     for (size_t nn = 0; nn < N; ++nn) {
@@ -478,6 +491,8 @@ extern "C" bool BTLAGemmUnPackB(float* FpData, const void* PackedBuf, size_t N, 
       float v;
       if (bits == 8) {
         v = (float)((int)(int8_t)qbuf[e] - (zbuf ? (int8_t)zbuf[ci] : 0)) * s;
+      } else if (planes) {
+        v = (float)(ns_planes::get(qbuf, pl, e) - (1 << (bits - 1)) - (zbuf ? (int8_t)zbuf[ci] : 0)) * s;
       } else {
         const int u = (e & 1) ? (qbuf[e >> 1] >> 4) : (qbuf[e >> 1] & 0xf);
         v = is_float ? kNf4Lut[u] * s : (float)(u - 8 - (zbuf ? (int8_t)zbuf[ci] : 0)) * s;

@@ -399,7 +399,7 @@ def btla_quantize(w_kn, g, nbits=4, asym=False, impl="oracle"):
         lib().orc_btla_quantize_rowblock(_p(w), _p(q), C.c_int(k), C.c_int(n), C.c_int(n), C.c_int(n), _p(sc),
                                          _p(zp) if asym else None, C.c_int(g), C.c_int(nbits))
     else:
-        qt = {4: BTLA_S4_CLIP, 8: BTLA_S8}[nbits]
+        qt = nbits | (1 << 8)  # S{n}_CLIP / S8 = EleBits | TypeInt (bestla.h:38-87)
         ref_btla().ref_btla_quantize_f32_sign_int_rowblock(_p(w), _p(q), C.c_int(k), C.c_int(n), C.c_int(n), C.c_int(n),
                                                            _p(sc), _p(zp) if asym else None, C.c_int(g), C.c_uint32(qt))
     return q, sc, zp

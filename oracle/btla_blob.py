@@ -10,6 +10,7 @@ Follows /root/reference/bestla/bestla:
   bestla_prologue_b.h:455-470 + kernel_ref.h:2132-2141  reduceWeight / row_reduce_sum
   bestla_prologue_b.h:337-356  setShuffleIndices
   bestla_gemm.h:83-125      CoreAttr id encoding
+  bestla_storage.h:724-745 + bestla_prologue_b.h:512-564 + kernel_ref.h:178-345   2/3/5/6/7-bit codes as bit planes
 """
 from __future__ import annotations
 
@@ -54,6 +55,41 @@ def interleave(q_kn: np.ndarray, ntile: int, packrow: int, kpad: int, npad: int)
 def compress_s4(flat: np.ndarray, bias: int = 8) -> np.ndarray:
     u = ((flat.astype(np.int16) + bias) & 0xF).astype(np.uint8)
     return (u[0::2] | (u[1::2] << 4)).astype(np.uint8)
+
+
+# plane widths per code width, low bits first (compress_{2,3,5,6,7}bit)
+PLANES = {2: (2,), 3: (2, 1), 5: (4, 1), 6: (4, 2), 7: (4, 2, 1)}
+
+
+def compress_planes(flat: np.ndarray, bits: int) -> np.ndarray:
+    """flat int8 [E] (values q) -> the plane bytes: u = q + 2^(bits-1); plane i holds its slice of u for every element, element e at
+    bit (e % (8/w)) * w of byte e // (8/w); planes laid one after the other (4-bit, 2-bit, 1-bit)."""
+    u = (flat.astype(np.int16) + (1 << (bits - 1))).astype(np.uint8)
+    out, sh = [], 0
+    for w in PLANES[bits]:
+        per = 8 // w
+        part = ((u >> sh) & ((1 << w) - 1)).reshape(-1, per)
+        byte = np.zeros(part.shape[0], np.uint8)
+        for j in range(per):
+            byte |= (part[:, j] << (j * w)).astype(np.uint8)
+        out.append(byte)
+        sh += w
+    return np.concatenate(out)
+
+
+def decompress_planes(raw: np.ndarray, bits: int, elt: int) -> np.ndarray:
+    """inverse of compress_planes: int32 [elt] values q."""
+    u = np.zeros(elt, np.int32)
+    at, sh = 0, 0
+    for w in PLANES[bits]:
+        per = 8 // w
+        nbytes = (elt * w + 7) // 8
+        plane = raw[at:at + nbytes].astype(np.int32)
+        e = np.arange(elt)
+        u |= ((plane[e // per] >> ((e % per) * w)) & ((1 << w) - 1)) << sh
+        at += nbytes
+        sh += w
+    return u - (1 << (bits - 1))
 
 
 def _aligned(buf: bytearray, base_addr: int, data: bytes) -> None:
@@ -209,6 +245,8 @@ def unpack(blob) -> np.ndarray:
     raw = np.frombuffer(h["qbuf"], np.uint8)
     if (h["dtype"] & 0xFF) == 8:
         flat = raw.view(np.int8).astype(np.int32)
+    elif (h["dtype"] & 0xFF) in PLANES and h["prologue"] == 1:
+        flat = decompress_planes(raw, h["dtype"] & 0xFF, npad * kpad)
     else:
         flat = np.empty(raw.size * 2, np.int32)
         flat[0::2] = raw & 0xF

@@ -61,6 +61,30 @@ REF_API int ref_btla_decompress_s4_s8(const uint8_t* src, int8_t* dst, size_t el
                                             nullptr, 0);
 }
 
+/* kernel_ref.h:178-345 compress_{7,6,5,3,2}bit with the plane pointers placed as compressBit{7,6,5,3,2}Weight do
+ * (bestla_prologue_b.h:512-564: bit1_offset / bit2_offset = N * K elements).  dst must hold the sum of the planes. */
+REF_API int ref_btla_compress_bits(int bits, const int8_t* src, uint8_t* dst, size_t elt) {
+  int8_t* d = reinterpret_cast<int8_t*>(dst);
+  switch (bits) {
+    case 7: {
+      auto b4 = reinterpret_cast<utils::bit4x2*>(d);
+      auto b2 = reinterpret_cast<utils::bit2x4*>(b4 + elt / 2);
+      auto b1 = reinterpret_cast<utils::bit1x8*>(b2 + elt / 4);
+      return (int)kernel::ref::compress_7bit(src, b4, b2, b1, elt);
+    }
+    case 6:
+      return (int)kernel::ref::compress_6bit(src, reinterpret_cast<utils::bit4x2*>(d), reinterpret_cast<utils::bit2x4*>(d + elt / 2), elt);
+    case 5:
+      return (int)kernel::ref::compress_5bit(src, reinterpret_cast<utils::bit4x2*>(d), reinterpret_cast<utils::bit1x8*>(d + elt / 2), elt);
+    case 3:
+      return (int)kernel::ref::compress_3bit(src, reinterpret_cast<utils::bit2x4*>(d), reinterpret_cast<utils::bit1x8*>(d + elt / 4), elt);
+    case 2:
+      return (int)kernel::ref::compress_2bit(src, reinterpret_cast<utils::bit2x4*>(d), elt);
+    default:
+      return -1;
+  }
+}
+
 /* bestla_utils.h:116-153 bf16 RNE, :503-526 cast<> rounding */
 REF_API uint16_t ref_btla_f32_to_bf16(float v) { return utils::bf16(v).x; }
 REF_API float ref_btla_bf16_to_f32(uint16_t x) { return utils::bf16::from_bin(x).tofloat(); }
