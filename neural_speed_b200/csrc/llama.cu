@@ -369,6 +369,180 @@ __global__ void __launch_bounds__(kAW * 32) attn_fast_kernel(const float* __rest
   }
 }
 
+// ---- prompt attention on the tensor cores ------------------------------------------------------------------------------------
+// The ggml attention of the reference for N > 1 new tokens (llama.cpp:286-302: KQ = mul_mat(K, Q) -> scale -> diag_mask_inf ->
+// soft_max -> mul_mat(V, KQ_soft_max); ne_compute_forward_mul_mat_f16_f32 rounds Q and the probabilities to fp16 and sums the
+// fp16 x fp16 products in fp32, ne_layers.c:6943-7083; soft_max rounds (s - max) and exp() to fp16, :8887-8954) as a causal
+// two-pass kernel on mma.sync.m16n8k16 f16 -> f32 (the same operand types and accumulator as the reference's dot products):
+//   pass A  S = Q K^T tile by tile, row maxima (the reference's soft_max uses the GLOBAL row maximum, not a running one)
+//   pass B  S again, e = fp16(exp(fp16(s - max))), l += e, O += e V (e is an exact fp16 value: the products are exact), out = O / l
+// (difference to the reference: it rounds e / l to fp16 before the V product; here the division happens once, in fp32, after it).
+// CTA = 64 query rows of one head (4 warps x 16 rows); K / V tiles of 64 keys staged in shared memory with 16-byte padded rows
+// (conflict-free 32-bit B-fragment loads for K, ldmatrix.trans for V); every q-tile of a head re-reads that head's K / V through L2.
+// Bound: tensor pipe / shared-memory bandwidth (K and V of one head are 0.5 MB at 2048 positions -- L2 resident).
+constexpr int kAttnMmaRows = 64, kAttnMmaKeys = 64;
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int HD>
+__global__ void __launch_bounds__(128) attn_mma_kernel(const float* __restrict__ q, int ldq, const __half* __restrict__ kc,
+                                                       const __half* __restrict__ vc, const int* __restrict__ state, float* __restrict__ out,
+                                                       int ldo, int n_head, int n_head_kv, int n_ctx, int m, float scale) {
+  constexpr int LD = HD + 8;  // halves per shared-memory row: 16 bytes of padding rotate the banks by 4 words per row
+  constexpr int KS = HD / 16, NT = HD / 8;
+  __shared__ __align__(16) __half Ks[kAttnMmaKeys * LD];
+  __shared__ __align__(16) __half Vs[kAttnMmaKeys * LD];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int h = blockIdx.y, hk = h / (n_head / n_head_kv);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const int pos0 = state[1];
+  const int q0 = blockIdx.x * kAttnMmaRows;
+  const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;  // this thread's two query rows (token indices of the batch)
+  const int total = min(pos0 + m, n_ctx);                // keys that exist
+  const __half* kh = kc + (size_t)hk * n_ctx * HD;
+  const __half* vh = vc + (size_t)hk * n_ctx * HD;
+
+  // Q A-fragments, rounded to fp16 as the reference's mul_mat does with src1 (rows past the batch: zeros)
+  uint32_t qa[KS][4];
+  {
+    const float* q0p = q + (size_t)row0 * ldq + (size_t)h * HD;
+    const float* q1p = q + (size_t)row1 * ldq + (size_t)h * HD;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int c = ks * 16 + 2 * t4;
+      const float2 a0 = row0 < m ? *reinterpret_cast<const float2*>(q0p + c) : make_float2(0.f, 0.f);
+      const float2 a1 = row1 < m ? *reinterpret_cast<const float2*>(q1p + c) : make_float2(0.f, 0.f);
+      const float2 a2 = row0 < m ? *reinterpret_cast<const float2*>(q0p + c + 8) : make_float2(0.f, 0.f);
+      const float2 a3 = row1 < m ? *reinterpret_cast<const float2*>(q1p + c + 8) : make_float2(0.f, 0.f);
+      qa[ks][0] = pack_h2(a0.x, a0.y);
+      qa[ks][1] = pack_h2(a1.x, a1.y);
+      qa[ks][2] = pack_h2(a2.x, a2.y);
+      qa[ks][3] = pack_h2(a3.x, a3.y);
+    }
+  }
+  const int last_row = min(q0 + kAttnMmaRows, m) - 1;
+  const int nkt = min(pos0 + last_row, total - 1) / kAttnMmaKeys + 1;  // key tiles this CTA needs
+  const int warp_last_key = pos0 + q0 + warp * 16 + 15;                // beyond it every key is masked for the whole warp
+
+  auto load_tile = [&](const __half* base, __half* dst, int key0) {
+    constexpr int C16 = HD / 8;  // 16-byte chunks per row
+#pragma unroll
+    for (int i = 0; i < kAttnMmaKeys * C16 / 128; ++i) {
+      const int idx = i * 128 + (int)threadIdx.x;
+      const int r = idx / C16, c = idx % C16;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (key0 + r < total) v = *reinterpret_cast<const uint4*>(base + (size_t)(key0 + r) * HD + c * 8);
+      *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+    }
+  };
+  auto scores = [&](float (&s)[8][4]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[j][c] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __half* kr = Ks + (j * 8 + g) * LD + ks * 16 + 2 * t4;
+        mma_f16_16816(s[j], qa[ks], *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
+      }
+  };
+
+  // ---- pass A: row maxima of the masked, scaled scores
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  for (int kt = 0; kt < nkt; ++kt) {
+    __syncthreads();
+    load_tile(kh, Ks, kt * kAttnMmaKeys);
+    __syncthreads();
+    if (kt * kAttnMmaKeys > warp_last_key) continue;
+    float s[8][4];
+    scores(s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int key = kt * kAttnMmaKeys + j * 8 + 2 * t4 + (c & 1);
+        const int row = (c < 2) ? row0 : row1;
+        if (key <= pos0 + row && key < total) {
+          if (c < 2) mx0 = fmaxf(mx0, s[j][c] * scale);
+          else mx1 = fmaxf(mx1, s[j][c] * scale);
+        }
+      }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  if (row0 >= m) mx0 = 0.f;  // rows past the batch: nothing valid, nothing stored
+  if (row1 >= m) mx1 = 0.f;
+
+  // ---- pass B: e = fp16(exp(fp16(s - max))), l = sum e, O = sum e V
+  float o[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[n][c] = 0.f;
+  float l0 = 0.f, l1 = 0.f;
+  for (int kt = 0; kt < nkt; ++kt) {
+    __syncthreads();
+    load_tile(kh, Ks, kt * kAttnMmaKeys);
+    load_tile(vh, Vs, kt * kAttnMmaKeys);
+    __syncthreads();
+    if (kt * kAttnMmaKeys > warp_last_key) continue;
+    float s[8][4];
+    scores(s);
+    uint32_t pe[8][2];  // per 8-key tile: (row0: keys 2t4, 2t4+1), (row1: same keys) as fp16 pairs
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float e[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int key = kt * kAttnMmaKeys + j * 8 + 2 * t4 + (c & 1);
+        const int row = (c < 2) ? row0 : row1;
+        const bool valid = key <= pos0 + row && key < total && row < m;
+        const float a = __half2float(__float2half_rn(s[j][c] * scale - (c < 2 ? mx0 : mx1)));
+        e[c] = valid ? __half2float(__float2half_rn(expf(a))) : 0.f;  // table_exp_f16 (ne_layers.c:8933-8937)
+      }
+      l0 += e[0] + e[1];
+      l1 += e[2] + e[3];
+      pe[j][0] = pack_h2(e[0], e[1]);
+      pe[j][1] = pack_h2(e[2], e[3]);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step: P as the A operand straight from the score accumulators
+      const uint32_t pa[4] = {pe[2 * kk][0], pe[2 * kk][1], pe[2 * kk + 1][0], pe[2 * kk + 1][1]};
+      const __half* vrow = Vs + (kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + 8 * (lane >> 4);
+#pragma unroll
+      for (int n2 = 0; n2 < NT / 2; ++n2) {
+        uint32_t b0, b1, b2, b3;
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(vrow + n2 * 16);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+        mma_f16_16816(o[2 * n2], pa, b0, b1);
+        mma_f16_16816(o[2 * n2 + 1], pa, b2, b3);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const int d = n * 8 + 2 * t4;
+    if (row0 < m) *reinterpret_cast<float2*>(out + (size_t)row0 * ldo + (size_t)h * HD + d) = make_float2(o[n][0] * i0, o[n][1] * i0);
+    if (row1 < m) *reinterpret_cast<float2*>(out + (size_t)row1 * ldo + (size_t)h * HD + d) = make_float2(o[n][2] * i1, o[n][3] * i1);
+  }
+}
+
 // greedy pick: index of the maximum, lowest index on ties (model_utils.cpp:2963-2985); also advances the device-side
 // position.  kArgmaxBlocks CTAs scan slices (all loads in flight at once); the last CTA to finish (ticket) merges the
 // partial results.  state[3] = pick; when `advance`: state[0] = pick, state[1] += n_tokens, record[state[2]++] = pick.
@@ -749,7 +923,14 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
                                 E, (const float*)k, kvd, (const float*)v, kvd, kc, vc, (const int*)c->state, hp.n_head, hp.n_head_kv, hd,
                                 hp.n_ctx, theta_scale, freq_scale));
       ns_count_launch();
-      if (fast) {
+      // prompts: causal attention on the tensor cores (64 query rows per CTA); a handful of rows stay on the decode-shaped kernel
+      const bool mma = fast && m >= 8 && !(E % 2) && !getenv("NS_ATTN_SCALAR");
+      if (mma) {
+        auto kern = hd == 128 ? attn_mma_kernel<128> : attn_mma_kernel<64>;
+        NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)((m + kAttnMmaRows - 1) / kAttnMmaRows), (unsigned)hp.n_head), dim3(128), 0, st,
+                                  (const float*)q, E, (const __half*)kc, (const __half*)vc, (const int*)c->state, c->attn, E, hp.n_head,
+                                  hp.n_head_kv, hp.n_ctx, m, attn_scale));
+      } else if (fast) {
         auto kern = hd == 128 ? attn_fast_kernel<128, false> : attn_fast_kernel<64, false>;
         NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)hp.n_head, (unsigned)m), dim3(kAW * 32), fast_smem, st, (const float*)q, E,
                                   (const float*)k, kvd, (const float*)v, kvd, kc, vc, (const int*)c->state, c->attn, E, hp.n_head,

@@ -227,3 +227,30 @@ def test_llama2_7b_shaped_greedy_decode_matches_the_reference_engine():
     for r in (ref, ref_jig):
         if hasattr(r, "close"):
             r.close()
+
+
+@pytest.mark.parametrize("n_head,n_head_kv", [(4, 4), (2, 2), (4, 2)])
+def test_tensor_core_prompt_attention_matches_the_scalar_kernel_and_the_cpu_graph(n_head, n_head_kv, monkeypatch):
+    """Prompts of >= 8 tokens run the causal attention on mma.sync (attn_mma_kernel: 64 query rows per CTA, K/V tiles of 64 keys):
+    several q tiles, several key tiles, a ragged last tile and a non-zero n_past (chunked prompt).  Against the decode-shaped
+    scalar kernel on the same engine (NS_ATTN_SCALAR=1; exact-prefill matmuls are deterministic, so only the attention differs)
+    and against the CPU graph."""
+    hp, orc, eng = _build(n_head_kv, seed=21, n_ctx=200, n_head=n_head)
+    eng.set_exact_prefill(True)
+    rng = np.random.default_rng(8)
+    p1 = [int(t) for t in rng.integers(3, hp["n_vocab"], 37)]
+    p2 = [int(t) for t in rng.integers(3, hp["n_vocab"], 141)]
+    a1 = eng.eval(p1, 0)[0]
+    a2 = eng.eval(p2, len(p1))[0]
+    a3 = eng.eval([11], len(p1) + len(p2))[0]
+    monkeypatch.setenv("NS_ATTN_SCALAR", "1")
+    b1 = eng.eval(p1, 0)[0]
+    b2 = eng.eval(p2, len(p1))[0]
+    b3 = eng.eval([11], len(p1) + len(p2))[0]
+    monkeypatch.delenv("NS_ATTN_SCALAR")
+    for a, b in ((a1, b1), (a2, b2), (a3, b3)):
+        assert np.isfinite(a).all()
+        assert float(np.abs(a - b).max()) <= 2e-3 * max(1.0, float(np.abs(b).max()))
+    want = orc.eval(p1, 0)
+    _check_logits(a1, want, tol=2.5e-2)
+    eng.close()
