@@ -233,7 +233,7 @@ REF_API void ref_ne_mul_mat_id(const void* const* experts, const size_t* expert_
   for (int e = 0; e < n_as; ++e) bytes += expert_bytes[e] + 4096;
   struct ne_context* ctx = ref_ne_ctx(bytes);
   struct ne_tensor* as[8];
-  if (n_as > 8) ref_ne_die("ref_ne_mul_mat_id: n_as > 8");
+  if (n_as > 8) { fprintf(stderr, "ref_ne_mul_mat_id: n_as > 8\n"); abort(); }
   for (int e = 0; e < n_as; ++e) {
     as[e] = wtype == NE_TYPE_BTLA ? ne_new_tensor_2d(ctx, NE_TYPE_BTLA, k, n, expert_bytes[e], NE_BACKEND_CPU)
                                   : ne_new_tensor_2d(ctx, (enum ne_type)wtype, k, n, NE_SIZE_CALC, NE_BACKEND_CPU);
@@ -260,7 +260,7 @@ REF_API void ref_ne_ffn_id_silu(const void* const* blobs, const size_t* blob_byt
   for (int e = 0; e < 3 * n_as; ++e) bytes += blob_bytes[e] + 4096;
   struct ne_context* ctx = ref_ne_ctx(bytes);
   struct ne_tensor *gate[8], *down[8], *up[8];
-  if (n_as > 8) ref_ne_die("ref_ne_ffn_id_silu: n_as > 8");
+  if (n_as > 8) { fprintf(stderr, "ref_ne_ffn_id_silu: n_as > 8\n"); abort(); }
   for (int e = 0; e < n_as; ++e) {
     gate[e] = ne_new_tensor_2d(ctx, NE_TYPE_BTLA, k, fmid, blob_bytes[e], NE_BACKEND_CPU);
     down[e] = ne_new_tensor_2d(ctx, NE_TYPE_BTLA, fmid, n_out, blob_bytes[n_as + e], NE_BACKEND_CPU);
