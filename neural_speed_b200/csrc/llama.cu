@@ -369,6 +369,237 @@ __global__ void __launch_bounds__(kAW * 32) attn_fast_kernel(const float* __rest
   }
 }
 
+// ---- decode attention: K / V of the head staged by TMA, split over the context ---------------------------------------------------
+// One new token (llama.cpp:286-302 with N = 1; RoPE of q and of the new k row and the KV append fused in, as attn_fast_kernel<FUSE>).
+// grid (n_head, ceil(n_ctx / 256)); CTA (h, s) owns cached positions [256 s, 256 s + 256) of head h and returns at once when the
+// sequence has not reached its range (the position lives in device memory: one CUDA graph serves every position).  The rows of a
+// head are contiguous in the cache ([kv head][n_ctx][hd] fp16), so the CTA's whole K and V ranges arrive as TWO cp.async.bulk copies
+// (<= 64 KB each) on one mbarrier: a single global-memory latency per launch instead of a chain of dependent row loads -- the old
+// kernel spent 2-3 round trips per pass at 100-200 positions.  Scores, soft_max and P.V then run out of shared memory.
+// One active range (<= 256 positions): exactly the reference arithmetic (global maximum, e = fp16(exp(fp16(s - max))),
+// p = fp16(e / sum), fp32 sums).  Several: every CTA leaves {max, sum e, sum e V} of its range, the last one to arrive (ticket per
+// head) merges them with exp(max_s - max) weights -- same values up to the fp16 rounding of p (5e-4 relative).
+// Bound: latency at short contexts; HBM (2 x len x hd x 2 B per kv head) at long ones, spread over n_head x ceil(len / 256) CTAs.
+constexpr int kSplitKeys = 256;
+constexpr int kDW = 16;  // warps per CTA
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int HD>
+static constexpr size_t attn_decode_smem() {
+  return (size_t)2 * kSplitKeys * HD * 2 + (size_t)(3 + kDW) * HD * 4 + (size_t)(kSplitKeys + 8) * 4 + 16;
+}
+template <int HD>
+__global__ void __launch_bounds__(kDW * 32) attn_decode_kernel(const float* __restrict__ q, const float* __restrict__ knew,
+                                                            const float* __restrict__ vnew, __half* __restrict__ kc, __half* __restrict__ vc,
+                                                            const int* __restrict__ state, float* __restrict__ out, float* __restrict__ part_ws,
+                                                            unsigned* __restrict__ tickets, int n_head, int n_head_kv, int n_ctx, int nsplit,
+                                                            float scale, float theta_scale, float freq_scale) {
+  constexpr int EPL = HD / 32;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __half* Kt = reinterpret_cast<__half*>(smraw);  // [kSplitKeys][HD]
+  __half* Vt = Kt + kSplitKeys * HD;
+  float* sq = reinterpret_cast<float*>(Vt + kSplitKeys * HD);
+  float* sk = sq + HD;
+  float* sv = sk + HD;
+  float* part = sv + HD;         // [kDW][HD]
+  float* sc = part + kDW * HD;   // [kSplitKeys + 1]: scores of the range (+ the new row)
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sc + kSplitKeys + 8);
+  __shared__ float red[kDW];
+  __shared__ float bcast;
+  __shared__ int last_flag;
+  pdl_launch_dependents();
+  const uint32_t bar_a = smem_addr(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_wait();
+  const int h = blockIdx.x, split = blockIdx.y;
+  const int group = n_head / n_head_kv, hk = h / group;
+  const int pos = state[1];
+  const int len = min(pos + 1, n_ctx);
+  const int nact = (len + kSplitKeys - 1) / kSplitKeys;
+  if (split >= nact) return;  // the sequence has not reached this range
+  const int i0 = split * kSplitKeys, i1 = min(len, i0 + kSplitKeys);
+  const bool has_new = (i1 == len) && pos < n_ctx;  // the token being evaluated sits in this range: its k / v come from registers
+  const int ncache = (has_new ? i1 - 1 : i1) - i0;  // rows read from the cache
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __half* kh = kc + (size_t)hk * n_ctx * HD;
+  __half* vh = vc + (size_t)hk * n_ctx * HD;
+  if (threadIdx.x == 0 && ncache > 0) {
+    const uint32_t bytes = (uint32_t)ncache * HD * 2;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2 * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(Kt)),
+                 "l"(kh + (size_t)i0 * HD), "r"(bytes), "r"(bar_a)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(Vt)),
+                 "l"(vh + (size_t)i0 * HD), "r"(bytes), "r"(bar_a)
+                 : "memory");
+  }
+  // RoPE of this head's q (every range needs it) and of the new k row; KV append by one CTA per kv head -- while the copies fly
+  if (threadIdx.x < HD / 2) {
+    const int i = threadIdx.x;
+    float theta = (float)pos;
+    for (int j = 0; j < i; ++j) theta *= theta_scale;  // ne_layers.c:9385: same sequence of roundings
+    theta *= freq_scale;
+    float sn, cs;
+    sincosf(theta, &sn, &cs);
+    const float* qr = q + (size_t)h * HD;
+    const float q0 = qr[2 * i], q1 = qr[2 * i + 1];
+    sq[2 * i] = __half2float(__float2half_rn(q0 * cs - q1 * sn));
+    sq[2 * i + 1] = __half2float(__float2half_rn(q0 * sn + q1 * cs));
+    if (has_new) {
+      const float* kr = knew + (size_t)hk * HD;
+      const float k0 = kr[2 * i], k1 = kr[2 * i + 1];
+      const __half r0 = __float2half_rn(k0 * cs - k1 * sn), r1 = __float2half_rn(k0 * sn + k1 * cs);
+      sk[2 * i] = __half2float(r0);
+      sk[2 * i + 1] = __half2float(r1);
+      const float* vr = vnew + (size_t)hk * HD;
+      const __half w0 = __float2half_rn(vr[2 * i]), w1 = __float2half_rn(vr[2 * i + 1]);
+      sv[2 * i] = __half2float(w0);
+      sv[2 * i + 1] = __half2float(w1);
+      if (h % group == 0) {
+        *reinterpret_cast<__half2*>(kh + (size_t)pos * HD + 2 * i) = __halves2half2(r0, r1);
+        *reinterpret_cast<__half2*>(vh + (size_t)pos * HD + 2 * i) = __halves2half2(w0, w1);
+      }
+    }
+  }
+  __syncthreads();
+  float ql[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) ql[e] = sq[lane * EPL + e];
+  if (ncache > 0) {
+    uint32_t ok;
+    do {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(ok)
+          : "r"(bar_a), "r"(0)
+          : "memory");
+    } while (!ok);
+  }
+  auto row = [&](const __half* base, int r, float* dst) {
+    if (EPL == 4) {
+      const uint2 u = *reinterpret_cast<const uint2*>(base + (size_t)r * HD + lane * 4);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      dst[0] = a.x, dst[1] = a.y, dst[2] = b.x, dst[3] = b.y;
+    } else {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(base + (size_t)r * HD + lane * 2));
+      dst[0] = a.x, dst[1] = a.y;
+    }
+  };
+  // pass 1: scores of the range
+  for (int r = warp; r < ncache; r += kDW) {
+    float kr[EPL];
+    row(Kt, r, kr);
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc = fmaf(ql[e], kr[e], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) sc[r] = acc * scale;
+  }
+  if (has_new && warp == kDW - 1) {
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc = fmaf(ql[e], sk[lane * EPL + e], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) sc[ncache] = acc * scale;
+  }
+  __syncthreads();
+  const int nloc = ncache + (has_new ? 1 : 0);
+  float lmax = -INFINITY;
+  for (int i = threadIdx.x; i < nloc; i += blockDim.x) lmax = fmaxf(lmax, sc[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if (lane == 0) red[warp] = lmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < kDW; ++i) m = fmaxf(m, red[i]);
+    bcast = m;
+  }
+  __syncthreads();
+  const float mx = bcast;
+  float lsum = 0.f;
+  for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
+    const float a = __half2float(__float2half_rn(sc[i] - mx));
+    const float e = __half2float(__float2half_rn(expf(a)));  // table_exp_f16 (ne_layers.c:8933-8937)
+    sc[i] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  __syncthreads();
+  if (lane == 0) red[warp] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s2 = 0.f;
+    for (int i = 0; i < kDW; ++i) s2 += red[i];
+    bcast = s2;
+  }
+  __syncthreads();
+  const float lrange = bcast;
+  const bool single = nact == 1;
+  const float inv = 1.f / lrange;
+  // pass 2: sum p V over the range; warps own rows, lanes own EPL output elements
+  float acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  for (int r = warp; r < ncache; r += kDW) {
+    float vr[EPL];
+    row(Vt, r, vr);
+    const float p = single ? __half2float(__float2half_rn(sc[r] * inv)) : sc[r];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, vr[e], acc[e]);
+  }
+  if (has_new && warp == kDW - 1) {
+    const float p = single ? __half2float(__float2half_rn(sc[ncache] * inv)) : sc[ncache];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, sv[lane * EPL + e], acc[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) part[warp * HD + lane * EPL + e] = acc[e];
+  __syncthreads();
+  float mine = 0.f;
+  if (threadIdx.x < HD) {
+#pragma unroll
+    for (int w = 0; w < kDW; ++w) mine += part[w * HD + threadIdx.x];
+  }
+  if (single) {
+    if (threadIdx.x < HD) out[(size_t)h * HD + threadIdx.x] = mine;
+    return;
+  }
+  // several ranges: leave {sum e V, max, sum e}; the last CTA of the head merges
+  float* mypart = part_ws + ((size_t)h * nsplit + split) * (HD + 2);
+  if (threadIdx.x < HD) mypart[threadIdx.x] = mine;
+  if (threadIdx.x == 0) {
+    mypart[HD] = mx;
+    mypart[HD + 1] = lrange;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_flag = (atomicAdd(&tickets[h], 1u) == (unsigned)(nact - 1)) ? 1 : 0;
+  __syncthreads();
+  if (!last_flag) return;
+  __threadfence();
+  if (threadIdx.x < HD) {
+    const float* base = part_ws + (size_t)h * nsplit * (HD + 2);
+    float gm = -INFINITY;
+    for (int s2 = 0; s2 < nact; ++s2) gm = fmaxf(gm, __ldcg(base + (size_t)s2 * (HD + 2) + HD));
+    float num = 0.f, den = 0.f;
+    for (int s2 = 0; s2 < nact; ++s2) {
+      const float w = expf(__ldcg(base + (size_t)s2 * (HD + 2) + HD) - gm);
+      num = fmaf(w, __ldcg(base + (size_t)s2 * (HD + 2) + threadIdx.x), num);
+      den = fmaf(w, __ldcg(base + (size_t)s2 * (HD + 2) + HD + 1), den);
+    }
+    out[(size_t)h * HD + threadIdx.x] = num / den;
+  }
+  if (threadIdx.x == 0) tickets[h] = 0u;  // ready for the next launch (graph replay)
+}
+
 // ---- prompt attention on the tensor cores ------------------------------------------------------------------------------------
 // The ggml attention of the reference for N > 1 new tokens (llama.cpp:286-302: KQ = mul_mat(K, Q) -> scale -> diag_mask_inf ->
 // soft_max -> mul_mat(V, KQ_soft_max); ne_compute_forward_mul_mat_f16_f32 rounds Q and the probabilities to fp16 and sums the
@@ -623,6 +854,10 @@ struct ns_llama {
   unsigned* am_ticket = nullptr;
   int m_cap = 0;
   size_t attn_attr = 0, fast_attr = 0;  // dynamic shared memory already granted to the attention kernels
+  int dec_attr = 0;                     // attn_decode_kernel attribute set for this context's device
+  float* attn_part = nullptr;           // split-context decode attention: [n_head][nsplit][hd + 2] partials
+  unsigned* attn_tickets = nullptr;     // [n_head]
+  int attn_nsplit = 0;
   int exact_prefill = 0;               // ns_llama_set_exact_prefill
   float *x = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *tmp = nullptr, *logits = nullptr;
   void* ws = nullptr;
@@ -689,7 +924,12 @@ extern "C" ns_llama* ns_llama_create(const ns_llama_hparams* hp, void* queue) {
   c->am_idx = (int*)dev_alloc(c, 64 * sizeof(int));
   c->am_ticket = (unsigned*)dev_alloc(c, sizeof(unsigned));
   if (c->am_ticket) cudaMemsetAsync(c->am_ticket, 0, sizeof(unsigned), c->st);
+  c->attn_nsplit = (hp->n_ctx + kSplitKeys - 1) / kSplitKeys;
+  c->attn_part = (float*)dev_alloc(c, (size_t)hp->n_head * c->attn_nsplit * (hd + 2) * sizeof(float));
+  c->attn_tickets = (unsigned*)dev_alloc(c, (size_t)hp->n_head * sizeof(unsigned));
+  if (c->attn_tickets) cudaMemsetAsync(c->attn_tickets, 0, (size_t)hp->n_head * sizeof(unsigned), c->st);
   if (!c->kc || !c->vc || !c->state || !c->tokens || !c->record || !c->logits || !c->am_val || !c->am_idx || !c->am_ticket ||
+      !c->attn_part || !c->attn_tickets ||
       cudaMallocHost((void**)&c->h_state, 4 * sizeof(int)) != cudaSuccess ||
       cudaMallocHost((void**)&c->h_logits, (size_t)hp->n_vocab * 4) != cudaSuccess) {
     ns_llama_free(c);
@@ -912,7 +1152,20 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
       }
     }
     const bool fast = (hd == 128 || hd == 64);
-    if (fast && m == 1) {  // rope + KV append + attention in one launch
+    if (fast && m == 1 && c->attn_nsplit <= 1024 && !getenv("NS_ATTN_OLD_DECODE")) {
+      // rope + KV append + attention in one launch, K / V staged by TMA, the context split over CTAs
+      const size_t dsm = hd == 128 ? attn_decode_smem<128>() : attn_decode_smem<64>();
+      if (!c->dec_attr) {
+        NS_CUDA_TRY(cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_decode_smem<128>()));
+        NS_CUDA_TRY(cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_decode_smem<64>()));
+        c->dec_attr = 1;
+      }
+      auto kern = hd == 128 ? attn_decode_kernel<128> : attn_decode_kernel<64>;
+      NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)hp.n_head, (unsigned)c->attn_nsplit), dim3(kDW * 32), dsm, st, (const float*)q,
+                                (const float*)k, (const float*)v, kc, vc, (const int*)c->state, c->attn, c->attn_part, c->attn_tickets,
+                                hp.n_head, hp.n_head_kv, hp.n_ctx, c->attn_nsplit, attn_scale, theta_scale, freq_scale));
+      ns_count_launch();
+    } else if (fast && m == 1) {  // the same fused launch with dependent row loads (one CTA per head)
       auto kern = hd == 128 ? attn_fast_kernel<128, true> : attn_fast_kernel<64, true>;
       NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)hp.n_head, 1u), dim3(kAW * 32), fast_smem, st, (const float*)q, E, (const float*)k, kvd,
                                 (const float*)v, kvd, kc, vc, (const int*)c->state, c->attn, E, hp.n_head, hp.n_head_kv, hp.n_ctx,
