@@ -262,38 +262,6 @@ NS_API ns_graph* ns_graph_end(void* queue);
 NS_API int ns_graph_launch(ns_graph* g, void* queue);
 NS_API void ns_graph_free(ns_graph* g);
 
-/* Persistent multi-op decode kernel: the matmul nodes of one token (M <= 4 rows) executed by ONE cooperative launch --
- * replaces the per-node walk of ne_graph_compute (core/ne_layers.c:11915) over the llama graph
- * (models/llama/llama.cpp:217-231,586,612-618,718).  Each op = one ne_mul_mat / ne_mul_qkv / ne_ffn_silu(first half) node:
- * fp32 device input -> (activation quantisation fused, same arithmetic as the reference's NE_TASK_INIT) -> GEMV ->
- * epilogue.  mode: 0 plain, 1 concat (outputs of the 1..3 weights concatenated along n in one [m][ldo] row),
- * 2 gate/up + SiLU*mul.  barrier_before != 0: the op's input is produced by the previous op (grid-wide dependency).
- * All weights of a program share format / scale type / compute type (4-bit integer weights, integer activations). */
-typedef struct ns_program ns_program;
-NS_API ns_program* ns_program_create(int m);
-NS_API int ns_program_add_matmul(ns_program* p, const ns_weight* const* weights, int nw, int mode, const float* in, int lda,
-                                 float* dst, int ldo, const float* bias, int bias_bcast, const float* residual, float* aux,
-                                 int barrier_before);
-/* extended form: norm_w != NULL fuses llama.cpp:205-210's rms_norm * weight into the op's activation prologue (eps = norm_eps);
- * in_index / res_index (device ints, read when the op starts) offset the input / residual by index * stride floats, e.g. the
- * embedding row of the token picked by the previous step (llama.cpp:190 ne_get_rows); eltop = NS_ELT_* (0 default, 1 GELU). */
-NS_API int ns_program_add_matmul_ex(ns_program* p, const ns_weight* const* weights, int nw, int mode, const float* in, int lda,
-                                    float* dst, int ldo, const float* bias, int bias_bcast, const float* residual, float* aux,
-                                    int barrier_before, const float* norm_w, float norm_eps, const int* in_index,
-                                    long long in_stride, const int* res_index, long long res_stride, int eltop);
-/* flag-in-data hand-over for the op added last (see program.cu): tagged input = polled 8-byte {value, tag} words written by the
- * previous op's dst_tag -- replaces the grid barrier between the two ops */
-NS_API int ns_program_tag_last(ns_program* p, int in_tagged, void* dst_tag);
-NS_API int ns_program_finalize(ns_program* p, void* queue);
-NS_API int ns_program_run(ns_program* p, void* queue);
-/* the op list executed `iters` times inside one launch (a generation loop whose ops read device-side state) */
-NS_API int ns_program_run_n(ns_program* p, int iters, void* queue);
-NS_API size_t ns_program_algorithmic_bytes(const ns_program* p);
-NS_API void ns_program_free(ns_program* p);
-/* debug aid: per-op, per-CTA clock stamps of the last run (only when NS_PROG_TIMELINE was set at finalize) */
-NS_API int ns_program_timeline(ns_program* p, unsigned long long* host, size_t cap_words, int* nops, int* grid);
-NS_API int ns_program_unit_trace(ns_program* p, unsigned long long* host, size_t cap_words);
-
 /* The host drop-ins (bestla_*_forward, ns_mul_mat_*_host) upload and repack a host weight once and cache the device copy by
  * host address + a checksum sampled over the whole payload.  ns_host_cache_clear() releases every cached copy (call it when the
  * model context that owned the host weights is freed: the reference frees its weights with the context, model_files.h:1490-1499). */

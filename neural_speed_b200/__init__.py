@@ -54,8 +54,6 @@ EXPORTS = [
     "ns_mul_mat", "ns_mul_qkv", "ns_ffn_silu", "ns_ffn_gelu",
     "ns_mul_mat_id", "ns_ffn_id", "ns_mul_mat_id_q4_0_f32_host",
     "ns_rmsnorm_fusable", "ns_rmsnorm_mul_mat", "ns_rmsnorm_mul_qkv", "ns_rmsnorm_ffn_silu", "ns_mul_mat_q4_0_f32_host", "ns_mul_mat_q6_K_f32_host",
-    "ns_program_create", "ns_program_add_matmul", "ns_program_add_matmul_ex", "ns_program_tag_last", "ns_program_finalize", "ns_program_run",
-    "ns_program_run_n", "ns_program_algorithmic_bytes", "ns_program_free", "ns_program_timeline", "ns_program_unit_trace",
     "ns_prepare_activation", "ns_matmul_prepared", "ns_graph_begin", "ns_graph_end", "ns_graph_launch", "ns_graph_free",
     "ns_device_quantize_q4_0", "ns_device_quantize_act",
     "BTLAGemmPackBSize", "BTLAGemmQuantPackB", "BTLAGemmPackB", "BTLAGemmUnPackB", "ns_quantize_row_q4_0", "ns_split_weight_size", "ns_split_weight",
@@ -164,19 +162,6 @@ def lib() -> C.CDLL:
     L.ns_mul_mat_q4_0_f32_host.argtypes = [vp, sz, vp, vp, i, i, i]
     L.ns_prepare_activation.argtypes = [vp, vp, i, i, vp, vp]
     L.ns_matmul_prepared.argtypes = [vp, i, i, vp, vp, i, i, vp, i, vp, vp, vp]
-    L.ns_program_create.restype = vp
-    L.ns_program_create.argtypes = [i]
-    L.ns_program_add_matmul.argtypes = [vp, vp, i, i, vp, i, vp, i, vp, i, vp, vp, i]
-    L.ns_program_add_matmul_ex.argtypes = [vp, vp, i, i, vp, i, vp, i, vp, i, vp, vp, i, vp, C.c_float, vp, C.c_longlong, vp,
-                                           C.c_longlong, i]
-    L.ns_program_tag_last.argtypes = [vp, i, vp]
-    L.ns_program_finalize.argtypes = [vp, vp]
-    L.ns_program_run.argtypes = [vp, vp]
-    L.ns_program_run_n.argtypes = [vp, i, vp]
-    L.ns_program_timeline.argtypes = [vp, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    L.ns_program_algorithmic_bytes.restype = sz
-    L.ns_program_algorithmic_bytes.argtypes = [vp]
-    L.ns_program_free.argtypes = [vp]
     L.ns_graph_begin.argtypes = [vp]
     L.ns_graph_end.restype = vp
     L.ns_graph_end.argtypes = [vp]
@@ -508,51 +493,5 @@ class Llama:
     def __del__(self):
         try:
             self.close()
-        except Exception:
-            pass
-
-
-class Program:
-    """Persistent multi-op decode kernel (ns_program_*): the matmul nodes of one token in one cooperative launch."""
-
-    PLAIN, CONCAT, GATE_UP_SILU = 0, 1, 2
-
-    def __init__(self, m: int = 1):
-        self.h = C.c_void_p(lib().ns_program_create(m))
-        if not self.h:
-            raise RuntimeError("ns_program_create failed: " + last_error())
-        self._keep = []
-
-    def add(self, weights, mode, in_ptr, lda, dst_ptr, ldo, bias_ptr=None, bias_bcast=0, residual_ptr=None, aux_ptr=None,
-            barrier_before=1, norm_ptr=None, norm_eps=0.0, in_index_ptr=None, in_stride=0, res_index_ptr=None, res_stride=0,
-            eltop=0, in_tagged=False, dst_tag_ptr=None):
-        """one matmul node; norm_ptr fuses rms_norm * weight into the activation prologue, in_index_ptr / res_index_ptr
-        (device int32) offset input / residual by index * stride floats (embedding row chosen on the device)"""
-        arr = (C.c_void_p * 3)(*([w.h for w in weights] + [None] * (3 - len(weights))))
-        self._keep.append(weights)
-        opt = lambda v: C.c_void_p(v) if v else None
-        _check(lib().ns_program_add_matmul_ex(self.h, arr, len(weights), mode, C.c_void_p(in_ptr), lda, C.c_void_p(dst_ptr), ldo,
-                                              opt(bias_ptr), bias_bcast, opt(residual_ptr), opt(aux_ptr), barrier_before,
-                                              opt(norm_ptr), float(norm_eps), opt(in_index_ptr), int(in_stride),
-                                              opt(res_index_ptr), int(res_stride), int(eltop)), "ns_program_add_matmul")
-        if in_tagged or dst_tag_ptr:
-            # flag-in-data hand-over: in_ptr is the previous op's dst_tag_ptr ([m][lda] 8-byte {value, tag} words)
-            _check(lib().ns_program_tag_last(self.h, 1 if in_tagged else 0, opt(dst_tag_ptr)), "ns_program_tag_last")
-
-    def finalize(self, queue=None):
-        _check(lib().ns_program_finalize(self.h, queue), "ns_program_finalize")
-
-    def run(self, queue=None, iters=1):
-        _check(lib().ns_program_run_n(self.h, iters, queue), "ns_program_run")
-
-    @property
-    def algorithmic_bytes(self):
-        return int(lib().ns_program_algorithmic_bytes(self.h))
-
-    def __del__(self):
-        try:
-            if self.h:
-                lib().ns_program_free(self.h)
-                self.h = None
         except Exception:
             pass

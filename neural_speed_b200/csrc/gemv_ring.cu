@@ -12,8 +12,8 @@
 // 7 consumer warps + 1 producer warp per CTA, 2 CTAs per SM (~105 KB ring each = 3 slots per consumer warp for K=4096;
 // measured r01: 8 warps x 2 slots 60.0 %, 7 x 3 66.3 %, 6 x 3 64.4 % of the HBM roofline in back-to-back launches).  The producer streams BEFORE
 // griddepcontrol.wait, so under programmatic dependent launch a CTA starts filling its ring the moment it becomes
-// resident.  (Measured alternative, r01: quarter-SM CTAs that let the next kernel co-reside were slower -- 8 consumer
-// warps per SM cannot keep up with HBM; the launch-boundary cost is removed instead by the persistent multi-op kernel.)
+// resident.  (Measured alternatives: quarter-SM CTAs that let the next kernel co-reside were slower -- 8 consumer warps per SM
+// cannot keep up with HBM; one persistent cooperative kernel per token was slower too, profiles/r02_summary.md section 2.)
 // Roofline: HBM.  Algorithmic bytes per launch = sum over weights of N*K/2 + N*ceil(K/g)*(scale_bytes [+1 if asym]).
 #include "nsb.cuh"
 #include "quant_smem.cuh"
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
   if (P.act_f32 && P.norm_w) {
     // fused ne_rms_norm + ne_mul + NE_TASK_INIT: every CTA already reads the whole fp32 row, the sum of squares costs one more
     // block reduction instead of a kernel boundary (llama.cpp:205-210; arithmetic of rmsnorm_kernel, llama.cu)
-    const nsq::NormQuantIn ni{P.act_f32, 0u, P.norm_w, P.norm_eps, P.lda, P.k, P.kpad, P.comp == NS_COMP_Q8_0 ? 32 : P.group,
+    const nsq::NormQuantIn ni{P.act_f32, P.norm_w, P.norm_eps, P.lda, P.k, P.kpad, P.comp == NS_COMP_Q8_0 ? 32 : P.group,
                               R.act_row, P.meta_off, P.meta_stride};
     float* red = reinterpret_cast<float*>(smem + R.red_off);
     if (AMODE == A_U8) nsq::norm_quantise_to_smem<NS_COMP_INT8, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x);

@@ -1,4 +1,4 @@
-// norm_quant.cuh -- activation prologue of the persistent decode kernel (program.cu): optional RMSNorm, then the reference's
+// norm_quant.cuh -- activation prologue of the decode GEMV with a fused RMSNorm (gemv_ring.cu): optional RMSNorm, then the reference's
 // activation quantisation, written straight into the shared-memory image the dp4a loops read.
 //   rms_norm * weight : models/llama/llama.cpp:205-210 (ne_rms_norm + ne_mul), arithmetic of kernel_ref.h:2199-2225 as rmsnorm_kernel
 //                       (llama.cu): y = x * (1 / sqrt(sum(x^2)/n + eps)) * w
@@ -12,10 +12,7 @@
 namespace nsq {
 
 struct NormQuantIn {
-  const float* in;      // [M][lda] fp32 (global, read through L2: other SMs produced it within the same launch);
-                        // when `tag` != 0: [M][lda] 8-byte words {value, tag} -- every word is polled until it carries `tag`
-                        // (the producer wrote value and tag with ONE 64-bit store: no flag, no fence, no grid barrier)
-  unsigned tag;
+  const float* in;      // [M][lda] fp32 (global, read through L2: another SM may have just written it)
   const float* norm_w;  // [k] RMSNorm weight, or NULL: no normalisation
   float eps;
   int lda, k, kpad, group;
@@ -52,42 +49,7 @@ __device__ __forceinline__ void norm_quantise_to_smem(const NormQuantIn& P, int 
         for (int i = 0; i < 8; ++i) v[i] = (e < ngroups8 && k0 + i < P.k) ? ldcg1(row + k0 + i) : 0.f;
       }
     };
-    if (P.tag) {
-      // tagged input (always `single`: the host checks kpad <= NI * NT * 8): 8 {value, tag} words = 4 x 16-byte loads per pass,
-      // retried until all eight carry the expected tag.  Passes run one after the other: the 16 registers of raw words are
-      // transient, and only lanes that own a group in the pass take part (K = 4096: 32 threads in the second pass).
-#pragma unroll
-      for (int it = 0; it < NI; ++it) {
-        const int e = it * NT + tid;
-        const int k0 = e * 8;
-        const int nv = e < ngroups8 ? (P.k - k0 >= 8 ? 8 : (P.k - k0 > 0 ? P.k - k0 : 0)) : 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) vv[it][i] = 0.f;
-        if (nv > 0) {
-          const unsigned long long* src = reinterpret_cast<const unsigned long long*>(P.in) + (size_t)m * P.lda + k0;
-          unsigned long long w[8];
-          bool ok;
-          do {
-            ok = true;
-            if (nv == 8) {
-#pragma unroll
-              for (int i = 0; i < 8; i += 2)
-                asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(w[i]), "=l"(w[i + 1]) : "l"(src + i) : "memory");
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (i < nv) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w[i]) : "l"(src + i) : "memory");
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (i < nv) ok = ok && (unsigned)(w[i] >> 32) == P.tag;
-          } while (!ok);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < nv) vv[it][i] = __uint_as_float((unsigned)w[i]);
-        }
-      }
-    } else if (single) {
+    if (single) {
 #pragma unroll
       for (int it = 0; it < NI; ++it) load8(it * NT + tid, vv[it]);
     }
