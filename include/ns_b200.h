@@ -56,6 +56,8 @@ enum ns_ne_comp_type { NS_NE_COMP_UNDEF = 0, NS_NE_COMP_F32 = 1, NS_NE_COMP_BF16
 #define NS_BTLA_S8 (8u | (1u << 8))
 #define NS_BTLA_S4_CLIP (4u | (1u << 8))
 #define NS_BTLA_F4_NF4 (4u | (2u << 16))
+#define NS_BTLA_F4_BNB (4u | (1u << 16)) /* 4-bit float codebooks of bestla.h:82-84, kernel_ref.h:1209-1321 */
+#define NS_BTLA_F4_E2M1 4u
 /* bit-plane integer types (bestla.h:75-81, storage bestla_storage.h:724-745): held on the device in the 4-bit (2, 3 bits) or
  * 8-bit (5, 6, 7 bits) container, same integers, same scales and zero points */
 #define NS_BTLA_S2_CLIP (2u | (1u << 8))

@@ -220,6 +220,7 @@ def _np_ptr(a: np.ndarray):
 
 # ------------------------------------------------------------------------------------------------ packing API (host)
 _BITS = {"int4": BTLA_S4_CLIP, "int8": BTLA_S8, "nf4": BTLA_F4_NF4,
+         "fp4": 4, "fp4_e2m1": 4, "fp4_bnb": 4 | (1 << 16),
          "int2": 2 | (1 << 8), "int3": 3 | (1 << 8), "int5": 5 | (1 << 8), "int6": 6 | (1 << 8), "int7": 7 | (1 << 8)}
 _SCALE = {"fp32": BTLA_F32, "bf16": BTLA_BF16, "fp16": BTLA_F16}
 _COMP = {"int8": NE_COMP_INT8, "bf16": NE_COMP_BF16, "fp16": NE_COMP_F16, "fp32": NE_COMP_F32}

@@ -452,9 +452,12 @@ static int blob_to_weight_meta(const BlobView& v, ns_weight* w) {
                       v.dtype == NS_BTLA_S6_CLIP || v.dtype == NS_BTLA_S7_CLIP;
   if (v.dtype == NS_BTLA_S4_CLIP || (planes && qbits < 4)) w->wfmt = NS_W_S4;  // 2- / 3-bit codes ride in the 4-bit container
   else if (v.dtype == NS_BTLA_S8 || planes) w->wfmt = NS_W_S8;                 // 5- / 6- / 7-bit codes in the 8-bit one
-  else if (v.dtype == NS_BTLA_F4_NF4) w->wfmt = NS_W_NF4;
+  else if (v.dtype == NS_BTLA_F4_NF4 || v.dtype == NS_BTLA_F4_BNB || v.dtype == NS_BTLA_F4_E2M1) {
+    w->wfmt = NS_W_NF4;  // 4-bit codes into a 16-level table: the table is chosen per weight
+    w->f4kind = v.dtype == NS_BTLA_F4_NF4 ? NS_F4_NF4 : v.dtype == NS_BTLA_F4_BNB ? NS_F4_BNB : NS_F4_E2M1;
+  }
   else {
-    ns_set_error("blob: weight dtype 0x%x not supported (int2..int8 / nf4 are)", v.dtype);
+    ns_set_error("blob: weight dtype 0x%x not supported (int2..int8 / nf4 / fp4 are)", v.dtype);
     return NS_E_UNSUPPORTED;
   }
   if (v.sca_t == NS_BTLA_F32) w->stype = NS_S_F32;

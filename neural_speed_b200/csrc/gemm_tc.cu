@@ -35,7 +35,7 @@ constexpr int DEQ_TILE = BLOCK_N * BLOCK_K * 2;       // 16384: the same as bf16
 
 struct GemmParams {
   const uint8_t* rows;
-  int wfmt;
+  int wfmt, f4kind;
   int pitch, sc_off, zp_off, stype, asym, group, ngroups;
   int n, k, kpad, m;
   float* dst;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256 + 128 * NB, 1)
   const int num_kb = (total_kb - kb0 < P.kb_per_split) ? total_kb - kb0 : P.kb_per_split;
 
   __shared__ float nf4_lut[16];  // constant memory serialises divergent indices; shared memory broadcasts per bank
-  if (threadIdx.x >= 32 && threadIdx.x < 48) nf4_lut[threadIdx.x - 32] = NS_NF4_LUT[threadIdx.x - 32];
+  if (threadIdx.x >= 32 && threadIdx.x < 48) nf4_lut[threadIdx.x - 32] = NS_F4_LUT[P.f4kind][threadIdx.x - 32];
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int i = 0; i < SP; ++i) {
@@ -576,6 +576,7 @@ int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, i
   GemmParams P;
   P.rows = w->rows;
   P.wfmt = w->wfmt;
+  P.f4kind = w->f4kind;
   P.pitch = w->pitch;
   P.sc_off = w->sc_off;
   P.zp_off = w->zp_off;

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvParams P) {
     uint4* dstv = reinterpret_cast<uint4*>(smem);
     const int nvec = P.act_bytes >> 4;
     for (int i = threadIdx.x; i < nvec; i += kThreads) dstv[i] = src[i];
-    if (WFMT == NS_W_NF4 && threadIdx.x < 16) lut_s[threadIdx.x] = NS_NF4_LUT[threadIdx.x];
+    if (WFMT == NS_W_NF4 && threadIdx.x < 16) lut_s[threadIdx.x] = NS_F4_LUT[P.f4kind][threadIdx.x];
   }
   __syncthreads();
   const int2* meta_s = reinterpret_cast<const int2*>(smem + P.meta_off);
@@ -383,7 +383,7 @@ int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* ac
   for (int i = 1; i < nw; ++i) {
     const ns_weight* wi = ws_[i];
     if (wi->k != w0->k || wi->group != w0->group || wi->wfmt != w0->wfmt || wi->stype != w0->stype ||
-        wi->comp != w0->comp || wi->asym != w0->asym || wi->shuffle != nullptr || w0->shuffle != nullptr) {
+        wi->comp != w0->comp || wi->asym != w0->asym || wi->f4kind != w0->f4kind || wi->shuffle != nullptr || w0->shuffle != nullptr) {
       ns_set_error("fused matmul: weights differ in format (or use act-order shuffles)");
       return NS_E_UNSUPPORTED;
     }
@@ -451,6 +451,7 @@ int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* ac
   P.lda = lda;
   P.eltop = eltop;
   P.comp = w0->comp;
+  P.f4kind = w0->f4kind;
   P.norm_w = norm_w;
   P.norm_eps = norm_eps;
   if (norm_w && !(act_f32 && ns_gemv_fused_quant_ok(w0))) {

@@ -34,7 +34,9 @@ struct ns_weight {
   void* base;          // allocation owning rows/shuffle (NULL if external)
   size_t total_bytes;  // bytes of the device image
   int external;        // 1: memory supplied by caller (bestla_device_load_storage)
+  int f4kind;          // NS_W_NF4 weights: which 16-level codebook the codes index (NS_F4_NF4 / _BNB / _E2M1)
 };
+enum { NS_F4_NF4 = 0, NS_F4_BNB = 1, NS_F4_E2M1 = 2 };
 
 static inline size_t ns_round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 static inline int ns_stype_size(int stype) { return stype == NS_S_F32 ? 4 : 2; }
@@ -150,6 +152,7 @@ struct GemvParams {
   float* aux;
   int npairs;
   int eltop;  // NS_ELT_*
+  int f4kind;           // NS_W_NF4 weights: codebook
   const float* norm_w;  // fused ne_rms_norm + ne_mul in front of the activation quantiser (llama.cpp:205-210), or NULL
   float norm_eps;
 };
@@ -215,21 +218,12 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
   asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-// NF4 levels by the reference's code (kernel_ref.h:1325-1368; code 0 <-> 0.0, code 7 <-> -1.0)
-static __device__ __constant__ const float NS_NF4_LUT[16] = {0.f,
-                                                             -0.6961928009986877f,
-                                                             -0.5250730514526367f,
-                                                             -0.39491748809814453f,
-                                                             -0.28444138169288635f,
-                                                             -0.18477343022823334f,
-                                                             -0.09105003625154495f,
-                                                             -1.f,
-                                                             0.07958029955625534f,
-                                                             0.16093020141124725f,
-                                                             0.24611230194568634f,
-                                                             0.33791524171829224f,
-                                                             0.44070982933044434f,
-                                                             0.5626170039176941f,
-                                                             0.7229568362236023f,
-                                                             1.0f};
+// 4-bit float codebooks by the reference's codes: NF4 (kernel_ref.h:1325-1368; code 0 <-> 0.0, code 7 <-> -1.0), FP4 "BNB"
+// (:1209-1230) and FP4 E2M1 (:1300-1321), both sign-magnitude with the sign in bit 3
+static __device__ __constant__ const float NS_F4_LUT[3][16] = {
+    {0.f, -0.6961928009986877f, -0.5250730514526367f, -0.39491748809814453f, -0.28444138169288635f, -0.18477343022823334f, -0.09105003625154495f, -1.f, 0.07958029955625534f, 0.16093020141124725f, 0.24611230194568634f, 0.33791524171829224f, 0.44070982933044434f, 0.5626170039176941f, 0.7229568362236023f, 1.0f},
+    {0.f, 5.208333333e-03f, 0.66666667f, 1.f, 0.33333333f, 0.5f, 0.16666667f, 0.25f,
+     -0.f, -5.208333333e-03f, -0.66666667f, -1.f, -0.33333333f, -0.5f, -0.16666667f, -0.25f},
+    {0.f, 0.010416666666666666f, 0.16666666666666666f, 0.25f, 0.3333333333333333f, 0.5f, 0.6666666666666666f, 1.f,
+     -0.f, -0.010416666666666666f, -0.16666666666666666f, -0.25f, -0.3333333333333333f, -0.5f, -0.6666666666666666f, -1.f}};
 #endif

@@ -115,6 +115,35 @@ const float kNf4Lut[16] = {0.f, -0.6961928009986877f, -0.5250730514526367f, -0.3
                            -0.18477343022823334f, -0.09105003625154495f, -1.f, 0.07958029955625534f, 0.16093020141124725f,
                            0.24611230194568634f, 0.33791524171829224f, 0.44070982933044434f, 0.5626170039176941f,
                            0.7229568362236023f, 1.0f};
+// FP4 "BNB" and FP4 E2M1 codebooks (kernel_ref.h:1209-1230, :1300-1321): sign-magnitude, sign in bit 3
+const float kBnbLut[8] = {0.f, 5.208333333e-03f, 0.66666667f, 1.f, 0.33333333f, 0.5f, 0.16666667f, 0.25f};
+const float kE2m1Lut[8] = {0.f, 0.010416666666666666f, 0.16666666666666666f, 0.25f, 0.3333333333333333f, 0.5f, 0.6666666666666666f, 1.f};
+inline float f4_level(uint32_t qtype, int u) {
+  if (qtype == NS_BTLA_F4_BNB) return (u & 8) ? -kBnbLut[u & 7] : kBnbLut[u & 7];
+  if (qtype == NS_BTLA_F4_E2M1) return (u & 8) ? -kE2m1Lut[u & 7] : kE2m1Lut[u & 7];
+  return kNf4Lut[u];
+}
+inline int bnb_code(float x) {  // fp4_bnb_quantize, kernel_ref.h:1234-1256
+  const int sign = x < 0 ? 8 : 0;
+  x = std::fabs(x);
+  if (x > 0.29166667f) {
+    if (x > 0.583333f) return (x > 0.8333333f ? 3 : 2) + sign;
+    return (x > 0.4166667f ? 5 : 4) + sign;
+  }
+  if (x > 0.0859375f) return (x > 0.20833333f ? 7 : 6) + sign;
+  return (x > 0.00260417f ? 1 : 0) + sign;
+}
+inline int e2m1_code(float x) {  // fp4_e2m1_quantize, kernel_ref.h:1258-1298
+  const int sign = x < 0 ? 8 : 0;
+  x = std::fabs(x);
+  if (x > 1.75f / 6) {
+    if (x > 3.5f / 6) return (x > 5.f / 6 ? 7 : 6) + sign;
+    return (x > 2.5f / 6 ? 5 : 4) + sign;
+  }
+  if (x > 0.53125f / 6) return (x > 1.25f / 6 ? 3 : 2) + sign;
+  return (x > 0.03125f / 6 ? 1 : 0) + sign;
+}
+inline bool is_f4(uint32_t t) { return t == NS_BTLA_F4_NF4 || t == NS_BTLA_F4_BNB || t == NS_BTLA_F4_E2M1; }
 inline int nf4_code(float x) {  // kernel_ref.h:1373-1414 as a sorted threshold walk
   static const float thr[15] = {-0.8480964004993439f, -0.6106329262256622f, -0.4599952697753906f, -0.33967943489551544f,
                                 -0.23460740596055984f, -0.13791173323988914f, -0.045525018125772476f, 0.03979014977812767f,
@@ -129,7 +158,7 @@ inline int nf4_code(float x) {  // kernel_ref.h:1373-1414 as a sorted threshold 
 // RTN quantisation of W[K][N] (row stride ldw) in K-blocks of g.  Outputs q [K][N], scales [nb][N], zps [nb][N].
 void quantize_kn(const float* W, size_t ldw, int K, int N, int g, uint32_t qtype, bool asym, int8_t* q, float* scales,
                  int8_t* zps) {
-  const bool nf4 = (qtype == NS_BTLA_F4_NF4);
+  const bool nf4 = is_f4(qtype);  // any 4-bit float codebook: absmax scale, nearest level (quantize_f32_f4_rowblock, kernel_ref.h:1802)
   const int bits = dtype_bits(qtype);
   const int full = 1 << (bits - 1), symv = full - 1;
 #pragma omp parallel for schedule(static)
@@ -142,7 +171,10 @@ void quantize_kn(const float* W, size_t ldw, int K, int N, int g, uint32_t qtype
         for (int i = 0; i < len; ++i) amax = std::max(amax, std::fabs(W[(size_t)(k0 + i) * ldw + n]));
         scales[sidx] = amax;
         const float r = 1.f / amax;
-        for (int i = 0; i < len; ++i) q[(size_t)(k0 + i) * N + n] = (int8_t)nf4_code(W[(size_t)(k0 + i) * ldw + n] * r);
+        for (int i = 0; i < len; ++i) {
+          const float x = W[(size_t)(k0 + i) * ldw + n] * r;
+          q[(size_t)(k0 + i) * N + n] = (int8_t)(qtype == NS_BTLA_F4_BNB ? bnb_code(x) : qtype == NS_BTLA_F4_E2M1 ? e2m1_code(x) : nf4_code(x));
+        }
       } else if (!asym) {
         float vmax = FLT_MIN, vmin = FLT_MAX, amax = 0.f;
         for (int i = 0; i < len; ++i) {
@@ -355,7 +387,7 @@ bool make_layout(size_t N, size_t K, size_t blk, uint32_t qtype, uint32_t stype,
   if (!N || !K) return false;
   if (blk == 0 || blk > K) blk = K;
   const bool is_int = dtype_is_int(qtype);
-  if (!(qtype == NS_BTLA_S4_CLIP || qtype == NS_BTLA_S8 || qtype == NS_BTLA_F4_NF4 || qtype == NS_BTLA_S2_CLIP ||
+  if (!(qtype == NS_BTLA_S4_CLIP || qtype == NS_BTLA_S8 || is_f4(qtype) || qtype == NS_BTLA_S2_CLIP ||
         qtype == NS_BTLA_S3_CLIP || qtype == NS_BTLA_S5_CLIP || qtype == NS_BTLA_S6_CLIP || qtype == NS_BTLA_S7_CLIP))
     return false;
   if (!(stype == NS_BTLA_F32 || stype == NS_BTLA_BF16 || stype == NS_BTLA_F16)) return false;
@@ -495,7 +527,7 @@ extern "C" bool BTLAGemmUnPackB(float* FpData, const void* PackedBuf, size_t N, 
         v = (float)(ns_planes::get(qbuf, pl, e) - (1 << (bits - 1)) - (zbuf ? (int8_t)zbuf[ci] : 0)) * s;
       } else {
         const int u = (e & 1) ? (qbuf[e >> 1] >> 4) : (qbuf[e >> 1] & 0xf);
-        v = is_float ? kNf4Lut[u] * s : (float)(u - 8 - (zbuf ? (int8_t)zbuf[ci] : 0)) * s;
+        v = is_float ? f4_level(qtype, u) * s : (float)(u - 8 - (zbuf ? (int8_t)zbuf[ci] : 0)) * s;
       }
       FpData[(size_t)kk * ldb + nn] = v;
     }

@@ -137,7 +137,7 @@ __global__ void repack_scales_kernel(const void* __restrict__ sc, int src_stype,
 
 // ---- NSB -> fp32 [n][ld] ---------------------------------------------------------------------------------------------
 __global__ void dequant_kernel(const uint8_t* __restrict__ rows, size_t pitch, int sc_off, int zp_off, int stype, int asym,
-                               int n, int k, int group, int wfmt, float* __restrict__ dst, int ld) {
+                               int n, int k, int group, int wfmt, int f4kind, float* __restrict__ dst, int ld) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * k) return;
   const int row = (int)(idx / k), kk = (int)(idx - (size_t)row * k);
@@ -153,7 +153,7 @@ __global__ void dequant_kernel(const uint8_t* __restrict__ rows, size_t pitch, i
     const int e = kk & 7;
     const int sh = ((e >> 1) << 2) + ((e & 1) << 4);
     const int u = (w >> sh) & 0xf;
-    v = (wfmt == NS_W_NF4) ? NS_NF4_LUT[u] * s : (float)(u - 8 - z) * s;
+    v = (wfmt == NS_W_NF4) ? NS_F4_LUT[f4kind][u] * s : (float)(u - 8 - z) * s;
   }
   dst[(size_t)row * ld + kk] = v;
 }
@@ -250,7 +250,7 @@ int ns_launch_repack_btla(const void* qbuf_dev, const void* sc_dev, int src_styp
 int ns_launch_dequant(const ns_weight* w, float* dst, int ld, cudaStream_t st) {
   const size_t total = (size_t)w->n * w->k;
   dequant_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w->rows, (size_t)w->pitch, w->sc_off, w->zp_off,
-                                                                  w->stype, w->asym, w->n, w->k, w->group, w->wfmt, dst, ld);
+                                                                  w->stype, w->asym, w->n, w->k, w->group, w->wfmt, w->f4kind, dst, ld);
   NS_CUDA_TRY(cudaGetLastError());
   ns_count_launch();
   return NS_OK;

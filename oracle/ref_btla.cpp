@@ -61,6 +61,22 @@ REF_API int ref_btla_decompress_s4_s8(const uint8_t* src, int8_t* dst, size_t el
                                             nullptr, 0);
 }
 
+/* kernel_ref.h:1802 quantize_f32_f4_rowblock<F4_T> and :1416 f4_unpack<F4_T> for the three 4-bit float codebooks.
+ * kind: 0 = F4_NF4, 1 = F4_BNB, 2 = F4_E2M1 */
+REF_API int ref_btla_quantize_f32_f4_rowblock(int kind, const float* src, int8_t* dst, int row, int col, int ld_src, int ld_dst,
+                                              float* scales, int blocksize) {
+  if (kind == 1)
+    return (int)kernel::ref::quantize_f32_f4_rowblock<BTLA_DTYPE::F4_BNB>(src, dst, row, col, ld_src, ld_dst, scales, blocksize);
+  if (kind == 2)
+    return (int)kernel::ref::quantize_f32_f4_rowblock<BTLA_DTYPE::F4_E2M1>(src, dst, row, col, ld_src, ld_dst, scales, blocksize);
+  return (int)kernel::ref::quantize_f32_f4_rowblock<BTLA_DTYPE::F4_NF4>(src, dst, row, col, ld_src, ld_dst, scales, blocksize);
+}
+REF_API float ref_btla_f4_unpack(int kind, int8_t v) {
+  if (kind == 1) return kernel::ref::f4_unpack<BTLA_DTYPE::F4_BNB>(v);
+  if (kind == 2) return kernel::ref::f4_unpack<BTLA_DTYPE::F4_E2M1>(v);
+  return kernel::ref::f4_unpack<BTLA_DTYPE::F4_NF4>(v);
+}
+
 /* kernel_ref.h:178-345 compress_{7,6,5,3,2}bit with the plane pointers placed as compressBit{7,6,5,3,2}Weight do
  * (bestla_prologue_b.h:512-564: bit1_offset / bit2_offset = N * K elements).  dst must hold the sum of the planes. */
 REF_API int ref_btla_compress_bits(int bits, const int8_t* src, uint8_t* dst, size_t elt) {

@@ -75,3 +75,31 @@ def test_split_and_copyattr_keep_the_bit_width():
     part = np.ascontiguousarray(btla_blob.unpack(blob)[:, n // 2:].T)
     want = ns.np_bestla_quantize(part, "int3", g, "sym", "fp32", "int8")
     assert np.array_equal(btla_blob.unpack(dst), btla_blob.unpack(want))
+
+
+@pytest.mark.skipif(oracle.ref_btla() is None, reason="oracle/_ref/libref_btla.so not built")
+@pytest.mark.parametrize("name,kind", [("nf4", 0), ("fp4_bnb", 1), ("fp4_e2m1", 2)])
+def test_f4_codebooks_against_the_reference_kernels(name, kind):
+    """4-bit float weights (F4_NF4 / F4_BNB / F4_E2M1, bestla.h:82-84): codes and scales of the packer == the reference's
+    quantize_f32_f4_rowblock (kernel_ref.h:1802), dequantised values == f4_unpack * scale (kernel_ref.h:1416-1436)."""
+    R = oracle.ref_btla()
+    R.ref_btla_f4_unpack.restype = C.c_float
+    R.ref_btla_f4_unpack.argtypes = [C.c_int, C.c_int8]
+    rng = np.random.default_rng(40 + kind)
+    n, k, g = 96, 256, 64
+    w = rng.normal(0, 0.05, (n, k)).astype(np.float32)
+    w[3, :64] = 0.0          # an all-zero block: absmax = FLT_MIN
+    w[5, 7] = -w[5].max() * 3  # a block whose maximum is negative
+    blob = ns.np_bestla_quantize(w, name, g, "sym", "fp32", "fp32")
+    h = btla_blob.parse(blob)
+    assert h["prologue"] == 2 and h["dtype"] == {0: 4 | (2 << 16), 1: 4 | (1 << 16), 2: 4}[kind]
+    wkn = np.ascontiguousarray(w.T)
+    q = np.zeros((k, n), np.int8)
+    sc = np.zeros((k // g, n), np.float32)
+    assert R.ref_btla_quantize_f32_f4_rowblock(kind, wkn.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), k, n, n, n,
+                                               sc.ctypes.data_as(C.c_void_p), g) == 0
+    lut = np.array([R.ref_btla_f4_unpack(kind, c) for c in range(16)], np.float32)
+    want = (lut[q.astype(np.int32) & 15] * np.repeat(sc, g, axis=0)).astype(np.float32)
+    assert np.array_equal(ns.unpack_blob(blob, n, k), want)
+    flat = btla_blob.interleave(q, h["ntile"], h["packrow"], h["kpad"], h["npad"])
+    assert bytes(h["qbuf"]) == bytes(btla_blob.compress_s4(flat, bias=0))
