@@ -148,7 +148,9 @@ __device__ __forceinline__ PairSrc resolve_single(const GemvParams& P, int u) {
   return s;
 }
 
-template <int AMODE, int M, bool ASYM, int STYPE, int ROWS>
+// NORM: the fused-RMSNorm prologue is a separate instantiation, so the plain kernels (the headline path) keep the code and the
+// register allocation they had without it
+template <int AMODE, int M, bool ASYM, int STYPE, int ROWS, bool NORM>
 __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams P, const RingCfg R) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -195,16 +197,28 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
   }
 
   // ===================== consumers =====================
+  // fused RMSNorm: the norm weights are model constants -- fetch this thread's share before the wait (single-pass rows)
+  float gw[NORM ? 3 : 1][8];
+  bool gw_pref = false;
+  if constexpr (NORM) {
+    gw_pref = (P.kpad >> 3) <= 3 * kConsumers * 32;
+    if (gw_pref) nsq::prefetch_norm_w<kConsumers * 32>(P.norm_w, P.k, P.kpad, (int)threadIdx.x, gw);
+  }
   pdl_wait();  // activations (and residual) come from earlier kernels
-  if (P.act_f32 && P.norm_w) {
-    // fused ne_rms_norm + ne_mul + NE_TASK_INIT: every CTA already reads the whole fp32 row, the sum of squares costs one more
-    // block reduction instead of a kernel boundary (llama.cpp:205-210; arithmetic of rmsnorm_kernel, llama.cu)
-    const nsq::NormQuantIn ni{P.act_f32, P.norm_w, P.norm_eps, P.lda, P.k, P.kpad, P.comp == NS_COMP_Q8_0 ? 32 : P.group,
-                              R.act_row, P.meta_off, P.meta_stride};
-    float* red = reinterpret_cast<float*>(smem + R.red_off);
-    if (AMODE == A_U8) nsq::norm_quantise_to_smem<NS_COMP_INT8, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x);
-    else if (P.comp == NS_COMP_Q8_0) nsq::norm_quantise_to_smem<NS_COMP_Q8_0, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x);
-    else nsq::norm_quantise_to_smem<NS_COMP_INT8_S8, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x);
+  if (NORM) {
+    if constexpr (NORM) {
+      // fused ne_rms_norm + ne_mul + NE_TASK_INIT: every CTA already reads the whole fp32 row, the sum of squares costs one more
+      // block reduction instead of a kernel boundary (llama.cpp:205-210; arithmetic of rmsnorm_kernel, llama.cu)
+      const nsq::NormQuantIn ni{P.act_f32, P.norm_w, P.norm_eps, P.lda, P.k, P.kpad, P.comp == NS_COMP_Q8_0 ? 32 : P.group,
+                                R.act_row, P.meta_off, P.meta_stride};
+      float* red = reinterpret_cast<float*>(smem + R.red_off);
+      if (AMODE == A_U8)
+        nsq::norm_quantise_to_smem<NS_COMP_INT8, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x, gw_pref ? gw : nullptr);
+      else if (P.comp == NS_COMP_Q8_0)
+        nsq::norm_quantise_to_smem<NS_COMP_Q8_0, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x, gw_pref ? gw : nullptr);
+      else
+        nsq::norm_quantise_to_smem<NS_COMP_INT8_S8, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x, gw_pref ? gw : nullptr);
+    }
   } else if (P.act_f32) {
     // fused NE_TASK_INIT: quantise the fp32 rows straight into the shared-memory image (no separate kernel, no round trip)
     const QuantIn qi{P.act_f32, P.lda, P.k, P.kpad, P.comp == NS_COMP_Q8_0 ? 32 : P.group, R.act_row, P.meta_off, P.meta_stride};
@@ -390,9 +404,9 @@ static RingPlan plan_ring(const GemvParams& P, size_t act_region) {
   return best;
 }
 
-template <int AMODE, int M, bool ASYM, int STYPE, int ROWS>
+template <int AMODE, int M, bool ASYM, int STYPE, int ROWS, bool NORM>
 int launch_rows(const GemvParams& P, const RingPlan& plan, size_t act_region, int act_row, int red_off, cudaStream_t st) {
-  auto kern = gemv_ring_kernel<AMODE, M, ASYM, STYPE, ROWS>;
+  auto kern = gemv_ring_kernel<AMODE, M, ASYM, STYPE, ROWS, NORM>;
   static bool attr_set = false;
   if (!attr_set) {
     NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -439,8 +453,18 @@ int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
     ns_set_error("gemv_ring: row pitch %d too large for shared memory", P.pitch);
     return NS_E_UNSUPPORTED;
   }
-  if (plan.rows == 2) return launch_rows<AMODE, M, ASYM, STYPE, 2>(P, plan, act_region, act_row, red_off, st);
-  return launch_rows<AMODE, M, ASYM, STYPE, 1>(P, plan, act_region, act_row, red_off, st);
+  if constexpr (M <= 2) {  // the norm is only ever folded into launches of <= 2 rows (ns_gemv_fused_norm_ok)
+    if (P.norm_w && P.act_f32) {
+      if (plan.rows == 2) return launch_rows<AMODE, M, ASYM, STYPE, 2, true>(P, plan, act_region, act_row, red_off, st);
+      return launch_rows<AMODE, M, ASYM, STYPE, 1, true>(P, plan, act_region, act_row, red_off, st);
+    }
+  }
+  if (P.norm_w) {
+    ns_set_error("gemv_ring: fused RMSNorm needs fp32 activations and <= 2 rows");
+    return NS_E_INVALID;
+  }
+  if (plan.rows == 2) return launch_rows<AMODE, M, ASYM, STYPE, 2, false>(P, plan, act_region, act_row, red_off, st);
+  return launch_rows<AMODE, M, ASYM, STYPE, 1, false>(P, plan, act_region, act_row, red_off, st);
 }
 
 template <int AMODE, bool ASYM, int STYPE>

@@ -407,35 +407,40 @@ __global__ void __launch_bounds__(kDW * 32) attn_decode_kernel(const float* __re
   __shared__ float bcast;
   __shared__ int last_flag;
   pdl_launch_dependents();
-  const uint32_t bar_a = smem_addr(bar);
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  pdl_wait();
+  // The position was written by the PREVIOUS token's argmax kernel (an earlier graph launch / an H2D copy ahead of this eval's
+  // first kernel), never by a kernel of this token: it may be read before griddepcontrol.wait.  CTAs whose range the sequence
+  // has not reached leave at once, without holding 141 KB of an SM until the Q/K/V launch in front of this one has drained.
   const int h = blockIdx.x, split = blockIdx.y;
   const int group = n_head / n_head_kv, hk = h / group;
   const int pos = state[1];
   const int len = min(pos + 1, n_ctx);
   const int nact = (len + kSplitKeys - 1) / kSplitKeys;
-  if (split >= nact) return;  // the sequence has not reached this range
+  if (split >= nact) return;
   const int i0 = split * kSplitKeys, i1 = min(len, i0 + kSplitKeys);
   const bool has_new = (i1 == len) && pos < n_ctx;  // the token being evaluated sits in this range: its k / v come from registers
   const int ncache = (has_new ? i1 - 1 : i1) - i0;  // rows read from the cache
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __half* kh = kc + (size_t)hk * n_ctx * HD;
   __half* vh = vc + (size_t)hk * n_ctx * HD;
-  if (threadIdx.x == 0 && ncache > 0) {
-    const uint32_t bytes = (uint32_t)ncache * HD * 2;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2 * bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(Kt)),
-                 "l"(kh + (size_t)i0 * HD), "r"(bytes), "r"(bar_a)
-                 : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(Vt)),
-                 "l"(vh + (size_t)i0 * HD), "r"(bytes), "r"(bar_a)
-                 : "memory");
+  const uint32_t bar_a = smem_addr(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the cached rows of this range were written by earlier tokens' launches: their copies start before the wait as well and
+    // overlap the tail of the Q/K/V launch
+    if (ncache > 0) {
+      const uint32_t bytes = (uint32_t)ncache * HD * 2;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2 * bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(Kt)),
+                   "l"(kh + (size_t)i0 * HD), "r"(bytes), "r"(bar_a)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(Vt)),
+                   "l"(vh + (size_t)i0 * HD), "r"(bytes), "r"(bar_a)
+                   : "memory");
+    }
   }
+  __syncthreads();
+  pdl_wait();  // q, k, v of the new token come from the launch in front
   // RoPE of this head's q (every range needs it) and of the new k row; KV append by one CTA per kv head -- while the copies fly
   if (threadIdx.x < HD / 2) {
     const int i = threadIdx.x;
@@ -1152,7 +1157,10 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
       }
     }
     const bool fast = (hd == 128 || hd == 64);
-    if (fast && m == 1 && c->attn_nsplit <= 1024 && !getenv("NS_ATTN_OLD_DECODE")) {
+    static const int dbg_skip = getenv("NS_LLAMA_DEBUG_SKIP") ? atoi(getenv("NS_LLAMA_DEBUG_SKIP")) : 0;  // timing experiments only
+    if (m == 1 && (dbg_skip & 1)) {
+      // (results are wrong: the attention launch is left out to measure what it costs inside the token's graph)
+    } else if (fast && m == 1 && c->attn_nsplit <= 1024 && !getenv("NS_ATTN_OLD_DECODE")) {
       // rope + KV append + attention in one launch, K / V staged by TMA, the context split over CTAs
       const size_t dsm = hd == 128 ? attn_decode_smem<128>() : attn_decode_smem<64>();
       if (!c->dec_attr) {

@@ -19,6 +19,26 @@ struct NormQuantIn {
   int act_row, meta_off, meta_stride;
 };
 
+// The RMSNorm weights of the 8-groups thread `tid` owns in a single-pass row (kpad / 8 <= 3 * NT).  They are constants of the model:
+// the caller fetches them BEFORE griddepcontrol.wait, so the L2 broadcast of the weight vector to every CTA overlaps the previous
+// launch's tail instead of sitting between the wait and the first dp4a.
+template <int NT>
+__device__ __forceinline__ void prefetch_norm_w(const float* __restrict__ norm_w, int k, int kpad, int tid, float (&gw)[3][8]) {
+  const int ngroups8 = kpad >> 3;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int e = it * NT + tid, k0 = e * 8;
+    if (e < ngroups8 && k0 + 8 <= k) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(norm_w + k0)), w1 = __ldg(reinterpret_cast<const float4*>(norm_w + k0 + 4));
+      gw[it][0] = w0.x; gw[it][1] = w0.y; gw[it][2] = w0.z; gw[it][3] = w0.w;
+      gw[it][4] = w1.x; gw[it][5] = w1.y; gw[it][6] = w1.z; gw[it][7] = w1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gw[it][i] = (e < ngroups8 && k0 + i < k) ? __ldg(norm_w + k0 + i) : 0.f;
+    }
+  }
+}
+
 template <int BAR, int NT>
 __device__ __forceinline__ void bar_sync() {
   asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory");
@@ -26,7 +46,8 @@ __device__ __forceinline__ void bar_sync() {
 
 // red: shared float[NT/32]
 template <int COMP, int NT, int BAR>
-__device__ __forceinline__ void norm_quantise_to_smem(const NormQuantIn& P, int M, uint32_t smem_base, float* red, int tid) {
+__device__ __forceinline__ void norm_quantise_to_smem(const NormQuantIn& P, int M, uint32_t smem_base, float* red, int tid,
+                                                      const float (*gw)[8] = nullptr) {  // gw: prefetch_norm_w's registers (single-pass rows)
   constexpr int NI = 3;  // load passes kept in registers (3 x 512 threads x 8 = 12288 elements)
   const int tpb = (COMP == NS_COMP_Q8_0 ? 32 : P.group) >> 3;
   const int ngroups8 = P.kpad >> 3;
@@ -94,7 +115,10 @@ __device__ __forceinline__ void norm_quantise_to_smem(const NormQuantIn& P, int 
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = vv[it][i];
-        if (norm) {
+        if (norm && gw != nullptr && single) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = v[i] * inv * gw[it][i];  // (padding lanes: gw = 0, v = 0)
+        } else if (norm) {
           if (live && k0 + 8 <= P.k) {
             const float4 w0 = __ldg((const float4*)(P.norm_w + k0)), w1 = __ldg((const float4*)(P.norm_w + k0 + 4));
             v[0] = v[0] * inv * w0.x; v[1] = v[1] * inv * w0.y; v[2] = v[2] * inv * w0.z; v[3] = v[3] * inv * w0.w;

@@ -10,6 +10,7 @@ import ctypes as C
 
 n_layer = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 n_new = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+n_prompt = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 E, FF, V = 4096, 11008, 32000
 L = ns.lib()
 L.bestla_init()
@@ -24,7 +25,7 @@ def mk(n, k):
     return ns.Weight.from_q4_0_device(rows.data_ptr(), n, k, (k // 32) * 18)
 
 
-eng = ns.Llama(V, E, 32, 32, n_layer, FF, 1024, 1e-5)
+eng = ns.Llama(V, E, 32, 32, n_layer, FF, max(1024, n_prompt + 64), 1e-5)
 eng.set_f32(ns.Llama.TOK_EMBD, 0, torch.randn(V, E).numpy())
 ones = np.ones(E, np.float32)
 eng.set_f32(ns.Llama.OUT_NORM, 0, ones)
@@ -36,6 +37,6 @@ for il in range(n_layer):
     eng.set_f32(ns.Llama.FFN_NORM, il, ones)
     for name, (n, k) in shapes.items():
         eng.set_weight(ids[name], il, mk(n, k))
-prompt = np.arange(1, 33, dtype=np.int32)
+prompt = (np.arange(n_prompt, dtype=np.int32) % 30000) + 1
 _, nxt = eng.eval(prompt, 0, want_logits=False)
-print("generated", eng.generate(int(nxt), 32, n_new))
+print("generated", eng.generate(int(nxt), n_prompt, n_new))

@@ -78,4 +78,6 @@ def test_f4_codebook_blobs(name, cdt, m):
                                    k, k, n, None)
     a_eff = a if cdt == "fp32" else oracle.bf16_bits_to_f32(oracle.f32_to_bf16_bits(a))
     want = oracle.gemm_f64acc(a_eff, wdq)
-    assert np.abs(out - want).max() <= (1e-3 if cdt == "fp32" else 2e-2)
+    # fp32 compute: the reference UT bar; bf16 compute: bf16 rounding of the dequantised weight too (GEMV keeps it in fp32, the tensor-core
+    # GEMM for > 16 rows rounds level x scale to bf16 as the reference does)
+    assert np.abs(out - want).max() <= (1e-3 if cdt == "fp32" else 2e-2 if m <= 16 else 4e-2)
