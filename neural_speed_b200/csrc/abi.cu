@@ -630,7 +630,8 @@ static int norm_unsupported(const char* who) {
 }
 
 static int mul_mat_impl(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* bias,
-                        const float* residual, int flags, void* workspace, void* queue, const float* norm_w, float norm_eps) {
+                        const float* residual, int flags, void* workspace, void* queue, const float* norm_w, float norm_eps,
+                        int one_image = 0) {
   if (int rc = ns_ensure_device()) return rc;
   if (!w || !act || !dst || m <= 0 || lda < w->k || ldo < w->n) {
     ns_set_error("ns_mul_mat: invalid arguments (m=%d lda=%d ldo=%d)", m, lda, ldo);
@@ -674,7 +675,7 @@ static int mul_mat_impl(const ns_weight* w, const float* act, int lda, float* ds
     if (int rc = ns_launch_gemv(&w, 1, NS_GEMV_PLAIN, fused ? nullptr : ws, dst + (size_t)m0 * ldo, ldo, mt, m,
                                 bias ? (bcast ? bias : bias + (size_t)m0 * ldo) : nullptr, bcast,
                                 residual ? residual + (size_t)m0 * ldo : nullptr, nullptr, st, fused ? a : nullptr, lda,
-                                NS_ELT_DEFAULT, norm_w, norm_eps))
+                                NS_ELT_DEFAULT, norm_w, norm_eps, one_image))
       return rc;
   }
   return NS_OK;
@@ -682,6 +683,10 @@ static int mul_mat_impl(const ns_weight* w, const float* act, int lda, float* ds
 extern "C" int ns_mul_mat(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* bias,
                           const float* residual, int flags, void* workspace, void* queue) {
   return mul_mat_impl(w, act, lda, dst, ldo, m, bias, residual, flags, workspace, queue, nullptr, 0.f);
+}
+int ns_mul_mat_engine(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* residual, void* workspace,
+                      cudaStream_t st, const float* norm_w, float norm_eps) {
+  return mul_mat_impl(w, act, lda, dst, ldo, m, nullptr, residual, 0, workspace, (void*)st, norm_w, norm_eps, 1);
 }
 // dst = W * (rms_norm(act) * norm_w) [+ residual]: ne_rms_norm + ne_mul + ne_mul_mat (llama.cpp:205-215, :703-712) as ONE launch
 extern "C" int ns_rmsnorm_mul_mat(const ns_weight* w, const float* act, int lda, const float* norm_w, float norm_eps, float* dst,
@@ -740,7 +745,7 @@ extern "C" int ns_rmsnorm_mul_qkv(const ns_weight* wq, const ns_weight* wk, cons
 // tmp: [2][m][fmid] floats when m > 4 and w3 is given (gate and up GEMM outputs; the product lands in the first half), else [m][fmid]
 static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, int eltop, const float* b1, const float* b2,
                     int bcast, const float* act, int lda, float* tmp, float* dst, int ldo, int m, void* workspace, void* queue,
-                    const float* residual = nullptr, const float* norm_w = nullptr, float norm_eps = 0.f) {
+                    const float* residual = nullptr, const float* norm_w = nullptr, float norm_eps = 0.f, int one_image = 0) {
   if (int rc = ns_ensure_device()) return rc;
   if (!w1 || !w2 || !act || !tmp || !dst || m <= 0 || w2->k != w1->n || (w3 && (w3->n != w1->n || w3->k != w1->k)) ||
       (w3 && (b1 || b2)) || (!w3 && eltop != NS_ELT_GELU)) {
@@ -792,7 +797,7 @@ static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w
       if (int rc = ns_launch_act_prep(a, lda, mt, w1, ws, st)) return rc;
     if (w3) {
       if (int rc = ns_launch_gemv(gu, 2, NS_GEMV_GATE_UP_SILU, fused1 ? nullptr : ws, tmp + (size_t)m0 * fmid, fmid, mt, m, nullptr,
-                                  0, nullptr, nullptr, st, fused1 ? a : nullptr, lda, eltop, norm_w, norm_eps))
+                                  0, nullptr, nullptr, st, fused1 ? a : nullptr, lda, eltop, norm_w, norm_eps, one_image))
         return rc;
     } else {
       if (int rc = ns_launch_gemv(gu, 1, NS_GEMV_PLAIN, fused1 ? nullptr : ws, tmp + (size_t)m0 * fmid, fmid, mt, m,
@@ -809,7 +814,8 @@ static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w
       if (int rc = ns_launch_act_prep(a, fmid, mt, w2, ws, st)) return rc;
     if (int rc = ns_launch_gemv(&w2, 1, NS_GEMV_PLAIN, fused2 ? nullptr : ws, dst + (size_t)m0 * ldo, ldo, mt, m,
                                 b2 ? (bcast ? b2 : b2 + (size_t)m0 * ldo) : nullptr, bcast,
-                                residual ? residual + (size_t)m0 * ldo : nullptr, nullptr, st, fused2 ? a : nullptr, fmid))
+                                residual ? residual + (size_t)m0 * ldo : nullptr, nullptr, st, fused2 ? a : nullptr, fmid, NS_ELT_DEFAULT,
+                                nullptr, 0.f, one_image))
       return rc;
   }
   return NS_OK;
@@ -817,10 +823,10 @@ static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w
 // dst = residual + FFN_SiLU(act): the decode engine's "cur = ne_add(ffn, inpFF)" (llama.cpp:698) folded into the down GEMV
 int ns_ffn_silu_residual(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda, float* tmp,
                          float* dst, int ldo, int m, const float* residual, void* workspace, cudaStream_t st, const float* norm_w,
-                         float norm_eps) {
+                         float norm_eps, int one_image) {
   if (!w3) return NS_E_INVALID;
   return ffn_impl(w1, w2, w3, NS_ELT_DEFAULT, nullptr, nullptr, 0, act, lda, tmp, dst, ldo, m, workspace, (void*)st, residual, norm_w,
-                  norm_eps);
+                  norm_eps, one_image);
 }
 // dst = residual + FFN_SiLU(rms_norm(act) * norm_w): llama.cpp:601-698 with the norm folded into the gate/up launch
 extern "C" int ns_rmsnorm_ffn_silu(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda,

@@ -378,7 +378,7 @@ bool ns_gemv_fused_norm_ok(const ns_weight* const* ws, int nw, int m) {
 
 int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* act_ws, float* dst, int ldo, int m,
                    int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st,
-                   const float* act_f32, int lda, int eltop, const float* norm_w, float norm_eps) {
+                   const float* act_f32, int lda, int eltop, const float* norm_w, float norm_eps, int one_image) {
   const ns_weight* w0 = ws_[0];
   for (int i = 1; i < nw; ++i) {
     const ns_weight* wi = ws_[i];
@@ -454,6 +454,7 @@ int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* ac
   P.f4kind = w0->f4kind;
   P.norm_w = norm_w;
   P.norm_eps = norm_eps;
+  P.one_image = one_image;
   if (norm_w && !(act_f32 && ns_gemv_fused_quant_ok(w0))) {
     ns_set_error("internal: fused RMSNorm needs the fused activation quantiser");
     return NS_E_INVALID;

@@ -201,12 +201,13 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
   float gw[NORM ? 3 : 1][8];
   bool gw_pref = false;
   if constexpr (NORM) {
-    gw_pref = (P.kpad >> 3) <= 3 * kConsumers * 32;
+    gw_pref = P.norm_w != nullptr && (P.kpad >> 3) <= 3 * kConsumers * 32;
     if (gw_pref) nsq::prefetch_norm_w<kConsumers * 32>(P.norm_w, P.k, P.kpad, (int)threadIdx.x, gw);
   }
   pdl_wait();  // activations (and residual) come from earlier kernels
-  if (NORM) {
-    if constexpr (NORM) {
+  bool normed = false;
+  if constexpr (NORM) {
+    if (P.norm_w) {  // (a norm-capable image also serves plain nodes: see GemvParams::one_image)
       // fused ne_rms_norm + ne_mul + NE_TASK_INIT: every CTA already reads the whole fp32 row, the sum of squares costs one more
       // block reduction instead of a kernel boundary (llama.cpp:205-210; arithmetic of rmsnorm_kernel, llama.cu)
       const nsq::NormQuantIn ni{P.act_f32, P.norm_w, P.norm_eps, P.lda, P.k, P.kpad, P.comp == NS_COMP_Q8_0 ? 32 : P.group,
@@ -218,7 +219,10 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
         nsq::norm_quantise_to_smem<NS_COMP_Q8_0, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x, gw_pref ? gw : nullptr);
       else
         nsq::norm_quantise_to_smem<NS_COMP_INT8_S8, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x, gw_pref ? gw : nullptr);
+      normed = true;
     }
+  }
+  if (normed) {
   } else if (P.act_f32) {
     // fused NE_TASK_INIT: quantise the fp32 rows straight into the shared-memory image (no separate kernel, no round trip)
     const QuantIn qi{P.act_f32, P.lda, P.k, P.kpad, P.comp == NS_COMP_Q8_0 ? 32 : P.group, R.act_row, P.meta_off, P.meta_stride};
@@ -454,12 +458,12 @@ int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
     return NS_E_UNSUPPORTED;
   }
   if constexpr (M <= 2) {  // the norm is only ever folded into launches of <= 2 rows (ns_gemv_fused_norm_ok)
-    if (P.norm_w && P.act_f32) {
+    if ((P.norm_w || P.one_image) && P.act_f32) {
       if (plan.rows == 2) return launch_rows<AMODE, M, ASYM, STYPE, 2, true>(P, plan, act_region, act_row, red_off, st);
       return launch_rows<AMODE, M, ASYM, STYPE, 1, true>(P, plan, act_region, act_row, red_off, st);
     }
   }
-  if (P.norm_w) {
+  if (P.norm_w) {  // (one_image without fp32 activations or with 4 rows simply takes the plain kernel)
     ns_set_error("gemv_ring: fused RMSNorm needs fp32 activations and <= 2 rows");
     return NS_E_INVALID;
   }

@@ -1204,12 +1204,12 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
       ns_count_launch();
     }
     // inpFF = wo * attn + inpSA, written over x (every row is read by its own output only after the matmul finished)
-    if (int rc = ns_mul_mat(L.wo, c->attn, E, c->xn, E, m, nullptr, c->x, 0, c->ws, (void*)st)) return rc;
+    if (int rc = ns_mul_mat_engine(L.wo, c->attn, E, c->xn, E, m, c->x, c->ws, st, nullptr, 0.f)) return rc;
     // xn now holds inpFF; FFN + residual back into x, the FFN RMSNorm folded into the gate/up launch where that is a ring GEMV,
     // else normalised into attn (free again) first
     const ns_weight* guw[2] = {L.w1, L.w3};
     if (ns_gemv_fused_norm_ok(guw, 2, m)) {
-      if (int rc = ns_ffn_silu_residual(L.w1, L.w2, L.w3, c->xn, E, c->tmp, c->x, E, m, c->xn, c->ws, st, L.ffn_norm, hp.norm_eps)) return rc;
+      if (int rc = ns_ffn_silu_residual(L.w1, L.w2, L.w3, c->xn, E, c->tmp, c->x, E, m, c->xn, c->ws, st, L.ffn_norm, hp.norm_eps, 1)) return rc;
     } else {
       if (int rc = launch_rmsnorm(c->xn, L.ffn_norm, c->attn, m, E, hp.norm_eps, st)) return rc;
       if (int rc = ns_ffn_silu_residual(L.w1, L.w2, L.w3, c->attn, E, c->tmp, c->x, E, m, c->xn, c->ws, st)) return rc;

@@ -77,7 +77,8 @@ int ns_launch_act_prep(const float* act, int lda, int m, const ns_weight* w, voi
 int ns_gemv_tile_rows(const ns_weight* w);
 int ns_launch_gemv(const ns_weight* const* ws_, int nw, int mode, const void* act_ws, float* dst, int ldo, int m,
                    int m_total, const float* bias, int bias_bcast, const float* residual, float* aux, cudaStream_t st,
-                   const float* act_f32 = nullptr, int lda = 0, int eltop = 0, const float* norm_w = nullptr, float norm_eps = 0.f);
+                   const float* act_f32 = nullptr, int lda = 0, int eltop = 0, const float* norm_w = nullptr, float norm_eps = 0.f,
+                   int one_image = 0);
 bool ns_gemv_fused_quant_ok(const ns_weight* w);  // can the GEMV quantise the activations itself (one launch)?
 // can RMSNorm(x) * norm_w be folded into that quantiser for m rows (m <= 2: the rows the ring GEMV takes before IMMA does)?
 bool ns_gemv_fused_norm_ok(const ns_weight* const* ws, int nw, int m);
@@ -100,7 +101,10 @@ int ns_launch_mul_mat_q6k(const ns_weight* w, const float* act, int lda, float* 
 // abi.cu: fused FFN with the residual add folded into the down projection (used by the decode engine, llama.cu)
 int ns_ffn_silu_residual(const ns_weight* w1, const ns_weight* w2, const ns_weight* w3, const float* act, int lda, float* tmp,
                          float* dst, int ldo, int m, const float* residual, void* workspace, cudaStream_t st,
-                         const float* norm_w = nullptr, float norm_eps = 0.f);
+                         const float* norm_w = nullptr, float norm_eps = 0.f, int one_image = 0);
+// abi.cu: plain matmul node of the decode engine (one_image: see GemvParams)
+int ns_mul_mat_engine(const ns_weight* w, const float* act, int lda, float* dst, int ldo, int m, const float* residual, void* workspace,
+                      cudaStream_t st, const float* norm_w, float norm_eps);
 // abi.cu: fused QKV with the attention RMSNorm folded into the activation quantiser (norm_w may be NULL: plain ns_mul_qkv)
 int ns_mul_qkv_norm(const ns_weight* wq, const ns_weight* wk, const ns_weight* wv, const float* act, int lda, float* dst, int ldo,
                     int m, void* workspace, void* queue, const float* norm_w, float norm_eps);
@@ -155,6 +159,8 @@ struct GemvParams {
   int f4kind;           // NS_W_NF4 weights: codebook
   const float* norm_w;  // fused ne_rms_norm + ne_mul in front of the activation quantiser (llama.cpp:205-210), or NULL
   float norm_eps;
+  int one_image;  // decode engine: run this node on the norm-capable kernel image even without a norm, so that ALL the GEMV nodes of
+                  // a token share ONE code image (two alternating images cost ~40 us per token in instruction-cache misses, measured)
 };
 int ns_launch_gemv_ring(const GemvParams& P, int amode, bool asym, int mt, cudaStream_t st);  // gemv_ring.cu
 
