@@ -150,8 +150,13 @@ __device__ __forceinline__ PairSrc resolve_single(const GemvParams& P, int u) {
 
 // NORM: the fused-RMSNorm prologue is a separate instantiation, so the plain kernels (the headline path) keep the code and the
 // register allocation they had without it
-template <int AMODE, int M, bool ASYM, int STYPE, int ROWS, bool NORM>
-__global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams P, const RingCfg R) {
+// NC consumer warps: 7 (+1 producer warp, two CTAs per SM) or 14 (+2 producer warps, ONE CTA per SM: the activation row is pulled
+// through L2 and quantised once per SM instead of twice -- the 16-44 KB broadcast to every CTA is what separates the fused launch
+// list from the pre-quantised one; the two producer warps take alternate ring stages)
+template <int AMODE, int M, bool ASYM, int STYPE, int ROWS, bool NORM, int NC>
+__global__ void __launch_bounds__((NC + (NC > kConsumers ? 2 : 1)) * 32, NC > kConsumers ? 1 : 2)
+    gemv_ring_kernel(const GemvParams P, const RingCfg R) {
+  constexpr int NP = NC > kConsumers ? 2 : 1;  // producer warps
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stage_bytes = ROWS * P.pitch;
@@ -175,20 +180,22 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
   const int gstride = (int)gridDim.x;
   const int my_units = first < R.units ? (R.units - first + gstride - 1) / gstride : 0;
 
-  if (warp == kConsumers) {
-    // ===================== producer: stream whole row pairs, never touches activations =====================
+  if (warp >= NC) {
+    // ===================== producer(s): stream whole row pairs, never touch activations =====================
+    // producer warp pw takes units pw, pw + NP, ...; unit j always lands in stage j % stages (`stages` is a multiple of NC: even)
     if (lane == 0) {
-      int s = 0;
+      int s = warp - NC;
       uint32_t phase = 0;
-      for (int j = 0; j < my_units; ++j) {
+      for (int j = warp - NC; j < my_units; j += NP) {
         if (j >= stages) mbar_wait(empty0 + 8 * s, phase ^ 1);
         const PairSrc ps = ROWS == 2 ? resolve_pair(P, first + j * gstride) : resolve_single(P, first + j * gstride);
         const uint32_t dst = ring + (uint32_t)s * stage_bytes;
         mbar_expect_tx(full0 + 8 * s, (uint32_t)stage_bytes);
         bulk_g2s(dst, ps.r0, (uint32_t)P.pitch, full0 + 8 * s);
         if (ROWS == 2) bulk_g2s(dst + P.pitch, ps.r1, (uint32_t)P.pitch, full0 + 8 * s);
-        if (++s == stages) {
-          s = 0;
+        s += NP;
+        if (s >= stages) {
+          s -= stages;
           phase ^= 1;
         }
       }
@@ -201,8 +208,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
   float gw[NORM ? 3 : 1][8];
   bool gw_pref = false;
   if constexpr (NORM) {
-    gw_pref = P.norm_w != nullptr && (P.kpad >> 3) <= 3 * kConsumers * 32;
-    if (gw_pref) nsq::prefetch_norm_w<kConsumers * 32>(P.norm_w, P.k, P.kpad, (int)threadIdx.x, gw);
+    gw_pref = P.norm_w != nullptr && (P.kpad >> 3) <= 3 * NC * 32;
+    if (gw_pref) nsq::prefetch_norm_w<NC * 32>(P.norm_w, P.k, P.kpad, (int)threadIdx.x, gw);
   }
   pdl_wait();  // activations (and residual) come from earlier kernels
   bool normed = false;
@@ -214,11 +221,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
                                 R.act_row, P.meta_off, P.meta_stride};
       float* red = reinterpret_cast<float*>(smem + R.red_off);
       if (AMODE == A_U8)
-        nsq::norm_quantise_to_smem<NS_COMP_INT8, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x, gw_pref ? gw : nullptr);
+        nsq::norm_quantise_to_smem<NS_COMP_INT8, NC * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x, gw_pref ? gw : nullptr);
       else if (P.comp == NS_COMP_Q8_0)
-        nsq::norm_quantise_to_smem<NS_COMP_Q8_0, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x, gw_pref ? gw : nullptr);
+        nsq::norm_quantise_to_smem<NS_COMP_Q8_0, NC * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x, gw_pref ? gw : nullptr);
       else
-        nsq::norm_quantise_to_smem<NS_COMP_INT8_S8, kConsumers * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x, gw_pref ? gw : nullptr);
+        nsq::norm_quantise_to_smem<NS_COMP_INT8_S8, NC * 32, 1>(ni, P.m, smem_base, red, (int)threadIdx.x, gw_pref ? gw : nullptr);
       normed = true;
     }
   }
@@ -226,16 +233,16 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_ring_kernel(const GemvParams
   } else if (P.act_f32) {
     // fused NE_TASK_INIT: quantise the fp32 rows straight into the shared-memory image (no separate kernel, no round trip)
     const QuantIn qi{P.act_f32, P.lda, P.k, P.kpad, P.comp == NS_COMP_Q8_0 ? 32 : P.group, R.act_row, P.meta_off, P.meta_stride};
-    if (P.comp == NS_COMP_Q8_0) nsq::quantise_to_smem<NS_COMP_Q8_0, kConsumers * 32>(qi, P.m, smem_base);
-    else if (P.comp == NS_COMP_INT8) nsq::quantise_to_smem<NS_COMP_INT8, kConsumers * 32>(qi, P.m, smem_base);
-    else nsq::quantise_to_smem<NS_COMP_INT8_S8, kConsumers * 32>(qi, P.m, smem_base);
+    if (P.comp == NS_COMP_Q8_0) nsq::quantise_to_smem<NS_COMP_Q8_0, NC * 32>(qi, P.m, smem_base);
+    else if (P.comp == NS_COMP_INT8) nsq::quantise_to_smem<NS_COMP_INT8, NC * 32>(qi, P.m, smem_base);
+    else nsq::quantise_to_smem<NS_COMP_INT8_S8, NC * 32>(qi, P.m, smem_base);
   } else {
     const uint4* src = reinterpret_cast<const uint4*>(P.act);
     uint4* dstv = reinterpret_cast<uint4*>(smem);
     const int nvec = P.act_bytes >> 4;
-    for (int i = threadIdx.x; i < nvec; i += kConsumers * 32) dstv[i] = src[i];
+    for (int i = threadIdx.x; i < nvec; i += NC * 32) dstv[i] = src[i];
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(kConsumers * 32) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(NC * 32) : "memory");
   const uint32_t meta_s = smem_base + P.meta_off;
   const int nchunks = P.kpad >> 5;
 
@@ -384,7 +391,7 @@ struct RingPlan {
 // is the number of consumer warps per SM that own a stage; pairs share the activation loads between two rows (measured:
 // K = 11008 with 7 pair stages beats 14 single-row stages, 950 vs 937 tok/s), so single rows are only taken when pairs would
 // leave consumer warps without a stage (K >= ~14000).  Ties go to the deeper ring.
-static RingPlan plan_ring(const GemvParams& P, size_t act_region) {
+static RingPlan plan_ring(const GemvParams& P, size_t act_region, bool wide) {
   static const int env_budget = getenv("NS_RING_BUDGET_KB") ? atoi(getenv("NS_RING_BUDGET_KB")) : 0;  // tuning aids
   static const int env_rows = getenv("NS_RING_ROWS") ? atoi(getenv("NS_RING_ROWS")) : 0;
   const size_t budgets[2] = {(size_t)(env_budget > 0 ? env_budget : 113) * 1024, 200 * 1024};
@@ -394,10 +401,12 @@ static RingPlan plan_ring(const GemvParams& P, size_t act_region) {
     if (env_rows && rows != env_rows && !(env_rows == 1 && P.mode == NS_GEMV_GATE_UP_SILU)) continue;
     const int stage_bytes = rows * P.pitch;
     for (int i = 0; i < 2; ++i) {
+      if (wide && i == 0) continue;  // the 14-consumer-warp kernel owns the SM
+      const int kc = (wide && i == 1) ? 2 * kConsumers : kConsumers;
       int raw = 0;
       if (budgets[i] > act_region + 64) raw = (int)((budgets[i] - act_region - 64) / (stage_bytes + 16));
-      if (raw > 32) raw = 32;
-      const int ac = raw < kConsumers ? raw : kConsumers;
+      if (raw > (wide ? 56 : 32)) raw = wide ? 56 : 32;
+      const int ac = raw < kc ? raw : kc;
       if (ac < 1) continue;
       const int st = raw - raw % ac;  // one consumer warp per stage residue class (see kernel)
       const int ctas = i == 0 ? 2 : 1;
@@ -408,9 +417,10 @@ static RingPlan plan_ring(const GemvParams& P, size_t act_region) {
   return best;
 }
 
-template <int AMODE, int M, bool ASYM, int STYPE, int ROWS, bool NORM>
+template <int AMODE, int M, bool ASYM, int STYPE, int ROWS, bool NORM, int NC = kConsumers>
 int launch_rows(const GemvParams& P, const RingPlan& plan, size_t act_region, int act_row, int red_off, cudaStream_t st) {
-  auto kern = gemv_ring_kernel<AMODE, M, ASYM, STYPE, ROWS, NORM>;
+  auto kern = gemv_ring_kernel<AMODE, M, ASYM, STYPE, ROWS, NORM, NC>;
+  constexpr int threads = (NC + (NC > kConsumers ? 2 : 1)) * 32;
   static bool attr_set = false;
   if (!attr_set) {
     NS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -441,7 +451,7 @@ int launch_rows(const GemvParams& P, const RingPlan& plan, size_t act_region, in
   if (dbg)
     fprintf(stderr, "gemv_ring: k=%d pitch=%d rows/stage=%d stages=%d active=%d smem=%zu ctas/sm=%d\n", P.k, P.pitch, ROWS, plan.stages,
             plan.active, smem, ctas_per_sm);
-  NS_CUDA_TRY(ns_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, st, P, R));
+  NS_CUDA_TRY(ns_launch_pdl(kern, dim3(grid), dim3(threads), smem, st, P, R));
   ns_count_launch();
   return NS_OK;
 }
@@ -450,9 +460,25 @@ template <int AMODE, int M, bool ASYM, int STYPE>
 int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
   const int act_row = (int)ns_round_up((size_t)P.kpad, 1024);
   const size_t img_end = (size_t)mt * act_row + (size_t)mt * P.meta_stride * 8;
-  const int red_off = (int)ns_round_up(img_end, 16);  // 8 floats of reduction scratch behind the image when a norm is fused
-  const size_t act_region = ns_round_up(P.norm_w ? (size_t)red_off + 32 : img_end, 128);
-  const RingPlan plan = plan_ring(P, act_region);
+  const int red_off = (int)ns_round_up(img_end, 16);  // one float per consumer warp (<= 14) of reduction scratch behind the image
+  const size_t act_region = ns_round_up(P.norm_w ? (size_t)red_off + 64 : img_end, 128);
+  // NS_RING_WIDE=1: single-row launches on the one-CTA-per-SM kernel with 14 consumer warps (experiment, see the kernel comment)
+  static const bool env_wide = getenv("NS_RING_WIDE") != nullptr && atoi(getenv("NS_RING_WIDE")) != 0;
+  if constexpr (M == 1) {
+    if (env_wide) {
+      const RingPlan wp = plan_ring(P, act_region, true);
+      if (wp.stages >= 2 && wp.stages % 2 == 0 && wp.active >= 2) {
+        const bool nrm = (P.norm_w || P.one_image) && P.act_f32;
+        if (P.norm_w && !P.act_f32) return NS_E_INVALID;
+        if (wp.rows == 2)
+          return nrm ? launch_rows<AMODE, 1, ASYM, STYPE, 2, true, 2 * kConsumers>(P, wp, act_region, act_row, red_off, st)
+                     : launch_rows<AMODE, 1, ASYM, STYPE, 2, false, 2 * kConsumers>(P, wp, act_region, act_row, red_off, st);
+        return nrm ? launch_rows<AMODE, 1, ASYM, STYPE, 1, true, 2 * kConsumers>(P, wp, act_region, act_row, red_off, st)
+                   : launch_rows<AMODE, 1, ASYM, STYPE, 1, false, 2 * kConsumers>(P, wp, act_region, act_row, red_off, st);
+      }
+    }
+  }
+  const RingPlan plan = plan_ring(P, act_region, false);
   if (plan.stages < 1) {
     ns_set_error("gemv_ring: row pitch %d too large for shared memory", P.pitch);
     return NS_E_UNSUPPORTED;
