@@ -462,10 +462,12 @@ int launch_one(const GemvParams& P, int mt, cudaStream_t st) {
   const size_t img_end = (size_t)mt * act_row + (size_t)mt * P.meta_stride * 8;
   const int red_off = (int)ns_round_up(img_end, 16);  // one float per consumer warp (<= 14) of reduction scratch behind the image
   const size_t act_region = ns_round_up(P.norm_w ? (size_t)red_off + 64 : img_end, 128);
-  // NS_RING_WIDE=1: single-row launches on the one-CTA-per-SM kernel with 14 consumer warps (experiment, see the kernel comment)
-  static const bool env_wide = getenv("NS_RING_WIDE") != nullptr && atoi(getenv("NS_RING_WIDE")) != 0;
+  // Single-row launches that quantise their activations themselves run on the one-CTA-per-SM kernel with 14 consumer warps
+  // (measured: 947 -> 1000 tok/s on the matmul-only token, 776 -> 849 on the whole eval step; on PRE-quantised images the two-CTA
+  // kernel stays ahead, 66 % against 62 %).  NS_RING_WIDE=0 / 1 forces the choice.
+  static const int env_wide = getenv("NS_RING_WIDE") ? atoi(getenv("NS_RING_WIDE")) : -1;
   if constexpr (M == 1) {
-    if (env_wide) {
+    if (env_wide == 1 || (env_wide < 0 && P.act_f32 != nullptr)) {
       const RingPlan wp = plan_ring(P, act_region, true);
       if (wp.stages >= 2 && wp.stages % 2 == 0 && wp.active >= 2) {
         const bool nrm = (P.norm_w || P.one_image) && P.act_f32;
