@@ -16,17 +16,17 @@ __global__ void __launch_bounds__(256) move_rows_kernel(const float* __restrict_
                                                         float* __restrict__ dst, int ld_dst, int cols) {
   pdl_launch_dependents();
   pdl_wait();
-  const int i = blockIdx.y;
+  const int i = blockIdx.x;  // row (grid.x: up to 2^31 - 1 rows)
   const int t = idx[i];
   const float* s = src + (size_t)(GATHER ? t : i) * ld_src;
   float* d = dst + (size_t)(GATHER ? i : t) * ld_dst;
   const bool v4 = !(cols & 3) && !(ld_src & 3) && !(ld_dst & 3) && !((size_t)src & 15) && !((size_t)dst & 15);
   if (v4) {
     const int c4 = cols >> 2;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < c4; c += gridDim.x * blockDim.x)
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < c4; c += gridDim.y * blockDim.x)
       reinterpret_cast<float4*>(d)[c] = reinterpret_cast<const float4*>(s)[c];
   } else {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) d[c] = s[c];
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < cols; c += gridDim.y * blockDim.x) d[c] = s[c];
   }
 }
 
@@ -38,7 +38,7 @@ int ns_launch_move_rows(bool gather, const float* src, int ld_src, const int* id
   int bx = (cols / 4 + 255) / 256;
   if (bx < 1) bx = 1;
   if (bx > 8) bx = 8;
-  const dim3 grid((unsigned)bx, (unsigned)rows);
+  const dim3 grid((unsigned)rows, (unsigned)bx);
   if (gather) NS_CUDA_TRY(ns_launch_pdl(move_rows_kernel<true>, grid, dim3(256), 0, st, src, ld_src, idx_dev, dst, ld_dst, cols));
   else NS_CUDA_TRY(ns_launch_pdl(move_rows_kernel<false>, grid, dim3(256), 0, st, src, ld_src, idx_dev, dst, ld_dst, cols));
   ns_count_launch();
