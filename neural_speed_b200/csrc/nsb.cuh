@@ -163,6 +163,8 @@ struct GemvParams {
                   // a token share ONE code image (two alternating images cost ~40 us per token in instruction-cache misses, measured)
 };
 int ns_launch_gemv_ring(const GemvParams& P, int amode, bool asym, int mt, cudaStream_t st);  // gemv_ring.cu
+int ns_launch_gemv_ring_wide(const GemvParams& P, int amode, bool asym, size_t act_region, int act_row, int red_off, cudaStream_t st,
+                             bool* taken);  // gemv_ring_wide.cu
 
 template <typename... Args>
 static inline cudaError_t ns_launch_pdl(void (*kern)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
