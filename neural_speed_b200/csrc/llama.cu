@@ -1128,6 +1128,9 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
       fast_attr = fast_smem;
     }
   }
+  // debugging aids, read per eval (not per process) so that a test can compare kernels on one engine
+  const bool old_decode = getenv("NS_ATTN_OLD_DECODE") != nullptr;  // decode attention: one CTA per head, dependent row loads
+  const bool scalar_attn = getenv("NS_ATTN_SCALAR") != nullptr;    // prompt attention: one CTA per (head, token), no tensor cores
   for (int il = 0; il < hp.n_layer; ++il) {
     const Layer& L = c->layers[il];
     __half* kc = c->kc + (size_t)il * hp.n_head_kv * hp.n_ctx * hd;
@@ -1160,7 +1163,7 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
     static const int dbg_skip = getenv("NS_LLAMA_DEBUG_SKIP") ? atoi(getenv("NS_LLAMA_DEBUG_SKIP")) : 0;  // timing experiments only
     if (m == 1 && (dbg_skip & 1)) {
       // (results are wrong: the attention launch is left out to measure what it costs inside the token's graph)
-    } else if (fast && m == 1 && c->attn_nsplit <= 1024 && !getenv("NS_ATTN_OLD_DECODE")) {
+    } else if (fast && m == 1 && c->attn_nsplit <= 1024 && !old_decode) {
       // rope + KV append + attention in one launch, K / V staged by TMA, the context split over CTAs
       const size_t dsm = hd == 128 ? attn_decode_smem<128>() : attn_decode_smem<64>();
       if (!c->dec_attr) {
@@ -1185,7 +1188,7 @@ static int enqueue_forward(ns_llama* c, int m, bool from_state, int advance, int
                                 hp.n_ctx, theta_scale, freq_scale));
       ns_count_launch();
       // prompts: causal attention on the tensor cores (64 query rows per CTA); a handful of rows stay on the decode-shaped kernel
-      const bool mma = fast && m >= 8 && !(E % 2) && !getenv("NS_ATTN_SCALAR");
+      const bool mma = fast && m >= 8 && !(E % 2) && !scalar_attn;
       if (mma) {
         auto kern = hd == 128 ? attn_mma_kernel<128> : attn_mma_kernel<64>;
         NS_CUDA_TRY(ns_launch_pdl(kern, dim3((unsigned)((m + kAttnMmaRows - 1) / kAttnMmaRows), (unsigned)hp.n_head), dim3(128), 0, st,
