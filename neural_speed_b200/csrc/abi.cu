@@ -780,6 +780,13 @@ static int ffn_impl(const ns_weight* w1, const ns_weight* w2, const ns_weight* w
     if (w3) {
       float* up = tmp + (size_t)m * fmid;
       if (int rc = ns_launch_gemm_tc(w3, ws, up, fmid, m, nullptr, 0, nullptr, st)) return rc;
+      // one_image (the eval step: nobody reads tmp): the product goes straight into the down projection's bf16 image (the
+      // activation image of gate/up in `ws` is dead once both GEMMs have been issued -- stream order)
+      int frc = NS_OK;
+      if (one_image && ns_launch_silu_mul_bf16(w2, gate, up, m, ws, st, eltop, &frc)) {
+        if (frc) return frc;
+        return ns_launch_gemm_tc(w2, ws, dst, ldo, m, b2, bcast, residual, st);
+      }
       if (int rc = ns_launch_silu_mul(gate, up, gate, nullptr, (size_t)m * fmid, st, eltop)) return rc;
     } else {
       if (int rc = ns_launch_gelu(gate, (size_t)m * fmid, st)) return rc;

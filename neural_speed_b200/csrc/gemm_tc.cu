@@ -505,6 +505,43 @@ __global__ void __launch_bounds__(256) silu_mul_kernel(const float* __restrict__
     }
   }
 }
+// silu(gate) * up written straight into the bf16 activation image of the down projection: the fp32 product (m x fmid, 90 MB at 2048
+// tokens of Llama-2-7B) is neither stored nor read back.  Same values as silu_mul_kernel followed by act_to_bf16_v8_kernel (the product
+// is formed in fp32 and rounded once).  Used when the caller does not look at the intermediate (the eval step).
+__global__ void __launch_bounds__(256) silu_mul_bf16_kernel(const float* __restrict__ g, const float* __restrict__ u, size_t total8,
+                                                            __nv_bfloat16* __restrict__ out, int eltop) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total8; idx += (size_t)gridDim.x * blockDim.x) {
+    const float4 x0 = ((const float4*)g)[2 * idx], x1 = ((const float4*)g)[2 * idx + 1];
+    const float4 y0 = ((const float4*)u)[2 * idx], y1 = ((const float4*)u)[2 * idx + 1];
+    const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    const float ys[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    float p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = (eltop == NS_ELT_GELU ? ns_gelu(xs[i]) : ns_silu(xs[i])) * ys[i];
+    __nv_bfloat162 q0 = __floats2bfloat162_rn(p[0], p[1]), q1 = __floats2bfloat162_rn(p[2], p[3]);
+    __nv_bfloat162 q2 = __floats2bfloat162_rn(p[4], p[5]), q3 = __floats2bfloat162_rn(p[6], p[7]);
+    uint4 o;
+    o.x = *(uint32_t*)&q0, o.y = *(uint32_t*)&q1, o.z = *(uint32_t*)&q2, o.w = *(uint32_t*)&q3;
+    ((uint4*)out)[idx] = o;
+  }
+}
+// g, u: [m][w2->k] fp32 contiguous.  false: the layout needs the general conversion kernel (act-order gather, padded K) -- the caller
+// takes the two-step path
+bool ns_launch_silu_mul_bf16(const ns_weight* w2, const float* g, const float* u, int m, void* ws, cudaStream_t st, int eltop, int* rc) {
+  if (w2->shuffle || w2->k != w2->kpad || (w2->k & 7) || (((uintptr_t)g | (uintptr_t)u | (uintptr_t)ws) & 15)) return false;
+  const size_t total8 = (size_t)m * (w2->k >> 3);
+  size_t blocks = (total8 + 255) / 256;
+  if (blocks > (size_t)ns_num_sms() * 16) blocks = (size_t)ns_num_sms() * 16;
+  if (blocks < 1) blocks = 1;
+  *rc = ns_cuda_ok(ns_launch_pdl(silu_mul_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, st, g, u, total8, (__nv_bfloat16*)ws, eltop),
+                   "silu_mul_bf16_kernel")
+            ? NS_OK
+            : NS_E_CUDA;
+  ns_count_launch();
+  return true;
+}
 int ns_launch_silu_mul(const float* g, const float* u, float* out, float* aux, size_t total, cudaStream_t st, int eltop) {
   const bool v4 = (total & 3) == 0 && (((uintptr_t)g | (uintptr_t)u | (uintptr_t)out | (uintptr_t)aux) & 15) == 0;
   const size_t n = v4 ? total >> 2 : total;

@@ -121,6 +121,7 @@ int ns_launch_gemm_tc(const ns_weight* w, const void* ws, float* dst, int ldo, i
                       const float* residual, cudaStream_t st);
 int ns_launch_silu_mul(const float* g, const float* u, float* out, float* aux, size_t total, cudaStream_t st, int eltop = 0);
 int ns_launch_gelu(float* x, size_t total, cudaStream_t st);
+bool ns_launch_silu_mul_bf16(const ns_weight* w2, const float* g, const float* u, int m, void* ws, cudaStream_t st, int eltop, int* rc);
 
 // integer tensor-core path for 5..32 activation rows (gemm_imma.cu); modes and epilogue arguments as ns_launch_gemv
 bool ns_gemm_imma_supported(const ns_weight* const* ws, int nw, int m);
