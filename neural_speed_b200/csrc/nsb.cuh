@@ -161,7 +161,7 @@ struct GemvParams {
   const float* norm_w;  // fused ne_rms_norm + ne_mul in front of the activation quantiser (llama.cpp:205-210), or NULL
   float norm_eps;
   int one_image;  // decode engine: run this node on the norm-capable kernel image even without a norm, so that ALL the GEMV nodes of
-                  // a token share ONE code image (two alternating images cost ~40 us per token in instruction-cache misses, measured)
+                  // a token share ONE code image (two alternating images cost ~70 us per token in instruction fetch, measured: 736 -> 776 tok/s)
 };
 int ns_launch_gemv_ring(const GemvParams& P, int amode, bool asym, int mt, cudaStream_t st);  // gemv_ring.cu
 int ns_launch_gemv_ring_wide(const GemvParams& P, int amode, bool asym, size_t act_region, int act_row, int red_off, cudaStream_t st,
