@@ -15,7 +15,10 @@ int wide_launch(const GemvParams& P, size_t act_region, int act_row, int red_off
   // two producer warps on alternate stages need an even ring; a ring too short for two consumer warps is not worth the SM
   if (!(wp.stages >= 2 && wp.stages % 2 == 0 && wp.active >= 2)) return NS_OK;
   *taken = true;
-  if (P.norm_w && !P.act_f32) return NS_E_INVALID;
+  if (P.norm_w && !P.act_f32) {
+    ns_set_error("gemv_ring: fused RMSNorm needs fp32 activations");
+    return NS_E_INVALID;
+  }
   const bool nrm = (P.norm_w || P.one_image) && P.act_f32;
   constexpr int NC = 2 * kConsumers;
   if (wp.rows == 2)
