@@ -794,11 +794,11 @@ def run_ours(args):
                          # committed ncu launch list of this same command (profiles/r02_launches_bench.csv); null when that
                          # file is absent or the workload differs (other formats / layer counts)
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "gemv_ring_kernel<S8,M=1,sym,f16> (fused Q8_0 activation quantisation)",
+                         "kernel": "gemv_ring_kernel<S8,M=1,sym,f16,NC=14> (one CTA per SM: 14 consumer + 2 producer warps, fused Q8_0 activation quantisation)",
                          "launches_per_step": launches_per_step, "avg_launch_us": ms_step * 1e3 / max(1, launches_per_step),
                          "peak_source": peak_kind, "algorithmic_bytes_per_launch": int(alg_bytes // max(1, launches_per_step)),
                          "note": "the timed region contains only this kernel (129 launches per token, one CUDA graph, PDL)",
-                         "per_op_gemv_only": {"kernel": "gemv_ring_kernel<S8,M=1,sym,f16>", "achieved": gemv_gbs,
+                         "per_op_gemv_only": {"kernel": "gemv_ring_kernel<S8,M=1,sym,f16,NC=7> (two CTAs per SM, pre-quantised activation image)", "achieved": gemv_gbs,
                                               "frac": gemv_gbs / hbm_peak, "avg_launch_us": ms_gemv * 1e3 / n_gemv,
                                               "launches": n_gemv}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
