@@ -243,6 +243,10 @@ NS_API int ns_mul_mat_id(const ns_weight* const* experts, int n_as, const int32_
 NS_API int ns_ffn_id(const ns_weight* const* gate, const ns_weight* const* down, const ns_weight* const* up, int n_as, int gelu,
                      const int32_t* ids, int ids_stride, int id, int ids_on_device, const float* act, int lda, float* tmp, float* dst,
                      int ldo, int m, void* queue);
+/* the host-side grouping ns_mul_mat_id / ns_ffn_id perform, on its own (no device): order[m] = token indices sorted stably by expert
+ * (the matrix_rows lists of ne_layers.c:7440-7449, flattened), span[2 * n_as] = per expert [begin, end) inside order.  Returns 1 when
+ * the tokens already lie grouped (no gather / scatter needed), 0 otherwise, NS_E_INVALID on an expert id outside [0, n_as). */
+NS_API int ns_moe_plan(const int32_t* ids, int ids_stride, int id, int m, int n_as, int* order, int* span);
 NS_API int ns_mul_mat_id_q4_0_f32_host(const void* const* expert_rows, int n_as, size_t nb01, const int32_t* ids, int ids_stride,
                                        int id, const float* src1, float* dst, int ne00, int ne01, int ne11);
 

@@ -900,6 +900,20 @@ static int plan_experts(const int32_t* ids, int ids_stride, int id, int ids_on_d
   return NS_OK;
 }
 
+// The host-side grouping on its own (no device needed): order[m] = token indices sorted stably by expert, span[2 * n_as] = per
+// expert [begin, end) inside order.  Returns 1 when order is the identity (rows already grouped), 0 otherwise, < 0 on bad ids.
+extern "C" int ns_moe_plan(const int32_t* ids, int ids_stride, int id, int m, int n_as, int* order, int* span) {
+  ExpertPlan pl;
+  if (int rc = plan_experts(ids, ids_stride, id, 0, m, n_as, nullptr, &pl)) return rc;
+  if (order) memcpy(order, pl.order.data(), (size_t)m * sizeof(int));
+  if (span)
+    for (int e = 0; e < n_as; ++e) {
+      span[2 * e] = pl.span[(size_t)e].first;
+      span[2 * e + 1] = pl.span[(size_t)e].second;
+    }
+  return pl.identity ? 1 : 0;
+}
+
 // scratch of a grouped node: [order: m int][xg: m x k][yg: m x n][workspace of the matmuls]
 struct ExpertScratch {
   int* order;

@@ -34,3 +34,34 @@ def test_restatement_matches_the_reference_engine(n_threads):
         want = oracle.ref_mul_mat_id(L, rows, oracle.NE_TYPE_Q4_0, n, k, ids, slot, a, n_threads=n_threads)
         got = oracle.mul_mat_id_q4_0_f32(rows, ids, slot, a)
         assert np.array_equal(got, want)
+
+
+def test_host_side_grouping_of_tokens_by_expert():
+    """ns_moe_plan: the grouping ns_mul_mat_id performs before it launches anything (matrix_rows / matrix_row_counts of
+    ne_layers.c:7440-7449): stable sort by expert, spans, the already-grouped shortcut, the reference's id range assertion."""
+    import ctypes as C
+
+    import neural_speed_b200 as ns
+    L = ns.lib()
+    rng = np.random.default_rng(2)
+    m, n_as, n_used = 37, 6, 2
+    ids = rng.integers(0, n_as, (m, n_used)).astype(np.int32)
+    ids[:, 1][ids[:, 1] == 4] = 0  # an expert nobody picks
+    order = np.zeros(m, np.int32)
+    span = np.zeros(2 * n_as, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for slot in range(n_used):
+        rc = L.ns_moe_plan(p(ids), n_used, slot, m, n_as, p(order), p(span))
+        assert rc == 0
+        want = np.argsort(ids[:, slot], kind="stable")
+        assert np.array_equal(order, want)
+        counts = np.bincount(ids[:, slot], minlength=n_as)
+        assert np.array_equal(span[1::2] - span[0::2], counts)
+        assert span[0] == 0 and np.array_equal(span[2::2], span[1:-1:2])  # contiguous spans
+    grouped = np.sort(ids[:, :1], axis=0)
+    assert L.ns_moe_plan(p(np.ascontiguousarray(grouped)), 1, 0, m, n_as, p(order), p(span)) == 1
+    assert np.array_equal(order, np.arange(m))
+    bad = ids.copy()
+    bad[5, 0] = n_as
+    assert L.ns_moe_plan(p(bad), n_used, 0, m, n_as, p(order), p(span)) < 0 and "expert id" in ns.last_error()
+    assert L.ns_moe_plan(p(ids), n_used, 2, m, n_as, p(order), p(span)) < 0  # slot outside the selection
